@@ -1,0 +1,163 @@
+/*
+ * vision_b200.h — C ABI of libvision_b200.so (sm_100a CUDA kernels for the
+ * torchvision custom-op hot path).  No torch types cross this boundary: plain
+ * device pointers, sizes and a CUDA stream handle.  Every entry point names
+ * the reference interface it replaces (paths relative to pytorch/vision).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - tensors are dense, row-major ("contiguous") NCHW exactly as the
+ *     reference kernels receive them after `.contiguous()`;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and
+ *     the call returns without synchronising unless documented otherwise;
+ *   - return value: 0 on success, otherwise a negative VB200_E* code or a
+ *     positive cudaError_t; vb200_last_error() gives a thread-local message
+ *     (the torch shim turns it into the RuntimeError the reference raises).
+ */
+#ifndef VISION_B200_H_
+#define VISION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VB200_API __attribute__((visibility("default")))
+#else
+#define VB200_API
+#endif
+
+typedef enum {
+  VB200_F32 = 0,
+  VB200_F16 = 1,
+  VB200_BF16 = 2,
+  VB200_F64 = 3,
+  VB200_U8 = 4
+} vb200_dtype;
+
+enum {
+  VB200_OK = 0,
+  VB200_EINVAL = -1,      /* bad argument (shape / dtype / alignment) */
+  VB200_EUNSUPPORTED = -2,/* valid request this build does not implement */
+  VB200_EWORKSPACE = -3   /* workspace too small */
+};
+
+/* NMS IoU arithmetic selector.  VB200_NMS_CUDA reproduces the compiled
+ * reference CUDA kernel (csrc/ops/cuda/nms_kernel.cu:42-54: Sb's product is
+ * FMA-contracted into Sa+Sb, threshold narrowed to float); VB200_NMS_CPU
+ * reproduces csrc/ops/cpu/nms_kernel.cpp:58,78-88 (separately rounded areas,
+ * comparison against the double threshold). */
+enum { VB200_NMS_CPU = 0, VB200_NMS_CUDA = 1 };
+
+/* batched_nms strategy (torchvision/ops/boxes.py:86-89). AUTO applies the
+ * reference's own switch for CUDA tensors (numel > 100_000 -> VANILLA). */
+enum { VB200_BNMS_AUTO = 0, VB200_BNMS_VANILLA = 1, VB200_BNMS_TRICK = 2 };
+
+enum { VB200_RESIZE_BILINEAR = 0, VB200_RESIZE_BICUBIC = 1 };
+
+typedef void* vb200_stream; /* cudaStream_t */
+
+VB200_API int vb200_abi_version(void);
+VB200_API const char* vb200_last_error(void);
+/* Number of kernel launches issued by this library in this process (all
+ * threads); bench.py reports the delta over the timed region. */
+VB200_API uint64_t vb200_launch_count(void);
+
+/* ---- roi_align ---------------------------------------------------------
+ * Replaces roi_align_forward_kernel, csrc/ops/cuda/roi_align_kernel.cu:334-394
+ * (schema torchvision::roi_align, csrc/ops/roi_align.cpp:74-75).
+ * input [batch, channels, height, width], rois [num_rois, 5] (same dtype),
+ * output [num_rois, channels, pooled_h, pooled_w] — written in full, no
+ * pre-zeroing needed.  dtype: F32, F16, F64.
+ * workspace: vb200_roi_align_workspace_bytes() bytes of device scratch (the
+ * per-RoI sampling geometry of the plane-resident path; 0 when not needed). */
+VB200_API size_t vb200_roi_align_workspace_bytes(int dtype, int batch, int channels, int height, int width,
+                                       int num_rois, int pooled_h, int pooled_w,
+                                       int sampling_ratio);
+VB200_API int vb200_roi_align_forward(const void* input, const void* rois, void* output, int dtype,
+                            int batch, int channels, int height, int width, int num_rois,
+                            int pooled_h, int pooled_w, double spatial_scale,
+                            int sampling_ratio, int aligned, void* workspace,
+                            size_t workspace_bytes, vb200_stream stream);
+
+/* ---- roi_pool ----------------------------------------------------------
+ * Replaces roi_pool_forward_kernel, csrc/ops/cuda/roi_pool_kernel.cu:127-188
+ * (schema torchvision::roi_pool, csrc/ops/roi_pool.cpp:67-68).
+ * argmax [num_rois, channels, pooled_h, pooled_w] int32. */
+VB200_API int vb200_roi_pool_forward(const void* input, const void* rois, void* output, int32_t* argmax,
+                           int dtype, int batch, int channels, int height, int width,
+                           int num_rois, int pooled_h, int pooled_w, double spatial_scale,
+                           vb200_stream stream);
+
+/* ---- ps_roi_align ------------------------------------------------------
+ * Replaces ps_roi_align_forward_kernel, csrc/ops/cuda/ps_roi_align_kernel.cu:319-389
+ * (schema torchvision::ps_roi_align, csrc/ops/ps_roi_align.cpp:74-75).
+ * channels must be a multiple of pooled_h*pooled_w; output and
+ * channel_mapping are [num_rois, channels/(pooled_h*pooled_w), pooled_h, pooled_w]. */
+VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, void* output,
+                               int32_t* channel_mapping, int dtype, int batch, int channels,
+                               int height, int width, int num_rois, int pooled_h, int pooled_w,
+                               double spatial_scale, int sampling_ratio, vb200_stream stream);
+
+/* ---- nms ---------------------------------------------------------------
+ * Replaces nms_kernel, csrc/ops/cuda/nms_kernel.cu:166-258 (schema
+ * torchvision::nms, csrc/ops/nms.cpp:27).  boxes [n,4] (x1,y1,x2,y2), scores [n].
+ * Writes the kept ORIGINAL indices, in descending-score order (stable), to
+ * keep_out[0..*num_keep_out) — both device memory, keep_out sized n.  The
+ * caller reads *num_keep_out (the reference's masked_select sync).
+ * dtype: F32 (F16 inputs are widened by the caller, as autocast does). */
+VB200_API size_t vb200_nms_workspace_bytes(int64_t n);
+VB200_API int vb200_nms(const void* boxes, const void* scores, int dtype, int64_t n, double iou_threshold,
+              int semantics, void* workspace, size_t workspace_bytes, int64_t* keep_out,
+              int64_t* num_keep_out, vb200_stream stream);
+
+/* ---- batched_nms -------------------------------------------------------
+ * Replaces the Python torchvision.ops.boxes.batched_nms (boxes.py:57-126):
+ * one fused device pipeline instead of a per-class Python loop.  idxs [n] int64.
+ * Output as vb200_nms.  strategy: VB200_BNMS_*. */
+VB200_API size_t vb200_batched_nms_workspace_bytes(int64_t n);
+VB200_API int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
+                      int64_t n, double iou_threshold, int semantics, int strategy,
+                      void* workspace, size_t workspace_bytes, int64_t* keep_out,
+                      int64_t* num_keep_out, vb200_stream stream);
+
+/* ---- deform_conv2d -----------------------------------------------------
+ * Replaces deform_conv2d_forward_kernel, csrc/ops/cuda/deform_conv2d_kernel.cu:1035-1255
+ * (schema torchvision::deform_conv2d, csrc/ops/deform_conv2d.cpp:101-102).
+ * input [batch,c_in,in_h,in_w], weight [c_out,c_in/groups,kh,kw],
+ * offset [batch, offset_groups*2*kh*kw, out_h, out_w],
+ * mask [batch, offset_groups*kh*kw, out_h, out_w] (ignored if !use_mask),
+ * bias [c_out] (may be NULL), out [batch,c_out,out_h,out_w].
+ * dtype: F32 (SIMT path), BF16/F16 (tcgen05 tensor-core path, fp32 accumulate).
+ * workspace: vb200_deform_conv2d_workspace_bytes() bytes (may be 0). */
+VB200_API size_t vb200_deform_conv2d_workspace_bytes(int dtype, int batch, int c_in, int in_h, int in_w,
+                                           int c_out, int kh, int kw, int out_h, int out_w,
+                                           int groups, int offset_groups);
+VB200_API int vb200_deform_conv2d_forward(const void* input, const void* weight, const void* offset,
+                                const void* mask, const void* bias, void* out, int dtype,
+                                int batch, int c_in, int in_h, int in_w, int c_out, int kh,
+                                int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                                int dil_h, int dil_w, int groups, int offset_groups,
+                                int use_mask, void* workspace, size_t workspace_bytes,
+                                vb200_stream stream);
+
+/* ---- resize ------------------------------------------------------------
+ * Replaces the interpolate path of resize_image,
+ * torchvision/transforms/v2/functional/_geometry.py:340-360 (cast to fp32 ->
+ * aten::upsample_bi{linear,cubic}2d[_aa] -> cast back) with ONE fused kernel:
+ * reads `dtype`, computes in fp32, writes `dtype` (round-to-nearest-even for
+ * floats; clamp(0,255)+round for U8 as _geometry.py:352-359).
+ * input [planes, in_h, in_w] -> output [planes, out_h, out_w]; mode VB200_RESIZE_*;
+ * align_corners=False semantics.  dtype: F32, F16, BF16, U8. */
+VB200_API int vb200_resize(const void* input, void* output, int dtype, int64_t planes, int in_h, int in_w,
+                 int out_h, int out_w, int mode, int antialias, vb200_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISION_B200_H_ */

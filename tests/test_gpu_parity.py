@@ -1,0 +1,491 @@
+"""GPU suite (-m gpu): the CUDA kernels, called through the C ABI (via the torch shim, and once
+directly through ctypes), against (a) the committed golden vectors of the reference CPU kernels,
+(b) the CPU oracle on seeded inputs — at BASELINE.json sizes where the oracle finishes in seconds,
+(c) size-independent properties, (d) the reference's CUDA kernels on the same box when the
+torchvision wheel is importable (an extra; never required).
+
+Tolerances (BASELINE.json north_star): bit-exact kept indices for nms / batched_nms; 1e-5 for fp32
+roi_align / roi_pool / ps_roi_align / resize / deform_conv2d; 1e-2 for 16-bit storage types."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = dict(rtol=1e-5, atol=1e-5)
+F16_TOL = dict(rtol=1e-2, atol=1e-2)
+DEV = "cuda"
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return x if dtype is None else x.to(dtype)
+
+
+def npy(x):
+    return x.detach().float().cpu().numpy() if x.is_floating_point() else x.detach().cpu().numpy()
+
+
+class force_env:
+    def __init__(self, key, val):
+        self.key, self.val = key, val
+
+    def __enter__(self):
+        self.old = os.environ.get(self.key)
+        os.environ[self.key] = self.val
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop(self.key, None)
+        else:
+            os.environ[self.key] = self.old
+
+
+def test_native_library_loaded(vb):
+    """The process must have the in-tree .so mapped — no eager / library fallback."""
+    maps = open("/proc/self/maps").read()
+    assert "libvision_b200.so" in maps and "libvision_b200_torch.so" in maps
+    assert torch.ops.vision_b200._abi_version() == 1
+
+
+# =============================== roi_align ===================================
+@pytest.mark.parametrize("aligned", [0, 1])
+@pytest.mark.parametrize("sr", [2, -1])
+def test_roi_align_golden(vb, golden, aligned, sr):
+    x, rois = t(golden["roi_x"]), t(golden["roi_rois"])
+    want = golden[f"roi_align_a{aligned}_s{sr}"]
+    before = vb.launch_count()
+    got = vb.ops.roi_align(x, rois, (7, 5), 0.25, sr, bool(aligned))
+    assert vb.launch_count() > before, "no vision_b200 kernel was launched"
+    np.testing.assert_allclose(npy(got), want, **F32_TOL)
+    # the generic kernel restates the reference CPU arithmetic op for op: expect bit equality
+    assert np.array_equal(npy(got), want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
+@pytest.mark.parametrize("contiguous", [True, False])
+def test_roi_align_reference_test_shapes(vb, oracle, dtype, contiguous):
+    # test/test_ops.py:127-163 (RoIOpTester.test_forward): x = rand(2, 50, 10, 10), 4 fixed RoIs, pool 5x5
+    torch.manual_seed(0)
+    x = torch.rand(2, 50, 10, 10, dtype=dtype, device=DEV)
+    if not contiguous:
+        x = x.permute(0, 1, 3, 2)
+    rois = torch.tensor([[0, 0, 0, 9, 9], [0, 0, 5, 4, 9], [0, 5, 5, 9, 9], [1, 0, 0, 9, 9]], dtype=dtype, device=DEV)
+    for aligned in (False, True):
+        got = vb.ops.roi_align(x, rois, 5, spatial_scale=1, sampling_ratio=-1, aligned=aligned)
+        want = oracle.roi_align(npy(x), npy(rois), 5, 1.0, -1, aligned)
+        tol = F16_TOL if dtype == torch.float16 else F32_TOL
+        np.testing.assert_allclose(npy(got), want, **tol)
+        assert got.dtype == dtype and got.shape == (4, 50, 5, 5)
+
+
+@pytest.mark.parametrize("aligned", [False, True])
+def test_roi_align_cfg2_full_size_vs_oracle(vb, oracle, aligned):
+    """BASELINE configs[1] at full size: 1x256x200x272 fp32, 1000 RoIs, 7x7, sr=2 (plane-resident kernel)."""
+    from vision_b200 import workloads
+
+    x, rois, kw = workloads.cfg2_roi_align()
+    want = oracle.roi_align(x.numpy(), rois.numpy(), kw["output_size"], kw["spatial_scale"], kw["sampling_ratio"], aligned)
+    got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), kw["output_size"], kw["spatial_scale"], kw["sampling_ratio"], aligned)
+    np.testing.assert_allclose(npy(got), want, **F32_TOL)
+    with force_env("VB200_ROI_ALIGN_PATH", "generic"):
+        got_g = vb.ops.roi_align(x.to(DEV), rois.to(DEV), kw["output_size"], kw["spatial_scale"], kw["sampling_ratio"], aligned)
+    assert np.array_equal(npy(got_g), want)
+
+
+def test_roi_align_plane_path_batched_and_sampling_ratios(vb, oracle):
+    from vision_b200 import workloads
+
+    for sr in (1, 3, 4):
+        x, rois, kw = workloads.cfg2_roi_align(seed=sr, k=300, batch=3, channels=7, height=40, width=52)
+        with force_env("VB200_ROI_ALIGN_PATH", "plane"):
+            got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), (3, 6), 0.25, sr, True)
+        want = oracle.roi_align(x.numpy(), rois.numpy(), (3, 6), 0.25, sr, True)
+        np.testing.assert_allclose(npy(got), want, **F32_TOL)
+
+
+def test_roi_align_edge_cases(vb, oracle):
+    x = torch.randn(1, 3, 8, 8, device=DEV)
+    assert vb.ops.roi_align(x, torch.zeros(0, 5, device=DEV), 7).shape == (0, 3, 7, 7)
+    # list-of-boxes input, boxes hanging outside the map, huge adaptive grid (table overflow path)
+    boxes = [torch.tensor([[-20.0, -20.0, 30.0, 30.0], [2.0, 2.0, 2.0, 2.0]], device=DEV)]
+    got = vb.ops.roi_align(x, boxes, 2, 1.0, -1, False)
+    rois = np.array([[0, -20, -20, 30, 30], [0, 2, 2, 2, 2]], np.float32)
+    np.testing.assert_allclose(npy(got), oracle.roi_align(npy(x), rois, 2, 1.0, -1, False), **F32_TOL)
+    big = torch.randn(1, 2, 600, 600, device=DEV)
+    r = torch.tensor([[0, 0.0, 0.0, 599.0, 599.0]], device=DEV)
+    got = vb.ops.roi_align(big, r, 1, 1.0, -1, False)     # grid 599x599 > table capacity
+    np.testing.assert_allclose(npy(got), oracle.roi_align(npy(big), npy(r), 1, 1.0, -1, False), rtol=1e-4, atol=1e-4)
+    with pytest.raises(RuntimeError, match="Tensor\\[K, 5\\]"):
+        torch.ops.vision_b200.roi_align(x, torch.zeros(2, 4, device=DEV), 1.0, 2, 2, 2, False)
+    with pytest.raises(RuntimeError, match="same type"):
+        torch.ops.vision_b200.roi_align(x, torch.zeros(2, 5, device=DEV, dtype=torch.float64), 1.0, 2, 2, 2, False)
+
+
+# =============================== roi_pool / ps_roi_align =======================
+def test_roi_pool_golden_and_random(vb, oracle, golden):
+    out, arg = torch.ops.vision_b200.roi_pool(t(golden["roi_x"]), t(golden["roi_rois"]), 0.25, 7, 5)
+    assert np.array_equal(npy(out), golden["roi_pool_out"]) and np.array_equal(npy(arg), golden["roi_pool_argmax"])
+    from vision_b200 import workloads
+
+    x, rois, kw = workloads.cfg2_roi_align(channels=16, k=200)
+    o, a = torch.ops.vision_b200.roi_pool(x.to(DEV), rois.to(DEV), 0.25, 7, 7)
+    wo, wa = oracle.roi_pool(x.numpy(), rois.numpy(), 7, 0.25)
+    assert np.array_equal(npy(o), wo) and np.array_equal(npy(a), wa)            # bit-exact incl. argmax
+    xh = x.half().to(DEV)
+    oh = vb.ops.roi_pool(xh, rois.half().to(DEV), 7, 0.25)
+    wh, _ = oracle.roi_pool(xh.float().cpu().numpy(), rois.half().float().numpy(), 7, 0.25)
+    np.testing.assert_allclose(npy(oh), wh, **F16_TOL)
+    assert vb.ops.roi_pool(x.to(DEV), torch.zeros(0, 5, device=DEV), 3).shape == (0, 16, 3, 3)
+
+
+def test_ps_roi_align_golden_and_random(vb, oracle, golden):
+    for sr in (2, -1):
+        out, mp = torch.ops.vision_b200.ps_roi_align(t(golden["psroi_x"]), t(golden["roi_rois"]), 0.25, 7, 5, sr)
+        np.testing.assert_array_equal(npy(out), golden[f"psroi_s{sr}_out"])     # incl. NaN/inf of degenerate RoIs
+        assert np.array_equal(npy(mp), golden[f"psroi_s{sr}_map"])
+    torch.manual_seed(1)
+    x = torch.randn(2, 5 * 49, 30, 41)
+    rois = torch.tensor([[0, 4.0, 4.0, 100.0, 90.0], [1, 10.0, 20.0, 150.0, 110.0], [1, 0.0, 0.0, 163.0, 119.0]])
+    got = vb.ops.ps_roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2)
+    want, _ = oracle.ps_roi_align(x.numpy(), rois.numpy(), 7, 0.25, 2)
+    np.testing.assert_allclose(npy(got), want, **F32_TOL)
+    with pytest.raises(RuntimeError, match="multiple of pooling height"):
+        vb.ops.ps_roi_align(torch.randn(1, 50, 8, 8, device=DEV), rois[:1].to(DEV), 7, 1.0, 2)
+
+
+# =============================== nms ==========================================
+def _set(vb, which):
+    vb.set_nms_semantics(which)
+
+
+def test_nms_golden_cpu_semantics(vb, golden):
+    _set(vb, "cpu")
+    try:
+        for i in range(3):
+            keep = vb.ops.nms(t(golden[f"nms{i}_boxes"]), t(golden[f"nms{i}_scores"]), float(golden[f"nms{i}_thr"]))
+            assert keep.dtype == torch.int64 and np.array_equal(npy(keep), golden[f"nms{i}_keep"])
+        keep = vb.ops.nms(t(golden["cfg1_boxes"]), t(golden["cfg1_scores"]), 0.5)
+        assert np.array_equal(npy(keep), golden["cfg1_keep"])
+    finally:
+        _set(vb, "cuda")
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 129, 1000, 3072, 3073, 9000])
+@pytest.mark.parametrize("sem", ["cpu", "cuda"])
+def test_nms_vs_oracle_sizes(vb, oracle, n, sem):
+    """Covers the one-CTA segment kernel (n <= 3072) and the tiled mask + scan path (n > 3072)."""
+    rng = np.random.default_rng(n)
+    b = (rng.random((n, 4), dtype=np.float32) * 100)
+    b[:, 2:] = b[:, :2] + rng.random((n, 2), dtype=np.float32) * 30 + 0.5
+    s = rng.random(n, dtype=np.float32)
+    s[::7] = s[0]                                  # ties: stable order decides
+    _set(vb, sem)
+    try:
+        for thr in (0.3, 0.5, 0.7):
+            keep = vb.ops.nms(t(b), t(s), thr)
+            want = oracle.nms(b, s, thr, oracle.NMS_MODE_CPU if sem == "cpu" else oracle.NMS_MODE_CUDA)
+            assert np.array_equal(npy(keep), want), (n, sem, thr)
+    finally:
+        _set(vb, "cuda")
+
+
+def test_nms_threshold_narrowing_semantics(vb):
+    a = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 2]], dtype=torch.float32, device=DEV)   # iou == 0.2f exactly
+    sc = torch.tensor([1.0, 0.5], device=DEV)
+    _set(vb, "cpu")
+    assert vb.ops.nms(a, sc, 0.2).tolist() == [0]
+    _set(vb, "cuda")
+    assert vb.ops.nms(a, sc, 0.2).tolist() == [0, 1]
+
+
+def test_nms_edge_cases_and_errors(vb):
+    assert vb.ops.nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), 0.5).shape == (0,)
+    z = torch.ones(3, 4, device=DEV)                                    # zero-area boxes: NaN > thr is False
+    assert vb.ops.nms(z, torch.tensor([3.0, 2.0, 1.0], device=DEV), 0.5).tolist() == [0, 1, 2]
+    same = torch.tensor([[0, 0, 4, 4.0]] * 5, device=DEV)
+    assert vb.ops.nms(same, torch.ones(5, device=DEV), 0.5).tolist() == [0]
+    # test/test_ops.py:927-935
+    for bad in ((torch.rand(4, device=DEV), torch.rand(3, device=DEV)), (torch.rand(3, 5, device=DEV), torch.rand(3, device=DEV)),
+                (torch.rand(3, 4, device=DEV), torch.rand(3, 2, device=DEV)), (torch.rand(3, 4, device=DEV), torch.rand(4, device=DEV))):
+        with pytest.raises(RuntimeError):
+            vb.ops.nms(bad[0], bad[1], 0.5)
+    # fp16 literal boxes of test_nms_float16 (test/test_ops.py:1010-1017)
+    boxes = torch.tensor([[285.3538, 185.5758, 1193.5110, 851.4551], [285.1472, 188.7374, 1192.4984, 851.0669],
+                          [279.2440, 197.9812, 1189.4746, 849.2019]], device=DEV)
+    scores = torch.tensor([0.6370, 0.7569, 0.3966], device=DEV)
+    assert torch.equal(vb.ops.nms(boxes, scores, 0.2), vb.ops.nms(boxes.half(), scores.half(), 0.2))
+
+
+# =============================== batched_nms ===================================
+def test_batched_nms_golden(vb, golden):
+    _set(vb, "cpu")
+    try:
+        g = golden
+        keep = vb.ops.batched_nms(t(g["bnms_trick_boxes"]), t(g["bnms_trick_scores"]), t(g["bnms_trick_idxs"]), 0.5)
+        assert np.array_equal(npy(keep), g["bnms_trick_keep_t"])          # numel 2400 <= 100k on CUDA -> trick
+        keep = vb.ops.batched_nms(t(g["bnms_vanilla_boxes"]), t(g["bnms_vanilla_scores"]), t(g["bnms_vanilla_idxs"]), 0.5)
+        assert np.array_equal(npy(keep), g["bnms_vanilla_keep_t"])        # numel 12000 <= 100k on CUDA -> trick
+    finally:
+        _set(vb, "cuda")
+
+
+@pytest.mark.parametrize("clustered", [False, True])
+@pytest.mark.parametrize("sem", ["cpu", "cuda"])
+def test_batched_nms_cfg3_full_size_vs_oracle(vb, oracle, clustered, sem):
+    """BASELINE configs[2] at full size: 100k boxes x 80 classes (vanilla semantics, numel 400k > 100k)."""
+    from vision_b200 import workloads
+
+    b, s, i = workloads.cfg3_batched_nms(clustered=clustered)
+    mode = oracle.NMS_MODE_CPU if sem == "cpu" else oracle.NMS_MODE_CUDA
+    want = oracle.batched_nms(b.numpy(), s.numpy(), i.numpy(), 0.5, mode=mode, device_is_cuda=True)
+    _set(vb, sem)
+    try:
+        before = vb.launch_count()
+        keep = vb.ops.batched_nms(b.to(DEV), s.to(DEV), i.to(DEV), 0.5)
+        assert vb.launch_count() > before
+    finally:
+        _set(vb, "cuda")
+    assert keep.dtype == torch.int64 and np.array_equal(npy(keep), want)
+    # properties: unique indices, scores non-increasing, per-class greedy validity is implied by equality
+    k = npy(keep)
+    assert len(np.unique(k)) == len(k) and np.all(np.diff(s.numpy()[k]) <= 0)
+
+
+def test_batched_nms_strategies_classes_and_edges(vb, oracle):
+    rng = np.random.default_rng(5)
+    for n, ncls, ids in ((3000, 4, None), (30_000, 3, None), (26_000, 1, None), (26_000, 26_000, None), (27_000, 5, "weird")):
+        b = rng.random((n, 4), dtype=np.float32) * 200
+        b[:, 2:] = b[:, :2] + rng.random((n, 2), dtype=np.float32) * 60 + 1
+        s = (rng.permutation(n).astype(np.float32)) / n
+        i = rng.integers(0, ncls, n).astype(np.int64)
+        if ids == "weird":
+            i = np.array([-7, 0, 3, 2**40, -2**35], dtype=np.int64)[i]     # arbitrary int64 class ids
+        keep = vb.ops.batched_nms(t(b), t(s), t(i), 0.5)
+        want = oracle.batched_nms(b, s, i, 0.5, mode=oracle.NMS_MODE_CUDA, device_is_cuda=True)
+        assert np.array_equal(npy(keep), want), (n, ncls, ids)
+    e = vb.ops.batched_nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), 0.5)
+    assert e.shape == (0,) and e.dtype == torch.int64
+
+
+# =============================== deform_conv2d ==================================
+def test_deform_conv2d_golden(vb, golden):
+    g = golden
+    sh, sw, ph, pw, dh, dw = [int(v) for v in g["dcn_args"]]
+    for key, mask in (("dcn_out_mask", t(g["dcn_mask"])), ("dcn_out_nomask", None)):
+        got = vb.ops.deform_conv2d(t(g["dcn_x"]), t(g["dcn_off"]), t(g["dcn_w"]), t(g["dcn_b"]), (sh, sw), (ph, pw), (dh, dw), mask)
+        np.testing.assert_allclose(npy(got), g[key], **F32_TOL)
+
+
+@pytest.mark.parametrize("batch", [0, 33])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_deform_conv2d_reference_test_geometry(vb, oracle, batch, dtype):
+    # test/test_ops.py:1113-1167 get_fn_args: groups 2, offset groups 3, stride (2,1), pad (1,0), dil (2,1), kernel (3,2)
+    torch.manual_seed(0)
+    cin, cout, g, og, sh, sw, ph, pw, dh, dw, kh, kw, ih, iw = 6, 2, 2, 3, 2, 1, 1, 0, 2, 1, 3, 2, 5, 4
+    oh = (ih + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    ow = (iw + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    x = torch.rand(batch, cin, ih, iw).to(dtype)
+    off = torch.randn(batch, og * 2 * kh * kw, oh, ow).to(dtype)
+    msk = torch.randn(batch, og * kh * kw, oh, ow).to(dtype)
+    w = torch.randn(cout, cin // g, kh, kw).to(dtype)
+    bias = torch.randn(cout).to(dtype)
+    for mask in (msk, None):
+        got = vb.ops.deform_conv2d(x.to(DEV), off.to(DEV), w.to(DEV), bias.to(DEV), (sh, sw), (ph, pw), (dh, dw),
+                                   None if mask is None else mask.to(DEV))
+        assert got.shape == (batch, cout, oh, ow) and got.dtype == dtype
+        if batch:
+            want = oracle.deform_conv2d(x.float().numpy(), off.float().numpy(), w.float().numpy(), bias.float().numpy(),
+                                        (sh, sw), (ph, pw), (dh, dw), None if mask is None else mask.float().numpy())
+            np.testing.assert_allclose(npy(got), want, **(F32_TOL if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)))
+    # non-contiguous inputs are accepted (reference calls .contiguous())
+    if batch:
+        xt = x.to(DEV).permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)
+        a = vb.ops.deform_conv2d(xt, off.to(DEV), w.to(DEV), bias.to(DEV), (sh, sw), (ph, pw), (dh, dw), msk.to(DEV))
+        b = vb.ops.deform_conv2d(x.to(DEV), off.to(DEV), w.to(DEV), bias.to(DEV), (sh, sw), (ph, pw), (dh, dw), msk.to(DEV))
+        assert torch.equal(a, b)
+
+
+def test_deform_conv2d_errors(vb):
+    x = torch.rand(1, 6, 5, 4, device=DEV)
+    w = torch.rand(2, 3, 3, 2, device=DEV)
+    off = torch.rand(1, 3 * 2 * 6, 2, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="mask.shape\\[1\\] is not valid"):
+        vb.ops.deform_conv2d(x, off, w, None, (2, 1), (1, 0), (2, 1), torch.rand(1, 5, 2, 3, device=DEV))
+    with pytest.raises(RuntimeError, match="the shape of the offset tensor"):
+        vb.ops.deform_conv2d(x, torch.rand(1, 2, 2, 3, device=DEV), w, None, (2, 1), (1, 0), (2, 1))
+    with pytest.raises(RuntimeError, match="offset.shape\\[1\\] is not valid"):
+        vb.ops.deform_conv2d(x, torch.rand(1, 3 * 2 * 6 + 12, 2, 3, device=DEV)[:, :3 * 2 * 6 + 1], w, None, (2, 1), (1, 0), (2, 1))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2), (torch.float16, 1e-2)])
+def test_deform_conv2d_cfg4_reduced_vs_oracle(vb, oracle, dtype, tol):
+    """cfg4 geometry (3x3, stride 1, pad 1, DCNv2) at N=2, C 64->128, 32x32: inputs rounded to `dtype`,
+    reference arithmetic in fp32 on the rounded values (the reference has no bf16 kernel)."""
+    from vision_b200 import workloads
+
+    x, off, w, b, m = workloads.cfg4_deform_conv2d(batch=2, c_in=64, c_out=128, hw=32, dtype=dtype)
+    want = oracle.deform_conv2d(x.float().numpy(), off.float().numpy(), w.float().numpy(), b.float().numpy(), (1, 1), (1, 1), (1, 1),
+                                m.float().numpy())
+    got = vb.ops.deform_conv2d(x.to(DEV), off.to(DEV), w.to(DEV), b.to(DEV), 1, 1, 1, m.to(DEV))
+    np.testing.assert_allclose(npy(got), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_deform_conv2d_zero_offset_is_conv2d(vb, dtype, tol):
+    """Property at a larger size: offsets 0 and no mask == plain convolution (cuDNN, fp32)."""
+    from vision_b200 import workloads
+
+    x, off, w, b, _ = workloads.cfg4_deform_conv2d(batch=4, c_in=256, c_out=256, hw=64, dtype=dtype, offset_scale=0.0, use_mask=False)
+    x, off, w, b = x.to(DEV), off.to(DEV), w.to(DEV), b.to(DEV)
+    got = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, None)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = torch.nn.functional.conv2d(x.float(), w.float(), b.float(), stride=1, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    np.testing.assert_allclose(npy(got), npy(want), rtol=tol, atol=tol)
+
+
+# =============================== resize =========================================
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+@pytest.mark.parametrize("aa", [0, 1])
+def test_resize_golden(vb, golden, mode, aa):
+    img = t(golden["rs_img"])
+    for size in ((12, 13), (60, 80), (37, 20)):
+        got = vb.transforms.resize_image(img, list(size), interpolation=mode, antialias=bool(aa))
+        np.testing.assert_allclose(npy(got), golden[f"rs_{mode}_aa{aa}_{size[0]}x{size[1]}"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("aa", [True, False])
+def test_resize_cfg5_reduced_batch_vs_oracle(vb, oracle, aa):
+    """cfg5 geometry at batch 2: 2x3x2160x3840 fp16 -> 224x224 (reference route: fp16->fp32->interp->fp16)."""
+    from vision_b200 import workloads
+
+    x = workloads.cfg5_resize(device=DEV, batch=2)
+    got = vb.transforms.resize(x, [224, 224], antialias=aa)
+    assert got.shape == (2, 3, 224, 224) and got.dtype == torch.float16
+    want = torch.from_numpy(oracle.resize(x.float().cpu().numpy(), (224, 224), 0, aa)).half().float().numpy()
+    np.testing.assert_allclose(npy(got), want, rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.uint8])
+def test_resize_dtypes_shapes_and_identity(vb, oracle, dtype):
+    torch.manual_seed(3)
+    base = torch.rand(2, 2, 3, 45, 70)
+    x = (base * 255).round().to(torch.uint8) if dtype == torch.uint8 else base.to(dtype)
+    xd = x.to(DEV)
+    for mode, code in (("bilinear", 0), ("bicubic", 1)):
+        for aa in (True, False):
+            for size in ([20, 31], [90, 100], 30):
+                got = vb.transforms.resize_image(xd, size, interpolation=mode, antialias=aa)
+                oh, ow = vb.transforms.compute_resized_output_size((45, 70), size)
+                assert got.shape == (2, 2, 3, oh, ow) and got.dtype == dtype
+                ref = oracle.resize(x.float().numpy(), (oh, ow), code, aa)
+                if dtype == torch.uint8:
+                    ref = np.rint(np.clip(ref, 0, 255))
+                    assert np.abs(npy(got).astype(np.float32) - ref).max() <= 1.0    # rounding ties only
+                else:
+                    tol = dict(rtol=0, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+                    np.testing.assert_allclose(npy(got), ref, **tol)
+    same = vb.transforms.resize_image(xd, [45, 70])
+    assert same is xd                                                           # _geometry.py:313-314
+    ver = xd._version
+    vb.transforms.resize_image(xd, [10, 10])
+    assert xd._version == ver                                                   # input never mutated
+
+
+# =============================== drop-in through torchvision ======================
+def test_dropin_through_torchvision_api(vb, oracle):
+    tv = pytest.importorskip("torchvision")
+    from torchvision.transforms.v2 import functional as TF
+    from torchvision import tv_tensors
+    from vision_b200 import workloads
+
+    x, rois, kw = workloads.cfg2_roi_align(channels=32, k=100)
+    xd, rd = x.to(DEV), rois.to(DEV)
+    ref_cuda = tv.ops.roi_align(xd, rd, **kw)                                   # reference CUDA kernel (sm_100 SASS)
+    vb.install()
+    try:
+        before = vb.launch_count()
+        ours = tv.ops.roi_align(xd, rd, **kw)
+        assert vb.launch_count() > before, "torchvision.ops.roi_align did not reach the vision_b200 kernel"
+        np.testing.assert_allclose(npy(ours), npy(ref_cuda), **F32_TOL)
+        # autograd still flows through the reference's registered backward
+        xg = xd[:, :4].clone().requires_grad_(True)
+        tv.ops.roi_align(xg, rd, **kw).sum().backward()
+        assert xg.grad is not None and torch.isfinite(xg.grad).all()
+        # autocast wrapper casts to fp32 and lands on our CUDA kernel
+        with torch.autocast("cuda", dtype=torch.float16):
+            y = tv.ops.roi_align(xd.half(), rd.half(), **kw)
+        assert y.dtype == torch.float16
+        # batched_nms + nms
+        b, s, i = workloads.cfg3_batched_nms(n=30_000)
+        k1 = tv.ops.batched_nms(b.to(DEV), s.to(DEV), i.to(DEV), 0.5)
+        want = oracle.batched_nms(b.numpy(), s.numpy(), i.numpy(), 0.5, mode=oracle.NMS_MODE_CUDA, device_is_cuda=True)
+        assert np.array_equal(npy(k1), want)
+        k2 = tv.ops.nms(b[:2000].to(DEV), s[:2000].to(DEV), 0.5)
+        assert np.array_equal(npy(k2), oracle.nms(b[:2000].numpy(), s[:2000].numpy(), 0.5, oracle.NMS_MODE_CUDA))
+        # resize through the v2 functional, incl. tv_tensors
+        img = torch.rand(3, 180, 320, device=DEV).half()
+        before = vb.launch_count()
+        r = TF.resize(tv_tensors.Image(img), [64, 64])
+        assert vb.launch_count() > before and isinstance(r, tv_tensors.Image) and r.shape == (3, 64, 64)
+        want = torch.from_numpy(oracle.resize(img.float().cpu().numpy(), (64, 64), 0, True)).half().float().numpy()
+        np.testing.assert_allclose(npy(r.as_subclass(torch.Tensor)), want, rtol=1e-2, atol=1e-3)
+        v = TF.resize(tv_tensors.Video(torch.rand(2, 3, 40, 50, device=DEV)), [20, 20])
+        assert v.shape == (2, 3, 20, 20)
+    finally:
+        vb.uninstall()
+    again = tv.ops.roi_align(xd, rd, **kw)
+    assert torch.equal(again, ref_cuda)                                          # reference kernel active again
+
+
+def test_against_reference_cuda_kernels_same_box(vb):
+    """Extra: our kernels vs the reference's own CUDA kernels (wheel, sm_100 SASS) on this GPU."""
+    tv = pytest.importorskip("torchvision")
+    from vision_b200 import workloads
+
+    assert not vb.installed()
+    b, s, i = workloads.cfg3_batched_nms(n=100_000)
+    bd, sd, idd = b.to(DEV), s.to(DEV), i.to(DEV)
+    ref = tv.ops.batched_nms(bd, sd, idd, 0.5)
+    ours = vb.ops.batched_nms(bd, sd, idd, 0.5)
+    assert torch.equal(ref, ours)                                                # bit-exact vs CUDA reference
+    ref = tv.ops.nms(bd[:20000], sd[:20000], 0.5)
+    assert torch.equal(ref, vb.ops.nms(bd[:20000], sd[:20000], 0.5))
+    x, rois, kw = workloads.cfg2_roi_align(channels=64)
+    xd, rd = x.to(DEV), rois.to(DEV)
+    np.testing.assert_allclose(npy(vb.ops.roi_align(xd, rd, **kw)), npy(tv.ops.roi_align(xd, rd, **kw)), **F32_TOL)
+    o1, a1 = torch.ops.torchvision.roi_pool(xd, rd, 0.25, 7, 7)
+    o2, a2 = torch.ops.vision_b200.roi_pool(xd, rd, 0.25, 7, 7)
+    assert torch.equal(o1, o2) and torch.equal(a1, a2)
+    img = torch.rand(4, 3, 540, 960, device=DEV)
+    ref = torch.nn.functional.interpolate(img, size=[224, 224], mode="bilinear", antialias=True, align_corners=False)
+    np.testing.assert_allclose(npy(vb.transforms.resize(img, [224, 224])), npy(ref), rtol=0, atol=1e-5)
+
+
+# =============================== the C ABI, directly ================================
+def test_c_abi_direct_ctypes_call(vb, oracle):
+    """include/vision_b200.h entry point called with raw device pointers — no torch types involved."""
+    from vision_b200 import _lib, workloads
+
+    lib = _lib.core()
+    x, rois, _ = workloads.cfg2_roi_align(channels=8, k=64)
+    xd, rd = x.to(DEV), rois.to(DEV)
+    out = torch.empty(64, 8, 7, 7, device=DEV)
+    arg = torch.empty(64, 8, 7, 7, device=DEV, dtype=torch.int32)
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.vb200_roi_pool_forward(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(rd.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                    ctypes.c_void_p(arg.data_ptr()), 0, 1, 8, 200, 272, 64, 7, 7, ctypes.c_double(0.25),
+                                    ctypes.c_void_p(stream))
+    assert rc == 0, lib.vb200_last_error()
+    torch.cuda.synchronize()
+    wo, wa = oracle.roi_pool(x.numpy(), rois.numpy(), 7, 0.25)
+    assert np.array_equal(npy(out), wo) and np.array_equal(npy(arg), wa)
+    rc = lib.vb200_roi_pool_forward(None, None, None, None, 0, 1, 8, 200, 272, 64, 0, 7, ctypes.c_double(0.25), None)
+    assert rc == -1 and b"pooled size" in lib.vb200_last_error()

@@ -1,0 +1,86 @@
+"""install()/uninstall(): put the kernels behind torchvision's own API surface.
+
+1. dispatcher ops (nms, roi_align, roi_pool, ps_roi_align, deform_conv2d): re-registered for the
+   CUDA key of the existing ``torchvision::`` schemas by the C++ shim (a run-time twin of the
+   reference's TORCH_LIBRARY_IMPL blocks, e.g. csrc/ops/cuda/roi_align_kernel.cu:470-477).  Meta,
+   Autograd, Autocast, CPU and quantized registrations are untouched.
+2. ``batched_nms`` is Python in the reference (torchvision/ops/boxes.py:57-126): the module
+   attribute is rebound (detection models call ``box_ops.batched_nms`` at call time).
+3. ``resize`` has no torchvision kernel (transforms/v2/functional/_geometry.py:283-362 calls
+   F.interpolate): the entries of ``_KERNEL_REGISTRY[resize]`` for Tensor / Image / Video are swapped.
+CPU tensors and unsupported dtypes/modes keep flowing to the reference implementation.
+"""
+from __future__ import annotations
+
+import functools
+import warnings
+
+import torch
+
+from . import _lib, transforms as _tf
+
+_state: dict = {}
+
+
+def installed() -> bool:
+    return bool(_state)
+
+
+def install() -> None:
+    if _state:
+        return
+    import torchvision  # the schemas must exist before the CUDA key is overridden
+    from torchvision.ops import boxes as tv_boxes
+    from torchvision.transforms.v2.functional import _geometry as tv_geo, _utils as tv_utils
+    from torchvision import tv_tensors
+
+    _lib.load_ops()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")   # "Overriding a previously registered kernel" (expected)
+        torch.ops.vision_b200._install(True)
+
+    # ---- batched_nms ----
+    orig_batched_nms = tv_boxes.batched_nms
+
+    @functools.wraps(orig_batched_nms)
+    def batched_nms(boxes, scores, idxs, iou_threshold):
+        if (isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype in (torch.float32, torch.float16)
+                and not torch.jit.is_scripting() and not torch.jit.is_tracing()):
+            return torch.ops.vision_b200.batched_nms(boxes, scores, idxs, float(iou_threshold))
+        return orig_batched_nms(boxes, scores, idxs, iou_threshold)
+
+    tv_boxes.batched_nms = batched_nms
+    torchvision.ops.batched_nms = batched_nms
+
+    # ---- resize ----
+    registry = tv_utils._KERNEL_REGISTRY[tv_geo.resize]
+    saved = dict(registry)
+    orig_image = tv_geo.resize_image
+
+    @functools.wraps(orig_image)
+    def resize_image(image, size, interpolation=tv_geo.InterpolationMode.BILINEAR, max_size=None, antialias=True):
+        if isinstance(image, torch.Tensor) and _tf.supports(image, interpolation):
+            return _tf.resize_image(image, size, interpolation=interpolation, max_size=max_size, antialias=antialias)
+        return orig_image(image, size, interpolation=interpolation, max_size=max_size, antialias=antialias)
+
+    def resize_video(video, size, interpolation=tv_geo.InterpolationMode.BILINEAR, max_size=None, antialias=True):
+        return resize_image(video, size, interpolation=interpolation, max_size=max_size, antialias=antialias)
+
+    registry[torch.Tensor] = resize_image
+    registry[tv_tensors.Image] = tv_utils._kernel_tv_tensor_wrapper(resize_image)
+    registry[tv_tensors.Video] = tv_utils._kernel_tv_tensor_wrapper(resize_video)
+
+    _state.update(dict(tv_boxes=tv_boxes, torchvision=torchvision, orig_batched_nms=orig_batched_nms,
+                       registry=registry, saved_registry=saved))
+
+
+def uninstall() -> None:
+    if not _state:
+        return
+    torch.ops.vision_b200._install(False)
+    _state["tv_boxes"].batched_nms = _state["orig_batched_nms"]
+    _state["torchvision"].ops.batched_nms = _state["orig_batched_nms"]
+    reg = _state["registry"]
+    reg.clear()
+    reg.update(_state["saved_registry"])
+    _state.clear()

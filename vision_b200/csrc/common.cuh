@@ -1,0 +1,82 @@
+// common.cuh — shared helpers for the sm_100a kernels behind include/vision_b200.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/vision_b200.h"
+
+namespace vb200 {
+
+constexpr int kNumSMsB200 = 148;
+
+// ---- error plumbing -------------------------------------------------------
+char* last_error_buf();
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+inline int check_launch(const char* what) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define VB200_CUDA_TRY(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      vb200::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));             \
+      return (int)_e;                                                               \
+    }                                                                               \
+  } while (0)
+
+#define VB200_REQUIRE(cond, ...)                                                    \
+  do {                                                                              \
+    if (!(cond)) {                                                                  \
+      vb200::set_error(__VA_ARGS__);                                                \
+      return VB200_EINVAL;                                                          \
+    }                                                                               \
+  } while (0)
+
+// device attribute cache (per current device)
+int sm_count();
+int max_smem_optin();
+
+// ---- dtype traits -----------------------------------------------------------
+template <typename T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+
+template <typename T> __device__ __forceinline__ typename Acc<T>::type to_acc(T v) { return (typename Acc<T>::type)v; }
+template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_acc<uint8_t>(uint8_t v) { return (float)v; }
+
+template <typename T, typename A> __device__ __forceinline__ T from_acc(A v) { return (T)v; }
+template <> __device__ __forceinline__ __half from_acc<__half, float>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16, float>(float v) { return __float2bfloat16_rn(v); }
+
+// Round-to-nearest single ops that the compiler may not contract into FMAs:
+// used wherever the reference's x86 CPU arithmetic (no contraction) must be
+// reproduced bit-for-bit (sample coordinates, NMS IoU).
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace vb200

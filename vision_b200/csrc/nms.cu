@@ -1,0 +1,501 @@
+// nms.cu — nms and fused segmented batched_nms for sm_100a.
+//
+// Reference semantics (pytorch/vision):
+//   nms           csrc/ops/cuda/nms_kernel.cu:42-148,166-258 ; csrc/ops/cpu/nms_kernel.cpp:17-95
+//   batched_nms   torchvision/ops/boxes.py:57-126 (Python: per-class loop or coordinate trick)
+//
+// Design (not a port):
+//   * order = stable radix sort of scores (descending);  batched: a second
+//     stable sort by class id turns the score order into class-major segments
+//     whose inner order is still score-descending;
+//   * "segment" kernel: one CTA per class segment walks the segment in blocks of
+//     64 boxes: (1) the 64x64 diagonal IoU bit-matrix by warp ballot, (2) one
+//     thread resolves the greedy chain inside the block on bit-words,
+//     (3) all threads test the still-alive later boxes against the <=64 boxes
+//     kept in this block (boxes kept in shared memory, broadcast reads).  Only
+//     kept boxes ever act as suppressors, suppressed boxes are skipped — this
+//     is the reference's greedy order exactly, with no N x N/64 mask in HBM.
+//     All classes run concurrently (grid = segments), replacing ~80 Python
+//     iterations x ~10 launches + syncs;
+//   * "mask" path for a single huge segment (plain nms, n > kSegmentMaxSingle):
+//     upper-triangular 64x64 tiles over all SMs -> bit mask, then a one-CTA scan;
+//   * kept indices are emitted in global score order by flag compaction.
+// IoU arithmetic is written with explicit round-to-nearest intrinsics so that
+// the selected semantics (compiled-CUDA-reference or CPU-reference) is
+// reproduced bit for bit regardless of compiler contraction decisions.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace vb200 {
+namespace {
+
+constexpr int kSegThreads = 1024;
+constexpr int64_t kSegmentMaxSingle = 3072;   // plain nms: above this use the mask path
+
+struct IouParams {
+  float thr_f;
+  double thr_d;
+  int semantics;
+};
+
+// a = higher-scoring (suppressor) box, b = candidate.  area_a precomputed = mul_rn(a.z-a.x, a.w-a.y).
+__device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const IouParams p) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(sub_rn(right, left), 0.f), h = fmaxf(sub_rn(bottom, top), 0.f);
+  const float inter = mul_rn(w, h);
+  if (p.semantics == VB200_NMS_CUDA) {
+    // nms_kernel.cu:50-53 as compiled: Sb's product contracted into (Sa + Sb), float threshold
+    const float t = __fmaf_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y), area_a);
+    const float iou = div_rn(inter, sub_rn(t, inter));
+    return iou > p.thr_f;
+  } else {
+    // cpu/nms_kernel.cpp:58,86-88: separately rounded areas, double threshold
+    const float area_b = mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y));
+    const float ovr = div_rn(inter, sub_rn(add_rn(area_a, area_b), inter));
+    return (double)ovr > p.thr_d;
+  }
+}
+
+__global__ void iota_kernel(int* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
+// boxes_sorted[p] = boxes[order[p]] (one 128-bit load per box)
+__global__ void gather_boxes_kernel(const float4* __restrict__ boxes, const int* __restrict__ order,
+                                    float4* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ldg(boxes + order[i]);
+}
+
+// class key of the box at score-rank r
+__global__ void gather_class_kernel(const int64_t* __restrict__ idxs, const int* __restrict__ order,
+                                    int64_t* __restrict__ keys, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = idxs[order[i]];
+}
+
+// class-major gather through two permutations + segment-start flags
+__global__ void gather_boxes_cm_kernel(const float4* __restrict__ boxes, const int* __restrict__ order,
+                                       const int* __restrict__ rank_cm, const int64_t* __restrict__ cls_sorted,
+                                       float4* __restrict__ out, uint8_t* __restrict__ seg_flag, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    out[i] = __ldg(boxes + order[rank_cm[i]]);
+    seg_flag[i] = (i == 0 || cls_sorted[i] != cls_sorted[i - 1]) ? 1 : 0;
+  }
+}
+
+// coordinate trick (boxes.py:103-107): boxes + float(idx) * (max + 1), each op rounded once
+__global__ void shift_boxes_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ idxs,
+                                   const float* __restrict__ max_coord, float4* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float step = add_rn(*max_coord, 1.0f);
+    const float off = mul_rn((float)idxs[i], step);
+    float4 b = boxes[i];
+    b.x = add_rn(b.x, off); b.y = add_rn(b.y, off); b.z = add_rn(b.z, off); b.w = add_rn(b.w, off);
+    out[i] = b;
+  }
+}
+
+// One CTA per segment; see file header.  `suppressed` (zero on entry) is indexed by
+// position in the sorted order; on exit suppressed[p] == 0  <=>  box p is kept.
+__global__ void __launch_bounds__(kSegThreads, 1)
+nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg_start,
+                   const int* __restrict__ num_seg_ptr, int n_total, IouParams prm,
+                   uint8_t* __restrict__ suppressed) {
+  __shared__ float4 sb[64];
+  __shared__ float sarea[64];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_removed, s_kept;
+  __shared__ unsigned int s_rm[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nseg = num_seg_ptr ? *num_seg_ptr : 1;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const int s = seg_start ? seg_start[seg] : 0;
+    const int e = seg_start ? ((seg + 1 < nseg) ? seg_start[seg + 1] : n_total) : n_total;
+    const int n = e - s;
+    for (int b0 = 0; b0 < n; b0 += 64) {
+      const int nb = min(64, n - b0);
+      // stage the block's boxes; collect which of them are already suppressed
+      bool sup = true;
+      if (tid < 64) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < nb) { b = boxes[s + b0 + tid]; sup = suppressed[s + b0 + tid] != 0; }
+        sb[tid] = b;
+        sarea[tid] = mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y));
+        const unsigned int m = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0) s_rm[warp] = m;
+      }
+      __syncthreads();
+      // (1) diagonal 64x64 bit-matrix: warp w owns rows 2w, 2w+1; lane owns cols lane, lane+32
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = warp * 2 + rr;
+        const float4 a = sb[row];
+        const float aa = sarea[row];
+        const bool p0 = (lane > row) && (lane < nb) && (row < nb) && iou_gt(a, aa, sb[lane], prm);
+        const bool p1 = (lane + 32 > row) && (lane + 32 < nb) && (row < nb) && iou_gt(a, aa, sb[lane + 32], prm);
+        const unsigned int lo = __ballot_sync(0xffffffffu, p0);
+        const unsigned int hi = __ballot_sync(0xffffffffu, p1);
+        if (lane == 0) diag[row] = ((unsigned long long)hi << 32) | lo;
+      }
+      __syncthreads();
+      // (2) greedy chain inside the block (nms_kernel.cu:121-146 order), on registers
+      if (tid == 0) {
+        unsigned long long removed = ((unsigned long long)s_rm[1] << 32) | s_rm[0];
+        unsigned long long kept = 0;
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) {
+          const unsigned long long d = diag[i];
+          if (!((removed >> i) & 1ull)) { kept |= 1ull << i; removed |= d; }
+        }
+        s_kept = kept;
+        s_removed = removed;
+      }
+      __syncthreads();
+      const unsigned long long kept = s_kept;
+      if (tid < nb) suppressed[s + b0 + tid] = ((kept >> tid) & 1ull) ? 0 : 1;
+      // (3) later boxes vs. the boxes kept in this block.  Two threads per candidate
+      // (even / odd kept bits) to halve the dependent chain.
+      if (kept != 0ull) {
+        const int half = tid & 1;
+        for (int j = b0 + 64 + (tid >> 1); j < n; j += kSegThreads / 2) {
+          if (suppressed[s + j]) continue;
+          const float4 bj = boxes[s + j];
+          unsigned long long k = kept & (half ? 0xaaaaaaaaaaaaaaaaull : 0x5555555555555555ull);
+          bool dead = false;
+          while (k && !dead) {
+            const int i = __ffsll((long long)k) - 1;
+            k &= k - 1;
+            dead = iou_gt(sb[i], sarea[i], bj, prm);
+          }
+          if (dead) suppressed[s + j] = 1;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- mask path (single large segment) -------------------------------------
+// tile (rb, cb), cb >= rb, 64 threads = 64 rows; col boxes in smem; mask[row * col_blocks + cb]
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4* __restrict__ boxes, int n, int col_blocks, IouParams prm,
+                unsigned long long* __restrict__ mask) {
+  // linear upper-triangular tile index -> (rb, cb)
+  const long long t = blockIdx.x;
+  // rows are enumerated so that row rb has (col_blocks - rb) tiles
+  // solve rb: t < sum_{r<=rb} (col_blocks - r)
+  const double cbd = (double)col_blocks;
+  long long rb = (long long)floor(((2.0 * cbd + 1.0) - sqrt((2.0 * cbd + 1.0) * (2.0 * cbd + 1.0) - 8.0 * (double)t)) * 0.5);
+  if (rb < 0) rb = 0;
+  // fix up rounding
+  while (rb > 0 && t < rb * col_blocks - rb * (rb - 1) / 2) --rb;
+  while (t >= (rb + 1) * col_blocks - (rb + 1) * rb / 2) ++rb;
+  const long long first = rb * col_blocks - rb * (rb - 1) / 2;
+  const int cb = (int)(rb + (t - first));
+
+  __shared__ float4 cbx[64];
+  const int col0 = cb * 64, row0 = (int)rb * 64;
+  const int ncol = min(64, n - col0), nrow = min(64, n - row0);
+  if ((int)threadIdx.x < ncol) cbx[threadIdx.x] = boxes[col0 + threadIdx.x];
+  __syncthreads();
+  if ((int)threadIdx.x < nrow) {
+    const int row = row0 + threadIdx.x;
+    const float4 a = boxes[row];
+    const float aa = mul_rn(sub_rn(a.z, a.x), sub_rn(a.w, a.y));
+    unsigned long long bits = 0;
+    const int start = (cb == (int)rb) ? (int)threadIdx.x + 1 : 0;
+    for (int i = start; i < ncol; ++i)
+      if (iou_gt(a, aa, cbx[i], prm)) bits |= 1ull << i;
+    mask[(long long)row * col_blocks + cb] = bits;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int col_blocks,
+                uint8_t* __restrict__ suppressed) {
+  extern __shared__ unsigned long long removed[];   // col_blocks words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < col_blocks; i += blockDim.x) removed[i] = 0;
+  __syncthreads();
+  for (int nb = 0; nb < col_blocks; ++nb) {
+    const int row0 = nb * 64;
+    const int cnt = min(64, n - row0);
+    if (tid < 64) diag[tid] = (tid < cnt) ? mask[(long long)(row0 + tid) * col_blocks + nb] : 0ull;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long rem = removed[nb], kept = 0;
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        const unsigned long long d = diag[i];
+        if (i < cnt && !((rem >> i) & 1ull)) { kept |= 1ull << i; rem |= d; }
+      }
+      s_kept = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept;
+    if (tid < cnt) suppressed[row0 + tid] = ((kept >> tid) & 1ull) ? 0 : 1;
+    // OR the mask rows of the kept boxes into removed[nb+1 ..]
+    for (int j = nb + 1 + tid; j < col_blocks; j += blockDim.x) {
+      unsigned long long acc = removed[j];
+      unsigned long long k = kept;
+      while (k) {
+        const int i = __ffsll((long long)k) - 1;
+        k &= k - 1;
+        acc |= mask[(long long)(row0 + i) * col_blocks + j];
+      }
+      removed[j] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+struct NotZero {
+  __host__ __device__ __forceinline__ bool operator()(const uint8_t v) const { return v == 0; }
+};
+struct ToI64 {
+  __host__ __device__ __forceinline__ int64_t operator()(const int v) const { return (int64_t)v; }
+};
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Carves a workspace; with base == nullptr only sizes are accumulated.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  template <typename T> T* take(size_t count) {
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += align256(count * sizeof(T));
+    return p;
+  }
+};
+
+size_t cub_temp_bytes(int64_t n) {
+  // upper bound over every cub call below (queried with null storage); memoised per thread
+  static thread_local int64_t cached_n = -1;
+  static thread_local size_t cached_bytes = 0;
+  if (n == cached_n) return cached_bytes;
+  size_t mx = 0, b = 0;
+  const int ni = (int)n;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr, ni);
+  mx = b > mx ? b : mx;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (const int64_t*)nullptr, (int64_t*)nullptr, (const int*)nullptr, (int*)nullptr, ni);
+  mx = b > mx ? b : mx;
+  cub::DeviceSelect::Flagged(nullptr, b, (const int*)nullptr, (const uint8_t*)nullptr, (int*)nullptr, (int*)nullptr, ni);
+  mx = b > mx ? b : mx;
+  cub::DeviceReduce::Max(nullptr, b, (const float*)nullptr, (float*)nullptr, ni * 4);
+  mx = b > mx ? b : mx;
+  cached_n = n;
+  cached_bytes = mx + 4096;
+  return cached_bytes;
+}
+
+struct NmsWs {
+  int* iota; int* order; float* scores_sorted; float4* boxes_sorted; uint8_t* suppressed;
+  unsigned long long* mask; void* cub_temp; size_t cub_bytes; size_t total;
+};
+
+NmsWs carve_nms(void* base, int64_t n) {
+  Carver c(base);
+  NmsWs w;
+  w.iota = c.take<int>(n);
+  w.order = c.take<int>(n);
+  w.scores_sorted = c.take<float>(n);
+  w.boxes_sorted = c.take<float4>(n);
+  w.suppressed = c.take<uint8_t>(n);
+  w.cub_bytes = cub_temp_bytes(n);
+  w.cub_temp = c.take<char>(w.cub_bytes);
+  const int64_t cb = ceil_div64(n, 64);
+  w.mask = (n > kSegmentMaxSingle) ? c.take<unsigned long long>((size_t)n * cb) : nullptr;
+  w.total = c.off;
+  return w;
+}
+
+// Sorted-order suppression for ONE segment of n boxes (boxes_sorted), result in suppressed[].
+int run_single_segment(const float4* boxes_sorted, int64_t n, IouParams prm, uint8_t* suppressed,
+                       unsigned long long* mask, cudaStream_t st) {
+  if (n <= kSegmentMaxSingle || mask == nullptr) {
+    VB200_CUDA_TRY(cudaMemsetAsync(suppressed, 0, (size_t)n, st));
+    nms_segment_kernel<<<1, kSegThreads, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, prm, suppressed);
+    return check_launch("nms_segment_kernel");
+  }
+  const int cb = (int)ceil_div64(n, 64);
+  const long long tiles = (long long)cb * (cb + 1) / 2;
+  nms_mask_kernel<<<(unsigned)tiles, 64, 0, st>>>(boxes_sorted, (int)n, cb, prm, mask);
+  int rc = check_launch("nms_mask_kernel");
+  if (rc) return rc;
+  const size_t smem = (size_t)cb * sizeof(unsigned long long);
+  if (smem > 48 * 1024)
+    VB200_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_scan_kernel<<<1, 1024, smem, st>>>(mask, (int)n, cb, suppressed);
+  return check_launch("nms_scan_kernel");
+}
+
+int nms_core(const float4* boxes, const float* scores, int64_t n, IouParams prm, void* workspace,
+             size_t workspace_bytes, int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st) {
+  NmsWs w = carve_nms(workspace, n);
+  if (workspace_bytes < w.total) { set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
+  const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
+  iota_kernel<<<grd, blk, 0, st>>>(w.iota, ni);
+  int rc = check_launch("iota_kernel");
+  if (rc) return rc;
+  size_t tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, scores, w.scores_sorted, w.iota, w.order, ni, 0, 32, st));
+  g_launch_count.fetch_add(3, std::memory_order_relaxed);
+  gather_boxes_kernel<<<grd, blk, 0, st>>>(boxes, w.order, w.boxes_sorted, ni);
+  rc = check_launch("gather_boxes_kernel");
+  if (rc) return rc;
+  rc = run_single_segment(w.boxes_sorted, n, prm, w.suppressed, w.mask, st);
+  if (rc) return rc;
+  cub::TransformInputIterator<int64_t, ToI64, const int*> in_it(w.order, ToI64());
+  cub::TransformInputIterator<bool, NotZero, const uint8_t*> flag_it(w.suppressed, NotZero());
+  tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, in_it, flag_it, keep_out, num_keep_out, ni, st));
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // namespace
+}  // namespace vb200
+
+using namespace vb200;
+
+extern "C" size_t vb200_nms_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return carve_nms(nullptr, n).total;
+}
+
+extern "C" int vb200_nms(const void* boxes, const void* scores, int dtype, int64_t n, double iou_threshold,
+                         int semantics, void* workspace, size_t workspace_bytes, int64_t* keep_out,
+                         int64_t* num_keep_out, vb200_stream stream) {
+  VB200_REQUIRE(dtype == VB200_F32, "nms: only float32 boxes are supported by this build (got dtype %d)", dtype);
+  VB200_REQUIRE(n >= 0 && n < (1ll << 31), "nms: bad box count");
+  VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "nms: bad semantics selector");
+  VB200_REQUIRE(num_keep_out != nullptr, "nms: null num_keep_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
+  VB200_REQUIRE(boxes && scores && keep_out && workspace, "nms: null pointer");
+  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "nms: boxes must be 16-byte aligned");
+  IouParams prm{(float)iou_threshold, iou_threshold, semantics};
+  return nms_core((const float4*)boxes, (const float*)scores, n, prm, workspace, workspace_bytes, keep_out,
+                  num_keep_out, st);
+}
+
+namespace vb200 {
+namespace {
+struct BnmsWs {
+  int* iota; int* order; float* scores_sorted; int64_t* cls_keys; int64_t* cls_sorted; int* rank_cm;
+  float4* boxes_cm; uint8_t* seg_flag; int* seg_start; int* num_seg; uint8_t* suppressed;
+  uint8_t* keep_by_rank; float* max_coord; float4* shifted; void* cub_temp; size_t cub_bytes;
+  size_t nms_off; size_t total;
+};
+BnmsWs carve_bnms(void* base, int64_t n) {
+  Carver c(base);
+  BnmsWs w;
+  w.iota = c.take<int>(n);
+  w.order = c.take<int>(n);
+  w.scores_sorted = c.take<float>(n);
+  w.cls_keys = c.take<int64_t>(n);
+  w.cls_sorted = c.take<int64_t>(n);
+  w.rank_cm = c.take<int>(n);
+  w.boxes_cm = c.take<float4>(n);
+  w.seg_flag = c.take<uint8_t>(n);
+  w.seg_start = c.take<int>(n + 1);
+  w.num_seg = c.take<int>(64);
+  w.suppressed = c.take<uint8_t>(n);
+  w.keep_by_rank = c.take<uint8_t>(n);
+  w.max_coord = c.take<float>(64);
+  w.shifted = c.take<float4>(n);
+  w.cub_bytes = cub_temp_bytes(n);
+  w.cub_temp = c.take<char>(w.cub_bytes);
+  w.nms_off = c.off;                       // trick strategy reuses the plain-nms pipeline
+  c.off += carve_nms(nullptr, n).total;
+  w.total = c.off;
+  return w;
+}
+
+__global__ void scatter_keep_kernel(const uint8_t* __restrict__ suppressed, const int* __restrict__ rank_cm,
+                                    uint8_t* __restrict__ keep_by_rank, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep_by_rank[rank_cm[i]] = suppressed[i] ? 0 : 1;
+}
+}  // namespace
+}  // namespace vb200
+
+extern "C" size_t vb200_batched_nms_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return carve_bnms(nullptr, n).total;
+}
+
+extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
+                                 int64_t n, double iou_threshold, int semantics, int strategy,
+                                 void* workspace, size_t workspace_bytes, int64_t* keep_out,
+                                 int64_t* num_keep_out, vb200_stream stream) {
+  VB200_REQUIRE(dtype == VB200_F32, "batched_nms: only float32 boxes are supported by this build (got dtype %d)", dtype);
+  VB200_REQUIRE(n >= 0 && n < (1ll << 31), "batched_nms: bad box count");
+  VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "batched_nms: bad semantics selector");
+  VB200_REQUIRE(strategy >= VB200_BNMS_AUTO && strategy <= VB200_BNMS_TRICK, "batched_nms: bad strategy");
+  VB200_REQUIRE(num_keep_out != nullptr, "batched_nms: null num_keep_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
+  VB200_REQUIRE(boxes && scores && idxs && keep_out && workspace, "batched_nms: null pointer");
+  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "batched_nms: boxes must be 16-byte aligned");
+  BnmsWs w = carve_bnms(workspace, n);
+  if (workspace_bytes < w.total) { set_error("batched_nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
+  IouParams prm{(float)iou_threshold, iou_threshold, semantics};
+  const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
+  if (strategy == VB200_BNMS_AUTO) strategy = (4 * n > 100000) ? VB200_BNMS_VANILLA : VB200_BNMS_TRICK;   // boxes.py:86
+
+  if (strategy == VB200_BNMS_TRICK) {
+    size_t tb = w.cub_bytes;
+    VB200_CUDA_TRY(cub::DeviceReduce::Max(w.cub_temp, tb, (const float*)boxes, w.max_coord, ni * 4, st));
+    g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    shift_boxes_kernel<<<grd, blk, 0, st>>>((const float4*)boxes, idxs, w.max_coord, w.shifted, ni);
+    int rc = check_launch("shift_boxes_kernel");
+    if (rc) return rc;
+    return nms_core(w.shifted, (const float*)scores, n, prm, (char*)workspace + w.nms_off,
+                    workspace_bytes - w.nms_off, keep_out, num_keep_out, st);
+  }
+
+  // ---- vanilla semantics, fused ------------------------------------------
+  iota_kernel<<<grd, blk, 0, st>>>(w.iota, ni);
+  int rc = check_launch("iota_kernel");
+  if (rc) return rc;
+  size_t tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, (const float*)scores, w.scores_sorted, w.iota, w.order, ni, 0, 32, st));
+  g_launch_count.fetch_add(3, std::memory_order_relaxed);
+  gather_class_kernel<<<grd, blk, 0, st>>>(idxs, w.order, w.cls_keys, ni);
+  rc = check_launch("gather_class_kernel");
+  if (rc) return rc;
+  tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.cls_keys, w.cls_sorted, w.iota, w.rank_cm, ni, 0, 64, st));
+  g_launch_count.fetch_add(9, std::memory_order_relaxed);
+  gather_boxes_cm_kernel<<<grd, blk, 0, st>>>((const float4*)boxes, w.order, w.rank_cm, w.cls_sorted, w.boxes_cm, w.seg_flag, ni);
+  rc = check_launch("gather_boxes_cm_kernel");
+  if (rc) return rc;
+  tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, w.iota, w.seg_flag, w.seg_start, w.num_seg, ni, st));
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  VB200_CUDA_TRY(cudaMemsetAsync(w.suppressed, 0, (size_t)n, st));
+  const int grid = sm_count() * 1;
+  nms_segment_kernel<<<grid, kSegThreads, 0, st>>>(w.boxes_cm, w.seg_start, w.num_seg, ni, prm, w.suppressed);
+  rc = check_launch("nms_segment_kernel");
+  if (rc) return rc;
+  scatter_keep_kernel<<<grd, blk, 0, st>>>(w.suppressed, w.rank_cm, w.keep_by_rank, ni);
+  rc = check_launch("scatter_keep_kernel");
+  if (rc) return rc;
+  cub::TransformInputIterator<int64_t, ToI64, const int*> in_it(w.order, ToI64());
+  tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, in_it, w.keep_by_rank, keep_out, num_keep_out, ni, st));
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  return 0;
+}

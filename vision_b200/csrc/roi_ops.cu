@@ -1,0 +1,535 @@
+// roi_ops.cu — roi_align / roi_pool / ps_roi_align forward for sm_100a.
+//
+// Reference semantics (pytorch/vision):
+//   roi_align     csrc/ops/cuda/roi_align_kernel.cu:14-143   (CPU: cpu/roi_align_kernel.cpp:18-115,
+//                                                             cpu/roi_align_common.h:32-124)
+//   roi_pool      csrc/ops/cuda/roi_pool_kernel.cu:15-78     (CPU: cpu/roi_pool_kernel.cpp:24-92)
+//   ps_roi_align  csrc/ops/cuda/ps_roi_align_kernel.cu:68-140 (CPU: cpu/ps_roi_align_kernel.cpp:73-151)
+//
+// Design (not a port — the reference runs one thread per output element and
+// recomputes the RoI geometry K*C*PH*PW times):
+//   * bilinear sampling is separable, so the geometry of a RoI is PH*gh row
+//     entries + PW*gw column entries; it is computed ONCE per RoI with the
+//     reference's exact (uncontracted, round-to-nearest) coordinate arithmetic;
+//   * generic kernel: CTA = (RoI, channel chunk), geometry table in shared
+//     memory, threads stride over (channel, bin) so output stores are coalesced;
+//   * plane-resident kernel (fp32, fixed sampling_ratio, plane <= ~220 KB):
+//     persistent CTAs hold one whole H*W channel plane in shared memory (bulk
+//     async copy + mbarrier), every gather is an LDS, each input byte leaves
+//     HBM once and each output byte is written once.
+#include "common.cuh"
+
+namespace vb200 {
+namespace {
+
+// One axis of a bilinear sample, exactly as bilinear_interpolate() derives it
+// (roi_align_kernel.cu:21-56): lo/hi pixel index and the two weights.
+template <typename A>
+struct AxisEnt {
+  int lo;   // low index (>= 0) or -1 when the coordinate is outside [-1, size]
+  int hi;   // high index
+  A l;      // weight of hi  (coordinate - lo)
+  A h;      // weight of lo  (1 - l)
+};
+
+template <typename A>
+__device__ __forceinline__ AxisEnt<A> axis_entry(A v, int size) {
+  AxisEnt<A> e;
+  if (v < (A)-1.0 || v > (A)size) {
+    e.lo = -1; e.hi = -1; e.l = 0; e.h = 0;
+    return e;
+  }
+  if (v <= 0) v = 0;
+  int lo = (int)v, hi;
+  if (lo >= size - 1) { hi = lo = size - 1; v = (A)lo; } else hi = lo + 1;
+  e.lo = lo; e.hi = hi;
+  e.l = sub_rn(v, (A)lo);
+  e.h = sub_rn((A)1, e.l);
+  return e;
+}
+
+template <typename A>
+struct RoiGeom {
+  int batch;
+  A start_w, start_h, bin_w, bin_h;
+  int gh, gw;
+  A count;
+};
+
+// RoI box -> sampling geometry; roi_align_kernel.cu:86-121.  `ps` selects the
+// ps_roi_align variant (always -0.5, no >=1 clamp, count not clamped).
+template <typename T, typename A>
+__device__ __forceinline__ RoiGeom<A> roi_geometry(const T* __restrict__ r, A scale, int PH, int PW,
+                                                   int sampling_ratio, bool aligned, bool ps) {
+  RoiGeom<A> g;
+  g.batch = (int)to_acc(r[0]);
+  A off = (aligned || ps) ? (A)0.5 : (A)0.0;
+  A sw = sub_rn(mul_rn((A)to_acc(r[1]), scale), off);
+  A sh = sub_rn(mul_rn((A)to_acc(r[2]), scale), off);
+  A ew = sub_rn(mul_rn((A)to_acc(r[3]), scale), off);
+  A eh = sub_rn(mul_rn((A)to_acc(r[4]), scale), off);
+  A rw = sub_rn(ew, sw), rh = sub_rn(eh, sh);
+  if (!aligned && !ps) {
+    rw = rw > (A)1 ? rw : (A)1;   // max(roi_width, 1.)
+    rh = rh > (A)1 ? rh : (A)1;
+  }
+  g.start_w = sw; g.start_h = sh;
+  g.bin_h = div_rn(rh, (A)PH);
+  g.bin_w = div_rn(rw, (A)PW);
+  g.gh = sampling_ratio > 0 ? sampling_ratio : (int)ceil(div_rn(rh, (A)PH));
+  g.gw = sampling_ratio > 0 ? sampling_ratio : (int)ceil(div_rn(rw, (A)PW));
+  int cnt = g.gh * g.gw;
+  g.count = ps ? (A)cnt : (A)(cnt > 1 ? cnt : 1);
+  return g;
+}
+
+// y = roi_start_h + ph * bin_size_h + (iy + .5f) * bin_size_h / grid_h  (left to right, no FMA)
+template <typename A>
+__device__ __forceinline__ A sample_coord(A start, A bin, int p, int i, int grid) {
+  A a = add_rn(start, mul_rn((A)p, bin));
+  A b = div_rn(mul_rn((A)((float)i + .5f), bin), (A)grid);
+  return add_rn(a, b);
+}
+
+constexpr int kMaxAxisEnt = 512;   // per-axis table capacity of the generic kernel
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_align_generic_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                         int C, int H, int W, int PH, int PW, typename Acc<T>::type scale,
+                         int sampling_ratio, int aligned, int ch_per_cta) {
+  using A = typename Acc<T>::type;
+  __shared__ AxisEnt<A> rowtab[kMaxAxisEnt];
+  __shared__ AxisEnt<A> coltab[kMaxAxisEnt];
+
+  const int n = blockIdx.x;
+  const int c0 = blockIdx.y * ch_per_cta;
+  const int nch = min(ch_per_cta, C - c0);
+  const RoiGeom<A> g = roi_geometry<T, A>(rois + (int64_t)n * 5, scale, PH, PW, sampling_ratio, aligned != 0, false);
+  const int nrow = PH * g.gh, ncol = PW * g.gw;
+  const bool tab = nrow <= kMaxAxisEnt && ncol <= kMaxAxisEnt;   // CTA-uniform
+  if (tab) {
+    for (int i = threadIdx.x; i < nrow; i += blockDim.x)
+      rowtab[i] = axis_entry<A>(sample_coord<A>(g.start_h, g.bin_h, i / g.gh, i % g.gh, g.gh), H);
+    for (int i = threadIdx.x; i < ncol; i += blockDim.x)
+      coltab[i] = axis_entry<A>(sample_coord<A>(g.start_w, g.bin_w, i / g.gw, i % g.gw, g.gw), W);
+    __syncthreads();
+  }
+  const int nbins = PH * PW;
+  const int64_t plane = (int64_t)H * W;
+  for (int i = threadIdx.x; i < nch * nbins; i += blockDim.x) {
+    const int cl = i / nbins, bin = i - cl * nbins;
+    const int ph = bin / PW, pw = bin - ph * PW;
+    const T* __restrict__ in = input + ((int64_t)g.batch * C + (c0 + cl)) * plane;
+    A sum = 0;
+    for (int iy = 0; iy < g.gh; ++iy) {
+      const AxisEnt<A> ey = tab ? rowtab[ph * g.gh + iy]
+                                : axis_entry<A>(sample_coord<A>(g.start_h, g.bin_h, ph, iy, g.gh), H);
+      for (int ix = 0; ix < g.gw; ++ix) {
+        const AxisEnt<A> ex = tab ? coltab[pw * g.gw + ix]
+                                  : axis_entry<A>(sample_coord<A>(g.start_w, g.bin_w, pw, ix, g.gw), W);
+        A val = 0;
+        if (ey.lo >= 0 && ex.lo >= 0) {
+          const A v1 = to_acc(in[ey.lo * W + ex.lo]), v2 = to_acc(in[ey.lo * W + ex.hi]);
+          const A v3 = to_acc(in[ey.hi * W + ex.lo]), v4 = to_acc(in[ey.hi * W + ex.hi]);
+          const A w1 = mul_rn(ey.h, ex.h), w2 = mul_rn(ey.h, ex.l), w3 = mul_rn(ey.l, ex.h), w4 = mul_rn(ey.l, ex.l);
+          val = add_rn(add_rn(add_rn(mul_rn(w1, v1), mul_rn(w2, v2)), mul_rn(w3, v3)), mul_rn(w4, v4));
+        }
+        sum = add_rn(sum, val);
+      }
+    }
+    sum = div_rn(sum, g.count);
+    output[((int64_t)n * C + (c0 + cl)) * nbins + bin] = from_acc<T, A>(sum);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Plane-resident fp32 path.
+// ---------------------------------------------------------------------------
+// Packed per-axis geometry entry (8 B): bit31 = invalid, bit30 = (hi != lo),
+// bits[0,30) = offset of `lo` in floats (row entries are pre-multiplied by W).
+struct PackedEnt { uint32_t p; float l; };
+
+__global__ void roi_align_geometry_kernel(const float* __restrict__ rois, PackedEnt* __restrict__ geo,
+                                          int32_t* __restrict__ roi_batch, int K, int H, int W, int PH,
+                                          int PW, float scale, int sr, int aligned) {
+  const int ent_per_roi = (PH + PW) * sr;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K * ent_per_roi) return;
+  const int n = t / ent_per_roi, e = t - n * ent_per_roi;
+  const RoiGeom<float> g = roi_geometry<float, float>(rois + (int64_t)n * 5, scale, PH, PW, sr, aligned != 0, false);
+  if (e == 0) roi_batch[n] = g.batch;
+  AxisEnt<float> a;
+  uint32_t mult;
+  if (e < PH * sr) { a = axis_entry<float>(sample_coord<float>(g.start_h, g.bin_h, e / sr, e % sr, sr), H); mult = (uint32_t)W; }
+  else { const int f = e - PH * sr; a = axis_entry<float>(sample_coord<float>(g.start_w, g.bin_w, f / sr, f % sr, sr), W); mult = 1u; }
+  PackedEnt pe;
+  if (a.lo < 0) { pe.p = 0x80000000u; pe.l = 0.f; }
+  else { pe.p = (uint32_t)a.lo * mult | (a.hi != a.lo ? 0x40000000u : 0u); pe.l = a.l; }
+  geo[t] = pe;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0, 16 B aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kPlaneThreads = 1024;
+constexpr uint32_t kBulkChunk = 32768;
+
+// Work = all (plane, roi) pairs in plane-major order, split evenly over the
+// persistent CTAs; a CTA (re)loads a plane only when its range crosses into it.
+template <int SR>
+__global__ void __launch_bounds__(kPlaneThreads, 1)
+roi_align_plane_kernel(const float* __restrict__ input, const PackedEnt* __restrict__ geo,
+                       const int32_t* __restrict__ roi_batch, float* __restrict__ output,
+                       int B, int C, int H, int W, int K, int PH, int PW, int plane_stride_f) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  __shared__ uint64_t bar;
+
+  const int HW = H * W;
+  const int nbins = PH * PW;
+  const int ent_per_roi = (PH + PW) * SR;
+  const float count = (float)(SR * SR);
+  const int64_t total = (int64_t)B * C * K;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per;
+  const int64_t w1 = min(total, w0 + per);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  int64_t w = w0;
+  while (w < w1) {
+    const int pl = (int)(w / K);              // plane index = b * C + c
+    const int r0 = (int)(w - (int64_t)pl * K);
+    const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
+    const int b = pl / C;
+    // ---- stage plane `pl` into shared memory (previous plane is dead: all threads synced) ----
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)HW * 4u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bar, bytes);
+      const char* src = reinterpret_cast<const char*>(input + (int64_t)pl * HW);
+      char* dst = reinterpret_cast<char*>(plane);
+      for (uint32_t o = 0; o < bytes; o += kBulkChunk)
+        bulk_g2s(dst + o, src + o, min(kBulkChunk, bytes - o), &bar);
+    }
+    mbar_wait(&bar, parity);
+    parity ^= 1u;
+
+    // ---- every thread owns (roi, bin) items of this plane ----
+    const int items = (r1 - r0) * nbins;
+    for (int it = threadIdx.x; it < items; it += kPlaneThreads) {
+      const int rl = it / nbins, bin = it - rl * nbins;
+      const int n = r0 + rl;
+      const int ph = bin / PW, pw = bin - ph * PW;
+      float res = 0.f;
+      if (__ldg(roi_batch + n) == b) {
+        const PackedEnt* __restrict__ ge = geo + (int64_t)n * ent_per_roi;
+        float sum = 0.f;
+#pragma unroll
+        for (int iy = 0; iy < SR; ++iy) {
+          const uint2 eyr = __ldg(reinterpret_cast<const uint2*>(ge + ph * SR + iy));
+          PackedEnt ey; ey.p = eyr.x; ey.l = __uint_as_float(eyr.y);
+          const bool vy = !(ey.p & 0x80000000u);
+          const uint32_t ro = ey.p & 0x3fffffffu;
+          const uint32_t dy = (ey.p & 0x40000000u) ? (uint32_t)W : 0u;
+          const float ly = ey.l, hy = vy ? 1.f - ly : 0.f;
+#pragma unroll
+          for (int ix = 0; ix < SR; ++ix) {
+            const uint2 exr = __ldg(reinterpret_cast<const uint2*>(ge + PH * SR + pw * SR + ix));
+            PackedEnt ex; ex.p = exr.x; ex.l = __uint_as_float(exr.y);
+            const bool vx = !(ex.p & 0x80000000u);
+            const uint32_t xo = ex.p & 0x3fffffffu;
+            const uint32_t dx = (ex.p & 0x40000000u) ? 1u : 0u;
+            const float lx = ex.l, hx = vx ? 1.f - lx : 0.f;
+            const uint32_t base = ro + xo;
+            const float v1 = plane[base], v2 = plane[base + dx];
+            const float v3 = plane[base + dy], v4 = plane[base + dy + dx];
+            const float top = fmaf(lx, v2, hx * v1);
+            const float bot = fmaf(lx, v4, hx * v3);
+            sum = fmaf(hy, top, sum);
+            sum = fmaf(ly, bot, sum);
+          }
+        }
+        res = __fdiv_rn(sum, count);
+        output[((int64_t)n * C + (pl - b * C)) * nbins + bin] = res;
+      }
+    }
+    __syncthreads();   // plane buffer may be overwritten by the next bulk copy
+    w += (r1 - r0);
+  }
+  (void)plane_stride_f;
+}
+
+// ---------------------------------------------------------------------------
+// roi_pool: one thread per output element, bin window shared arithmetic
+// (roi_pool_kernel.cu:15-78) — integer/compare work, bit-exact incl. argmax.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+roi_pool_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                int32_t* __restrict__ argmax, int64_t total, int C, int H, int W, int PH, int PW,
+                typename Acc<T>::type scale) {
+  using A = typename Acc<T>::type;
+  for (int64_t index = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; index < total;
+       index += (int64_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(index % PW);
+    const int ph = (int)((index / PW) % PH);
+    const int c = (int)((index / PW / PH) % C);
+    const int64_t n = index / PW / PH / C;
+    const T* r = rois + n * 5;
+    const int b = (int)to_acc(r[0]);
+    const int rsw = (int)round(mul_rn((A)to_acc(r[1]), scale));
+    const int rsh = (int)round(mul_rn((A)to_acc(r[2]), scale));
+    const int rew = (int)round(mul_rn((A)to_acc(r[3]), scale));
+    const int reh = (int)round(mul_rn((A)to_acc(r[4]), scale));
+    const int rw = max(rew - rsw + 1, 1), rh = max(reh - rsh + 1, 1);
+    const A bh = div_rn((A)rh, (A)PH), bw = div_rn((A)rw, (A)PW);
+    int hs = (int)floor(mul_rn((A)ph, bh)), ws = (int)floor(mul_rn((A)pw, bw));
+    int he = (int)ceil(mul_rn((A)(ph + 1), bh)), we = (int)ceil(mul_rn((A)(pw + 1), bw));
+    hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+    ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
+    const bool empty = (he <= hs) || (we <= ws);
+    A maxval = empty ? (A)0 : (A)-3.402823466e+38F;   // -FLT_MAX, also for double (reference uses -FLT_MAX)
+    int maxidx = -1;
+    const T* in = input + ((int64_t)b * C + c) * H * W;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) {
+        const int ii = h * W + w;
+        const A v = to_acc(in[ii]);
+        if (v > maxval) { maxval = v; maxidx = ii; }
+      }
+    output[index] = from_acc<T, A>(maxval);
+    argmax[index] = maxidx;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ps_roi_align: one thread per output element, reference arithmetic order
+// (ps_roi_align_kernel.cu:68-140) with uncontracted coordinates.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+ps_roi_align_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                    int32_t* __restrict__ mapping, int64_t total, int C, int H, int W, int PH, int PW,
+                    int Cout, typename Acc<T>::type scale, int sampling_ratio) {
+  using A = typename Acc<T>::type;
+  for (int64_t index = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; index < total;
+       index += (int64_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(index % PW);
+    const int ph = (int)((index / PW) % PH);
+    const int co = (int)((index / PW / PH) % Cout);
+    const int64_t n = index / PW / PH / Cout;
+    const int c_in = (co * PH + ph) * PW + pw;
+    const RoiGeom<A> g = roi_geometry<T, A>(rois + n * 5, scale, PH, PW, sampling_ratio, true, true);
+    const A hstart = add_rn(mul_rn((A)ph, g.bin_h), g.start_h);
+    const A wstart = add_rn(mul_rn((A)pw, g.bin_w), g.start_w);
+    const T* in = input + ((int64_t)g.batch * C + c_in) * H * W;
+    A sum = 0;
+    for (int iy = 0; iy < g.gh; ++iy) {
+      const A y = add_rn(hstart, div_rn(mul_rn((A)((float)iy + .5f), g.bin_h), (A)g.gh));
+      const AxisEnt<A> ey = axis_entry<A>(y, H);
+      for (int ix = 0; ix < g.gw; ++ix) {
+        const A x = add_rn(wstart, div_rn(mul_rn((A)((float)ix + .5f), g.bin_w), (A)g.gw));
+        const AxisEnt<A> ex = axis_entry<A>(x, W);
+        A val = 0;
+        if (ey.lo >= 0 && ex.lo >= 0) {
+          const A v1 = to_acc(in[ey.lo * W + ex.lo]), v2 = to_acc(in[ey.lo * W + ex.hi]);
+          const A v3 = to_acc(in[ey.hi * W + ex.lo]), v4 = to_acc(in[ey.hi * W + ex.hi]);
+          const A w1 = mul_rn(ey.h, ex.h), w2 = mul_rn(ey.h, ex.l), w3 = mul_rn(ey.l, ex.h), w4 = mul_rn(ey.l, ex.l);
+          val = add_rn(add_rn(add_rn(mul_rn(w1, v1), mul_rn(w2, v2)), mul_rn(w3, v3)), mul_rn(w4, v4));
+        }
+        sum = add_rn(sum, val);
+      }
+    }
+    sum = div_rn(sum, g.count);
+    output[index] = from_acc<T, A>(sum);
+    mapping[index] = c_in;
+  }
+}
+
+template <typename T>
+int launch_roi_align_generic(const void* input, const void* rois, void* output, int C, int H, int W, int K,
+                             int PH, int PW, double scale, int sr, int aligned, cudaStream_t st) {
+  const int ch_per_cta = C >= 64 ? 32 : (C >= 16 ? 16 : C);
+  dim3 grid((unsigned)K, (unsigned)ceil_div(C, ch_per_cta));
+  roi_align_generic_kernel<T><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, C, H, W, PH, PW,
+                                                   (typename Acc<T>::type)scale, sr, aligned, ch_per_cta);
+  return check_launch("roi_align_generic_kernel");
+}
+
+}  // namespace
+}  // namespace vb200
+
+using namespace vb200;
+
+namespace {
+// Path selection shared by the workspace query and the launcher.
+bool roi_align_use_plane(int dtype, const void* input, int batch, int channels, int height, int width,
+                         int num_rois, int sampling_ratio) {
+  if (dtype != VB200_F32) return false;
+  const size_t plane_bytes = (size_t)height * width * 4;
+  const bool fits = plane_bytes + 1024 <= (size_t)max_smem_optin();
+  const bool sr_ok = sampling_ratio >= 1 && sampling_ratio <= 4;
+  const bool align_ok = plane_bytes % 16 == 0 && (input == nullptr || ((uintptr_t)input % 16) == 0);
+  const int64_t pairs = (int64_t)batch * channels * num_rois;
+  bool use_plane = fits && sr_ok && align_ok && pairs >= 4096;
+  const char* force = getenv("VB200_ROI_ALIGN_PATH");   // "generic" | "plane" (testing / profiling)
+  if (force && force[0] == 'g') use_plane = false;
+  if (force && force[0] == 'p') use_plane = fits && sr_ok && align_ok;
+  return use_plane;
+}
+size_t roi_align_geo_bytes(int num_rois, int pooled_h, int pooled_w, int sampling_ratio) {
+  const size_t geo = (size_t)num_rois * (pooled_h + pooled_w) * sampling_ratio * sizeof(PackedEnt);
+  return (geo + 255) & ~(size_t)255;
+}
+}  // namespace
+
+extern "C" size_t vb200_roi_align_workspace_bytes(int dtype, int batch, int channels, int height, int width,
+                                                  int num_rois, int pooled_h, int pooled_w,
+                                                  int sampling_ratio) {
+  if (num_rois <= 0 || channels <= 0) return 0;
+  if (!roi_align_use_plane(dtype, nullptr, batch, channels, height, width, num_rois, sampling_ratio)) return 0;
+  return roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio) + (size_t)num_rois * 4;
+}
+
+extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void* output, int dtype,
+                                       int batch, int channels, int height, int width, int num_rois,
+                                       int pooled_h, int pooled_w, double spatial_scale,
+                                       int sampling_ratio, int aligned, void* workspace,
+                                       size_t workspace_bytes, vb200_stream stream) {
+  VB200_REQUIRE(batch >= 0 && channels >= 0 && height >= 0 && width >= 0 && num_rois >= 0, "roi_align: negative size");
+  VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "roi_align: pooled size must be positive");
+  if (num_rois == 0 || channels == 0) return 0;
+  VB200_REQUIRE(input && rois && output, "roi_align: null pointer");
+  VB200_REQUIRE((int64_t)num_rois * channels * pooled_h * pooled_w < (1ll << 31) &&
+                (int64_t)batch * channels * height * width < (1ll << 31), "roi_align: tensor too large for 32-bit indexing");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB200_F32) {
+    const size_t geo_pad = roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio);
+    const bool use_plane = roi_align_use_plane(dtype, input, batch, channels, height, width, num_rois, sampling_ratio) &&
+                           workspace != nullptr && workspace_bytes >= geo_pad + (size_t)num_rois * 4 &&
+                           ((uintptr_t)workspace % 16) == 0;
+    if (use_plane) {
+      const size_t plane_bytes = (size_t)height * width * 4;
+      const int64_t pairs = (int64_t)batch * channels * num_rois;
+      const int ent = (pooled_h + pooled_w) * sampling_ratio;
+      PackedEnt* geo = (PackedEnt*)workspace;
+      int32_t* rb = (int32_t*)((char*)workspace + geo_pad);
+      const int nt = num_rois * ent;
+      roi_align_geometry_kernel<<<ceil_div(nt, 256), 256, 0, st>>>((const float*)rois, geo, rb, num_rois, height,
+                                                                   width, pooled_h, pooled_w, (float)spatial_scale,
+                                                                   sampling_ratio, aligned);
+      int rc = check_launch("roi_align_geometry_kernel");
+      if (rc) return rc;
+      const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+      const size_t smem = plane_bytes + 128;
+#define VB200_LAUNCH_PLANE(SR)                                                                                     \
+  {                                                                                                                \
+    VB200_CUDA_TRY(cudaFuncSetAttribute(roi_align_plane_kernel<SR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                        (int)smem));                                                               \
+    roi_align_plane_kernel<SR><<<grid, kPlaneThreads, smem, st>>>((const float*)input, geo, rb, (float*)output,    \
+                                                                  batch, channels, height, width, num_rois,       \
+                                                                  pooled_h, pooled_w, 0);                         \
+  }
+      switch (sampling_ratio) {
+        case 1: VB200_LAUNCH_PLANE(1) break;
+        case 2: VB200_LAUNCH_PLANE(2) break;
+        case 3: VB200_LAUNCH_PLANE(3) break;
+        default: VB200_LAUNCH_PLANE(4) break;
+      }
+#undef VB200_LAUNCH_PLANE
+      return check_launch("roi_align_plane_kernel");
+    }
+    return launch_roi_align_generic<float>(input, rois, output, channels, height, width, num_rois, pooled_h,
+                                           pooled_w, spatial_scale, sampling_ratio, aligned, st);
+  }
+  if (dtype == VB200_F16)
+    return launch_roi_align_generic<__half>(input, rois, output, channels, height, width, num_rois, pooled_h,
+                                            pooled_w, spatial_scale, sampling_ratio, aligned, st);
+  if (dtype == VB200_F64)
+    return launch_roi_align_generic<double>(input, rois, output, channels, height, width, num_rois, pooled_h,
+                                            pooled_w, spatial_scale, sampling_ratio, aligned, st);
+  set_error("roi_align: unsupported dtype %d (float, double, half as the reference)", dtype);
+  return VB200_EUNSUPPORTED;
+}
+
+template <typename T>
+static int launch_roi_pool(const void* input, const void* rois, void* output, int32_t* argmax, int C, int H, int W,
+                           int K, int PH, int PW, double scale, cudaStream_t st) {
+  const int64_t total = (int64_t)K * C * PH * PW;
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count() * 32 ? ceil_div64(total, 256) : (int64_t)sm_count() * 32);
+  roi_pool_kernel<T><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, argmax, total, C, H, W, PH, PW,
+                                          (typename Acc<T>::type)scale);
+  return check_launch("roi_pool_kernel");
+}
+
+extern "C" int vb200_roi_pool_forward(const void* input, const void* rois, void* output, int32_t* argmax,
+                                      int dtype, int batch, int channels, int height, int width, int num_rois,
+                                      int pooled_h, int pooled_w, double spatial_scale, vb200_stream stream) {
+  VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "roi_pool: pooled size must be positive");
+  if (num_rois == 0 || channels == 0) return 0;
+  VB200_REQUIRE(input && rois && output && argmax, "roi_pool: null pointer");
+  VB200_REQUIRE((int64_t)batch * channels * height * width < (1ll << 31), "roi_pool: input too large for 32-bit indexing");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case VB200_F32: return launch_roi_pool<float>(input, rois, output, argmax, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F16: return launch_roi_pool<__half>(input, rois, output, argmax, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F64: return launch_roi_pool<double>(input, rois, output, argmax, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+  }
+  set_error("roi_pool: unsupported dtype %d", dtype);
+  return VB200_EUNSUPPORTED;
+}
+
+template <typename T>
+static int launch_ps_roi_align(const void* input, const void* rois, void* output, int32_t* mapping, int C, int H, int W,
+                               int K, int PH, int PW, double scale, int sr, cudaStream_t st) {
+  const int Cout = C / (PH * PW);
+  const int64_t total = (int64_t)K * Cout * PH * PW;
+  if (total == 0) return 0;
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count() * 32 ? ceil_div64(total, 256) : (int64_t)sm_count() * 32);
+  ps_roi_align_kernel<T><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, mapping, total, C, H, W, PH,
+                                              PW, Cout, (typename Acc<T>::type)scale, sr);
+  return check_launch("ps_roi_align_kernel");
+}
+
+extern "C" int vb200_ps_roi_align_forward(const void* input, const void* rois, void* output,
+                                          int32_t* channel_mapping, int dtype, int batch, int channels,
+                                          int height, int width, int num_rois, int pooled_h, int pooled_w,
+                                          double spatial_scale, int sampling_ratio, vb200_stream stream) {
+  VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "ps_roi_align: pooled size must be positive");
+  VB200_REQUIRE(channels % (pooled_h * pooled_w) == 0,
+                "input channels must be a multiple of pooling height * pooling width");
+  if (num_rois == 0 || channels == 0) return 0;
+  VB200_REQUIRE(input && rois && output && channel_mapping, "ps_roi_align: null pointer");
+  VB200_REQUIRE((int64_t)batch * channels * height * width < (1ll << 31), "ps_roi_align: input too large for 32-bit indexing");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case VB200_F32: return launch_ps_roi_align<float>(input, rois, output, channel_mapping, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
+    case VB200_F16: return launch_ps_roi_align<__half>(input, rois, output, channel_mapping, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
+    case VB200_F64: return launch_ps_roi_align<double>(input, rois, output, channel_mapping, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
+  }
+  set_error("ps_roi_align: unsupported dtype %d", dtype);
+  return VB200_EUNSUPPORTED;
+}

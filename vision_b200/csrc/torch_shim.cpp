@@ -1,0 +1,308 @@
+// torch_shim.cpp — PyTorch dispatcher glue over the C ABI in include/vision_b200.h.
+//
+// * defines the ops under our own namespace `vision_b200::` with the reference's schemas
+//   (csrc/ops/nms.cpp:27, roi_align.cpp:74-75, roi_pool.cpp:67-68, ps_roi_align.cpp:74-75,
+//   deform_conv2d.cpp:101-102) plus `batched_nms` and `resize`, which are Python-only in the
+//   reference (torchvision/ops/boxes.py:57-126, transforms/v2/functional/_geometry.py:283-362);
+// * `vision_b200::_install(True)` registers the same functions for (`torchvision::<op>`, CUDA)
+//   at run time (a heap torch::Library, the dynamic twin of the reference's
+//   TORCH_LIBRARY_IMPL(torchvision, CUDA, m) blocks, e.g. cuda/roi_align_kernel.cu:470-477);
+//   `_install(False)` destroys it, which re-activates the reference kernels (A/B in-process).
+// Tensors are plumbing only: device memory, current stream, allocator.  All checks and error
+// strings follow the reference's host functions so its tests read the same.
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/library.h>
+
+#include <atomic>
+#include <memory>
+
+#include "../../include/vision_b200.h"
+
+namespace {
+
+std::atomic<int> g_nms_semantics{VB200_NMS_CUDA};
+
+int dtype_code(at::ScalarType t, const char* op) {
+  switch (t) {
+    case at::kFloat: return VB200_F32;
+    case at::kHalf: return VB200_F16;
+    case at::kBFloat16: return VB200_BF16;
+    case at::kDouble: return VB200_F64;
+    case at::kByte: return VB200_U8;
+    default: TORCH_CHECK(false, op, ": unsupported dtype ", t);
+  }
+  return -1;
+}
+
+void check_rc(int rc, const char* op) {
+  TORCH_CHECK(rc == 0, op, ": ", vb200_last_error(), " [vision_b200 rc=", rc, "]");
+}
+
+vb200_stream cur_stream() { return (vb200_stream)at::cuda::getCurrentCUDAStream().stream(); }
+
+at::Tensor workspace(size_t bytes, const at::Tensor& like) {
+  return at::empty({(int64_t)(bytes ? bytes : 1)}, like.options().dtype(at::kByte));
+}
+
+// ---- roi ops -------------------------------------------------------------
+void check_roi_inputs(const at::Tensor& input, const at::Tensor& rois) {
+  TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+  TORCH_CHECK(rois.is_cuda(), "rois must be a CUDA tensor");
+  TORCH_CHECK(rois.dim() == 2 && rois.size(1) == 5, "rois must have shape as Tensor[K, 5]");
+  TORCH_CHECK(input.dim() == 4, "input must be a 4-d tensor [N, C, H, W]");
+  TORCH_CHECK(input.get_device() == rois.get_device(), "input and rois must be on the same GPU");
+  TORCH_CHECK(input.scalar_type() == rois.scalar_type(), "Expected tensor for argument #1 'input' to have the same type as tensor for argument #2 'rois'");
+}
+
+at::Tensor roi_align(const at::Tensor& input, const at::Tensor& rois, double spatial_scale, int64_t pooled_height,
+                     int64_t pooled_width, int64_t sampling_ratio, bool aligned) {
+  check_roi_inputs(input, rois);
+  at::cuda::CUDAGuard guard(input.device());
+  const int64_t K = rois.size(0), N = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
+  at::Tensor out = at::empty({K, C, pooled_height, pooled_width}, input.options());
+  if (out.numel() == 0) return out;
+  const int dt = dtype_code(input.scalar_type(), "roi_align");
+  at::Tensor in_c = input.contiguous(), rois_c = rois.contiguous();
+  const size_t wsb = vb200_roi_align_workspace_bytes(dt, (int)N, (int)C, (int)H, (int)W, (int)K, (int)pooled_height,
+                                                     (int)pooled_width, (int)sampling_ratio);
+  at::Tensor ws = workspace(wsb, input);
+  check_rc(vb200_roi_align_forward(in_c.data_ptr(), rois_c.data_ptr(), out.data_ptr(), dt, (int)N, (int)C, (int)H, (int)W,
+                                   (int)K, (int)pooled_height, (int)pooled_width, spatial_scale, (int)sampling_ratio,
+                                   aligned ? 1 : 0, wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+           "roi_align");
+  return out;
+}
+
+std::tuple<at::Tensor, at::Tensor> roi_pool(const at::Tensor& input, const at::Tensor& rois, double spatial_scale,
+                                            int64_t pooled_height, int64_t pooled_width) {
+  check_roi_inputs(input, rois);
+  at::cuda::CUDAGuard guard(input.device());
+  const int64_t K = rois.size(0), N = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
+  at::Tensor out = at::empty({K, C, pooled_height, pooled_width}, input.options());
+  at::Tensor argmax = at::empty({K, C, pooled_height, pooled_width}, input.options().dtype(at::kInt));
+  if (out.numel() == 0) return std::make_tuple(out, argmax);
+  const int dt = dtype_code(input.scalar_type(), "roi_pool");
+  at::Tensor in_c = input.contiguous(), rois_c = rois.contiguous();
+  check_rc(vb200_roi_pool_forward(in_c.data_ptr(), rois_c.data_ptr(), out.data_ptr(), argmax.data_ptr<int32_t>(), dt,
+                                  (int)N, (int)C, (int)H, (int)W, (int)K, (int)pooled_height, (int)pooled_width,
+                                  spatial_scale, cur_stream()),
+           "roi_pool");
+  return std::make_tuple(out, argmax);
+}
+
+std::tuple<at::Tensor, at::Tensor> ps_roi_align(const at::Tensor& input, const at::Tensor& rois, double spatial_scale,
+                                                int64_t pooled_height, int64_t pooled_width, int64_t sampling_ratio) {
+  check_roi_inputs(input, rois);
+  at::cuda::CUDAGuard guard(input.device());
+  const int64_t K = rois.size(0), N = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
+  TORCH_CHECK(C % (pooled_height * pooled_width) == 0,
+              "input channels must be a multiple of pooling height * pooling width");
+  const int64_t Cout = C / (pooled_height * pooled_width);
+  at::Tensor out = at::empty({K, Cout, pooled_height, pooled_width}, input.options());
+  at::Tensor mapping = at::empty({K, Cout, pooled_height, pooled_width}, input.options().dtype(at::kInt));
+  if (out.numel() == 0) return std::make_tuple(out, mapping);
+  const int dt = dtype_code(input.scalar_type(), "ps_roi_align");
+  at::Tensor in_c = input.contiguous(), rois_c = rois.contiguous();
+  check_rc(vb200_ps_roi_align_forward(in_c.data_ptr(), rois_c.data_ptr(), out.data_ptr(), mapping.data_ptr<int32_t>(), dt,
+                                      (int)N, (int)C, (int)H, (int)W, (int)K, (int)pooled_height, (int)pooled_width,
+                                      spatial_scale, (int)sampling_ratio, cur_stream()),
+           "ps_roi_align");
+  return std::make_tuple(out, mapping);
+}
+
+// ---- nms -------------------------------------------------------------------
+void check_nms_inputs(const at::Tensor& dets, const at::Tensor& scores) {
+  TORCH_CHECK(dets.is_cuda(), "dets must be a CUDA tensor");
+  TORCH_CHECK(scores.is_cuda(), "scores must be a CUDA tensor");
+  TORCH_CHECK(dets.dim() == 2, "boxes should be a 2d tensor, got ", dets.dim(), "D");
+  TORCH_CHECK(dets.size(1) == 4, "boxes should have 4 elements in dimension 1, got ", dets.size(1));
+  TORCH_CHECK(scores.dim() == 1, "scores should be a 1d tensor, got ", scores.dim(), "D");
+  TORCH_CHECK(dets.size(0) == scores.size(0), "boxes and scores should have same number of elements in ",
+              "dimension 0, got ", dets.size(0), " and ", scores.size(0));
+}
+
+at::Tensor as_f32_boxes(const at::Tensor& t, const char* op) {
+  // The reference instantiates float / double / Half.  Half is widened (its reference kernel
+  // already multiplies in float); double is refused rather than silently narrowed.
+  TORCH_CHECK(t.scalar_type() != at::kDouble, op,
+              ": float64 boxes are not supported by the vision_b200 CUDA kernels (float32 / float16 only)");
+  return t.to(at::kFloat).contiguous();
+}
+
+at::Tensor nms(const at::Tensor& dets, const at::Tensor& scores, double iou_threshold) {
+  check_nms_inputs(dets, scores);
+  at::cuda::CUDAGuard guard(dets.device());
+  if (dets.numel() == 0) return at::empty({0}, dets.options().dtype(at::kLong));
+  at::Tensor boxes = as_f32_boxes(dets, "nms"), sc = as_f32_boxes(scores, "nms");
+  const int64_t n = boxes.size(0);
+  const size_t wsb = vb200_nms_workspace_bytes(n);
+  at::Tensor ws = workspace(wsb, boxes);
+  at::Tensor keep = at::empty({n}, boxes.options().dtype(at::kLong));
+  at::Tensor count = at::empty({1}, boxes.options().dtype(at::kLong));
+  check_rc(vb200_nms(boxes.data_ptr(), sc.data_ptr(), VB200_F32, n, iou_threshold, g_nms_semantics.load(), ws.data_ptr(),
+                     wsb, keep.data_ptr<int64_t>(), count.data_ptr<int64_t>(), cur_stream()),
+           "nms");
+  const int64_t k = count.item<int64_t>();   // the reference's masked_select sync (nms_kernel.cu:257)
+  return keep.narrow(0, 0, k);
+}
+
+at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const at::Tensor& idxs, double iou_threshold) {
+  check_nms_inputs(dets, scores);
+  TORCH_CHECK(idxs.is_cuda(), "idxs must be a CUDA tensor");
+  TORCH_CHECK(idxs.dim() == 1 && idxs.size(0) == dets.size(0), "idxs should be a 1d tensor with one entry per box");
+  at::cuda::CUDAGuard guard(dets.device());
+  if (dets.numel() == 0) return at::empty({0}, dets.options().dtype(at::kLong));
+  at::Tensor boxes = as_f32_boxes(dets, "batched_nms"), sc = as_f32_boxes(scores, "batched_nms");
+  at::Tensor cls = idxs.to(at::kLong).contiguous();
+  const int64_t n = boxes.size(0);
+  const size_t wsb = vb200_batched_nms_workspace_bytes(n);
+  at::Tensor ws = workspace(wsb, boxes);
+  at::Tensor keep = at::empty({n}, boxes.options().dtype(at::kLong));
+  at::Tensor count = at::empty({1}, boxes.options().dtype(at::kLong));
+  check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), VB200_F32, n, iou_threshold,
+                             g_nms_semantics.load(), VB200_BNMS_AUTO, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
+                             count.data_ptr<int64_t>(), cur_stream()),
+           "batched_nms");
+  const int64_t k = count.item<int64_t>();
+  return keep.narrow(0, 0, k);
+}
+
+// ---- deform_conv2d ---------------------------------------------------------
+at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset,
+                         const at::Tensor& mask, const at::Tensor& bias, int64_t stride_h, int64_t stride_w,
+                         int64_t pad_h, int64_t pad_w, int64_t dilation_h, int64_t dilation_w, int64_t n_weight_grps,
+                         int64_t n_offset_grps, bool use_mask) {
+  at::Tensor input_c = input.contiguous(), offset_c = offset.contiguous(), weight_c = weight.contiguous();
+  at::Tensor mask_c = mask.contiguous(), bias_c = bias.contiguous();
+  TORCH_CHECK(input_c.ndimension() == 4);
+  TORCH_CHECK(offset_c.ndimension() == 4);
+  TORCH_CHECK(!use_mask || mask_c.ndimension() == 4);
+  TORCH_CHECK(weight_c.ndimension() == 4);
+  TORCH_CHECK(input_c.is_cuda(), "input must be a CUDA tensor");
+  at::cuda::CUDAGuard guard(input_c.device());
+
+  const int64_t batch = input_c.size(0), c_in = input_c.size(1), in_h = input_c.size(2), in_w = input_c.size(3);
+  const int64_t c_out = weight_c.size(0), kh = weight_c.size(2), kw = weight_c.size(3);
+  TORCH_CHECK(kh > 0 && kw > 0, "weight_h: ", kh, " weight_w: ", kw);
+  TORCH_CHECK(stride_h > 0 && stride_w > 0, "stride_h: ", stride_h, " stride_w: ", stride_w);
+  TORCH_CHECK(pad_h >= 0 && pad_w >= 0, "pad_h: ", pad_h, " pad_w: ", pad_w);
+  TORCH_CHECK(dilation_h > 0 && dilation_w > 0, "dilation_h: ", dilation_h, " dilation_w: ", dilation_w);
+  const int64_t ker_h = dilation_h * (kh - 1) + 1, ker_w = dilation_w * (kw - 1) + 1;
+  const int64_t out_h = ((in_h + 2 * pad_h - ker_h) / stride_h) + 1;
+  const int64_t out_w = ((in_w + 2 * pad_w - ker_w) / stride_w) + 1;
+  TORCH_CHECK(n_weight_grps > 0 && n_offset_grps > 0);
+  TORCH_CHECK(weight_c.size(1) * n_weight_grps == c_in);
+  TORCH_CHECK(c_out % n_weight_grps == 0);
+  TORCH_CHECK(offset_c.size(1) == n_offset_grps * 2 * kh * kw, "offset.shape[1] is not valid: got: ", offset_c.size(1),
+              " expected: ", n_offset_grps * 2 * kh * kw);
+  TORCH_CHECK(!use_mask || mask_c.size(1) == n_offset_grps * kh * kw, "mask.shape[1] is not valid: got: ",
+              mask_c.size(1), " expected: ", n_offset_grps * kh * kw);
+  TORCH_CHECK(c_in % n_offset_grps == 0);
+  TORCH_CHECK(offset_c.size(0) == batch, "invalid batch size of offset");
+  TORCH_CHECK(offset_c.size(2) == out_h && offset_c.size(3) == out_w, "offset output dims: (", offset_c.size(2), ", ",
+              offset_c.size(3), ") - computed output dims: (", out_h, ", ", out_w, ")");
+  TORCH_CHECK(mask_c.size(0) == batch, "invalid batch size of mask");
+  TORCH_CHECK(!use_mask || (mask_c.size(2) == out_h && mask_c.size(3) == out_w), "mask output dims: (", mask_c.size(2),
+              ", ", mask_c.size(3), ") - computed output dims: (", out_h, ", ", out_w, ")");
+  TORCH_CHECK(out_h > 0 && out_w > 0, "Calculated output size too small - out_h: ", out_h, " out_w: ", out_w);
+  const auto st = input_c.scalar_type();
+  TORCH_CHECK(weight_c.scalar_type() == st && offset_c.scalar_type() == st && (!use_mask || mask_c.scalar_type() == st) &&
+                  bias_c.scalar_type() == st,
+              "deform_conv2d: all tensors must share one dtype");
+
+  at::Tensor out = at::empty({batch, c_out, out_h, out_w}, input_c.options());
+  if (batch == 0 || out.numel() == 0) return out;
+  const int dt = dtype_code(st, "deform_conv2d");
+  TORCH_CHECK(dt == VB200_F32 || dt == VB200_F16 || dt == VB200_BF16, "deform_conv2d: unsupported dtype ", st);
+  TORCH_CHECK(bias_c.numel() == c_out, "bias must have one entry per output channel");
+  const size_t wsb = vb200_deform_conv2d_workspace_bytes(dt, (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out, (int)kh,
+                                                         (int)kw, (int)out_h, (int)out_w, (int)n_weight_grps,
+                                                         (int)n_offset_grps);
+  at::Tensor ws = workspace(wsb, input_c);
+  check_rc(vb200_deform_conv2d_forward(input_c.data_ptr(), weight_c.data_ptr(), offset_c.data_ptr(),
+                                       use_mask ? mask_c.data_ptr() : nullptr, bias_c.data_ptr(), out.data_ptr(), dt,
+                                       (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out, (int)kh, (int)kw,
+                                       (int)stride_h, (int)stride_w, (int)pad_h, (int)pad_w, (int)dilation_h,
+                                       (int)dilation_w, (int)n_weight_grps, (int)n_offset_grps, use_mask ? 1 : 0,
+                                       wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+           "deform_conv2d");
+  return out;
+}
+
+// ---- resize ----------------------------------------------------------------
+// input [..., H, W] -> [..., out_h, out_w]; mode 0 bilinear / 1 bicubic (align_corners=False).
+at::Tensor resize(const at::Tensor& input, int64_t out_h, int64_t out_w, int64_t mode, bool antialias) {
+  TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+  TORCH_CHECK(input.dim() >= 2, "resize: input must have at least 2 dimensions");
+  TORCH_CHECK(out_h > 0 && out_w > 0, "resize: output size must be positive");
+  at::cuda::CUDAGuard guard(input.device());
+  at::Tensor in_c = input.contiguous();
+  std::vector<int64_t> shape(in_c.sizes().begin(), in_c.sizes().end());
+  const int64_t in_h = shape[shape.size() - 2], in_w = shape[shape.size() - 1];
+  TORCH_CHECK(in_h > 0 && in_w > 0, "resize: empty spatial dimensions");
+  shape[shape.size() - 2] = out_h;
+  shape[shape.size() - 1] = out_w;
+  at::Tensor out = at::empty(shape, in_c.options());
+  if (out.numel() == 0) return out;
+  const int64_t planes = in_c.numel() / (in_h * in_w);
+  const int dt = dtype_code(in_c.scalar_type(), "resize");
+  check_rc(vb200_resize(in_c.data_ptr(), out.data_ptr(), dt, planes, (int)in_h, (int)in_w, (int)out_h, (int)out_w, (int)mode,
+                        antialias ? 1 : 0, cur_stream()),
+           "resize");
+  return out;
+}
+
+// ---- install / uninstall -----------------------------------------------------
+std::unique_ptr<torch::Library> g_override;
+
+void install(bool on) {
+  if (!on) { g_override.reset(); return; }
+  if (g_override) return;
+  auto lib = std::make_unique<torch::Library>(torch::Library::IMPL, "torchvision",
+                                              c10::make_optional(c10::DispatchKey::CUDA), __FILE__, __LINE__);
+  lib->impl("nms", TORCH_FN(nms));
+  lib->impl("roi_align", TORCH_FN(roi_align));
+  lib->impl("roi_pool", TORCH_FN(roi_pool));
+  lib->impl("ps_roi_align", TORCH_FN(ps_roi_align));
+  lib->impl("deform_conv2d", TORCH_FN(deform_conv2d));
+  g_override = std::move(lib);
+}
+bool installed() { return (bool)g_override; }
+void set_nms_semantics(int64_t s) {
+  TORCH_CHECK(s == VB200_NMS_CPU || s == VB200_NMS_CUDA, "nms semantics must be 0 (cpu) or 1 (cuda)");
+  g_nms_semantics.store((int)s);
+}
+int64_t get_nms_semantics() { return g_nms_semantics.load(); }
+int64_t launch_count() { return (int64_t)vb200_launch_count(); }
+int64_t abi_version() { return vb200_abi_version(); }
+
+}  // namespace
+
+TORCH_LIBRARY(vision_b200, m) {
+  m.def("nms(Tensor dets, Tensor scores, float iou_threshold) -> Tensor");
+  m.def("batched_nms(Tensor boxes, Tensor scores, Tensor idxs, float iou_threshold) -> Tensor");
+  m.def("roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio, bool aligned) -> Tensor");
+  m.def("roi_pool(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width) -> (Tensor, Tensor)");
+  m.def("ps_roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio) -> (Tensor, Tensor)");
+  m.def("deform_conv2d(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> Tensor");
+  m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
+  m.def("_install(bool on) -> ()", &install);
+  m.def("_installed() -> bool", &installed);
+  m.def("_set_nms_semantics(int s) -> ()", &set_nms_semantics);
+  m.def("_get_nms_semantics() -> int", &get_nms_semantics);
+  m.def("_launch_count() -> int", &launch_count);
+  m.def("_abi_version() -> int", &abi_version);
+}
+
+TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
+  m.impl("nms", TORCH_FN(nms));
+  m.impl("batched_nms", TORCH_FN(batched_nms));
+  m.impl("roi_align", TORCH_FN(roi_align));
+  m.impl("roi_pool", TORCH_FN(roi_pool));
+  m.impl("ps_roi_align", TORCH_FN(ps_roi_align));
+  m.impl("deform_conv2d", TORCH_FN(deform_conv2d));
+  m.impl("resize", TORCH_FN(resize));
+}
