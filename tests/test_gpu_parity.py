@@ -373,6 +373,22 @@ def test_resize_cfg5_reduced_batch_vs_oracle(vb, oracle, aa):
     np.testing.assert_allclose(npy(got), want, rtol=1e-2, atol=1e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape,size", [((3, 2, 96, 1024), (17, 40)), ((5, 301, 1000), (33, 97)), ((1, 1, 64, 4000), (64, 160)),
+                                        ((2, 3, 500, 808), (224, 224)), ((2, 400, 1600), (7, 3))])
+def test_resize_stream_path_vs_generic_and_oracle(vb, oracle, dtype, shape, size):
+    """The streaming bilinear-AA downscale kernel (scale_w >= 2, 16-bit storage) against the generic
+    kernel and the oracle: pixel-pair slot widths LW 4/6/10/16, band splitting, ragged last intervals."""
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape).to(dtype).to(DEV)
+    fast = vb.transforms.resize_image(x.unsqueeze(-3) if x.dim() == 2 else x, list(size), antialias=True)
+    with force_env("VB200_RESIZE_PATH", "generic"):
+        slow = vb.transforms.resize_image(x, list(size), antialias=True)
+    want = oracle.resize(x.float().cpu().numpy(), size, 0, True)
+    np.testing.assert_allclose(npy(fast), want, rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(npy(fast), npy(slow), rtol=1e-2, atol=4e-3)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.uint8])
 def test_resize_dtypes_shapes_and_identity(vb, oracle, dtype):
     torch.manual_seed(3)
@@ -399,6 +415,18 @@ def test_resize_dtypes_shapes_and_identity(vb, oracle, dtype):
     assert xd._version == ver                                                   # input never mutated
 
 
+def _check_roi_align_vs_both_references(ours, ref_cuda, ref_cpu):
+    """The reference has TWO implementations that disagree with each other by more than 1e-5 on
+    FPN-sized maps: nvcc contracts the sample-coordinate arithmetic of roi_align_kernel.cu:125-135
+    into FMAs, the x86 build of cpu/roi_align_kernel.cpp does not, and an ulp of a coordinate ~200 is
+    1.5e-5 pixels times the local gradient.  Parity is defined against the CPU kernel (what oracle/
+    restates, to 1e-5); against the CUDA kernel we must be no farther than the CPU kernel itself is."""
+    np.testing.assert_allclose(ours, ref_cpu, **F32_TOL)
+    ref_gap = np.abs(ref_cuda - ref_cpu).max()
+    our_gap = np.abs(ours - ref_cuda).max()
+    assert our_gap <= ref_gap + 1e-5, (our_gap, ref_gap)
+
+
 # =============================== drop-in through torchvision ======================
 def test_dropin_through_torchvision_api(vb, oracle):
     tv = pytest.importorskip("torchvision")
@@ -414,7 +442,7 @@ def test_dropin_through_torchvision_api(vb, oracle):
         before = vb.launch_count()
         ours = tv.ops.roi_align(xd, rd, **kw)
         assert vb.launch_count() > before, "torchvision.ops.roi_align did not reach the vision_b200 kernel"
-        np.testing.assert_allclose(npy(ours), npy(ref_cuda), **F32_TOL)
+        _check_roi_align_vs_both_references(npy(ours), npy(ref_cuda), npy(tv.ops.roi_align(x, rois, **kw)))
         # autograd still flows through the reference's registered backward
         xg = xd[:, :4].clone().requires_grad_(True)
         tv.ops.roi_align(xg, rd, **kw).sum().backward()
@@ -460,7 +488,8 @@ def test_against_reference_cuda_kernels_same_box(vb):
     assert torch.equal(ref, vb.ops.nms(bd[:20000], sd[:20000], 0.5))
     x, rois, kw = workloads.cfg2_roi_align(channels=64)
     xd, rd = x.to(DEV), rois.to(DEV)
-    np.testing.assert_allclose(npy(vb.ops.roi_align(xd, rd, **kw)), npy(tv.ops.roi_align(xd, rd, **kw)), **F32_TOL)
+    _check_roi_align_vs_both_references(npy(vb.ops.roi_align(xd, rd, **kw)), npy(tv.ops.roi_align(xd, rd, **kw)),
+                                        npy(tv.ops.roi_align(x, rois, **kw)))
     o1, a1 = torch.ops.torchvision.roi_pool(xd, rd, 0.25, 7, 7)
     o2, a2 = torch.ops.vision_b200.roi_pool(xd, rd, 0.25, 7, 7)
     assert torch.equal(o1, o2) and torch.equal(a1, a2)

@@ -17,6 +17,7 @@
 //     persistent CTAs hold one whole H*W channel plane in shared memory (bulk
 //     async copy + mbarrier), every gather is an LDS, each input byte leaves
 //     HBM once and each output byte is written once.
+#include "async_copy.cuh"
 #include "common.cuh"
 
 namespace vb200 {
@@ -146,77 +147,83 @@ roi_align_generic_kernel(const T* __restrict__ input, const T* __restrict__ rois
 // ---------------------------------------------------------------------------
 // Plane-resident fp32 path.
 // ---------------------------------------------------------------------------
-// Packed per-axis geometry entry (8 B): bit31 = invalid, bit30 = (hi != lo),
-// bits[0,30) = offset of `lo` in floats (row entries are pre-multiplied by W).
-struct PackedEnt { uint32_t p; float l; };
+// Shared-memory image of one channel plane: rows at a padded pitch (a multiple of 4 floats whose
+// quarter is odd, so consecutive rows rotate through all eight 16-byte bank groups), pad columns
+// and two extra rows are zero.  Geometry entries are (offset, l) only:
+//   * border: the reference's "hi = lo = size-1, l = 0" is stored as lo = size-2, l = 1 (same value),
+//     so the high neighbour is ALWAYS at +1 / +pitch and needs no flag;
+//   * a sample outside [-1, size] points at the zero columns / zero rows, so it contributes 0
+//     without a validity select.
+struct PackedEnt { uint32_t off; float l; };   // off in floats (row entries: row * pitch)
+
+__host__ __device__ inline int plane_pitch(int W) {
+  int p = (W + 2 + 3) & ~3;
+  if (((p >> 2) & 1) == 0) p += 4;
+  return p;
+}
 
 __global__ void roi_align_geometry_kernel(const float* __restrict__ rois, PackedEnt* __restrict__ geo,
                                           int32_t* __restrict__ roi_batch, int K, int H, int W, int PH,
-                                          int PW, float scale, int sr, int aligned) {
+                                          int PW, float scale, int sr, int aligned, int pitch) {
   const int ent_per_roi = (PH + PW) * sr;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= K * ent_per_roi) return;
   const int n = t / ent_per_roi, e = t - n * ent_per_roi;
   const RoiGeom<float> g = roi_geometry<float, float>(rois + (int64_t)n * 5, scale, PH, PW, sr, aligned != 0, false);
   if (e == 0) roi_batch[n] = g.batch;
-  AxisEnt<float> a;
-  uint32_t mult;
-  if (e < PH * sr) { a = axis_entry<float>(sample_coord<float>(g.start_h, g.bin_h, e / sr, e % sr, sr), H); mult = (uint32_t)W; }
-  else { const int f = e - PH * sr; a = axis_entry<float>(sample_coord<float>(g.start_w, g.bin_w, f / sr, f % sr, sr), W); mult = 1u; }
+  const bool is_row = e < PH * sr;
+  const int f = is_row ? e : e - PH * sr;
+  const int size = is_row ? H : W;
+  const AxisEnt<float> a = is_row ? axis_entry<float>(sample_coord<float>(g.start_h, g.bin_h, f / sr, f % sr, sr), H)
+                                  : axis_entry<float>(sample_coord<float>(g.start_w, g.bin_w, f / sr, f % sr, sr), W);
+  int lo; float l;
+  if (a.lo < 0) { lo = size; l = 0.f; }                    // zero rows / zero columns
+  else if (a.hi == a.lo) { lo = size - 2; l = 1.f; }       // border: value is v[size-1]
+  else { lo = a.lo; l = a.l; }
   PackedEnt pe;
-  if (a.lo < 0) { pe.p = 0x80000000u; pe.l = 0.f; }
-  else { pe.p = (uint32_t)a.lo * mult | (a.hi != a.lo ? 0x40000000u : 0u); pe.l = a.l; }
+  pe.off = (uint32_t)(is_row ? lo * pitch : lo);
+  pe.l = l;
   geo[t] = pe;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr int kPlaneMaxThreads = 1024;
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk async copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0, 16 B aligned.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-constexpr int kPlaneThreads = 1024;
-constexpr uint32_t kBulkChunk = 32768;
-
-// Work = all (plane, roi) pairs in plane-major order, split evenly over the
-// persistent CTAs; a CTA (re)loads a plane only when its range crosses into it.
+// Work = all (plane, roi) pairs in plane-major order, split evenly over the persistent CTAs; a
+// CTA (re)loads a plane only when its range crosses into it.  blockDim.x = NT = a multiple of
+// nbins, so a thread keeps ONE bin position (ph, pw) for its whole life and walks RoIs with a
+// fixed stride: no index arithmetic in the loop, geometry for the next RoI is prefetched.
 template <int SR>
-__global__ void __launch_bounds__(kPlaneThreads, 1)
+__global__ void __launch_bounds__(kPlaneMaxThreads, 1)
 roi_align_plane_kernel(const float* __restrict__ input, const PackedEnt* __restrict__ geo,
                        const int32_t* __restrict__ roi_batch, float* __restrict__ output,
-                       int B, int C, int H, int W, int K, int PH, int PW, int plane_stride_f) {
+                       int B, int C, int H, int W, int K, int PH, int PW, int pitch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* plane = reinterpret_cast<float*>(smem_raw);
   __shared__ uint64_t bar;
 
-  const int HW = H * W;
+  const int tid = threadIdx.x, NT = blockDim.x;
   const int nbins = PH * PW;
   const int ent_per_roi = (PH + PW) * SR;
+  const int bin = tid % nbins, rl0 = tid / nbins, rstep = NT / nbins;
+  const int ph = bin / PW, pw = bin - ph * PW;
+  const int gy = ph * SR, gx = PH * SR + pw * SR;
+  const float inv_count = 1.0f / (float)(SR * SR);
   const float count = (float)(SR * SR);
+  const bool pow2 = (SR & (SR - 1)) == 0;
   const int64_t total = (int64_t)B * C * K;
   const int64_t per = (total + gridDim.x - 1) / gridDim.x;
   const int64_t w0 = (int64_t)blockIdx.x * per;
   const int64_t w1 = min(total, w0 + per);
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+  // zero the pad columns and the two zero rows once (bulk copies only ever write [0, W) of rows < H)
+  for (int r = tid; r < H; r += NT)
+    for (int c = W; c < pitch; ++c) plane[r * pitch + c] = 0.f;
+  for (int i = H * pitch + tid; i < (H + 2) * pitch + 2; i += NT) plane[i] = 0.f;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_proxy_async();
   __syncthreads();
   uint32_t parity = 0;
+  const uint32_t row_bytes = (uint32_t)W * 4u;
 
   int64_t w = w0;
   while (w < w1) {
@@ -224,62 +231,58 @@ roi_align_plane_kernel(const float* __restrict__ input, const PackedEnt* __restr
     const int r0 = (int)(w - (int64_t)pl * K);
     const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
     const int b = pl / C;
-    // ---- stage plane `pl` into shared memory (previous plane is dead: all threads synced) ----
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)HW * 4u;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&bar, bytes);
-      const char* src = reinterpret_cast<const char*>(input + (int64_t)pl * HW);
-      char* dst = reinterpret_cast<char*>(plane);
-      for (uint32_t o = 0; o < bytes; o += kBulkChunk)
-        bulk_g2s(dst + o, src + o, min(kBulkChunk, bytes - o), &bar);
+    // ---- stage plane `pl`: one bulk copy per row, issued by warp 0, all completing on `bar` ----
+    if (tid < 32) {
+      if (tid == 0) { fence_proxy_async(); mbar_expect_tx(&bar, row_bytes * (uint32_t)H); }
+      __syncwarp();
+      const float* src = input + (int64_t)pl * H * W;
+      for (int r = tid; r < H; r += 32) bulk_g2s(plane + r * pitch, src + (int64_t)r * W, row_bytes, &bar);
     }
     mbar_wait(&bar, parity);
     parity ^= 1u;
 
-    // ---- every thread owns (roi, bin) items of this plane ----
-    const int items = (r1 - r0) * nbins;
-    for (int it = threadIdx.x; it < items; it += kPlaneThreads) {
-      const int rl = it / nbins, bin = it - rl * nbins;
-      const int n = r0 + rl;
-      const int ph = bin / PW, pw = bin - ph * PW;
-      float res = 0.f;
-      if (__ldg(roi_batch + n) == b) {
-        const PackedEnt* __restrict__ ge = geo + (int64_t)n * ent_per_roi;
-        float sum = 0.f;
+    int n = r0 + rl0;
+    uint2 ey[SR], ex[SR];
+    if (n < r1) {
+      const uint2* ge = reinterpret_cast<const uint2*>(geo + (int64_t)n * ent_per_roi);
 #pragma unroll
-        for (int iy = 0; iy < SR; ++iy) {
-          const uint2 eyr = __ldg(reinterpret_cast<const uint2*>(ge + ph * SR + iy));
-          PackedEnt ey; ey.p = eyr.x; ey.l = __uint_as_float(eyr.y);
-          const bool vy = !(ey.p & 0x80000000u);
-          const uint32_t ro = ey.p & 0x3fffffffu;
-          const uint32_t dy = (ey.p & 0x40000000u) ? (uint32_t)W : 0u;
-          const float ly = ey.l, hy = vy ? 1.f - ly : 0.f;
-#pragma unroll
-          for (int ix = 0; ix < SR; ++ix) {
-            const uint2 exr = __ldg(reinterpret_cast<const uint2*>(ge + PH * SR + pw * SR + ix));
-            PackedEnt ex; ex.p = exr.x; ex.l = __uint_as_float(exr.y);
-            const bool vx = !(ex.p & 0x80000000u);
-            const uint32_t xo = ex.p & 0x3fffffffu;
-            const uint32_t dx = (ex.p & 0x40000000u) ? 1u : 0u;
-            const float lx = ex.l, hx = vx ? 1.f - lx : 0.f;
-            const uint32_t base = ro + xo;
-            const float v1 = plane[base], v2 = plane[base + dx];
-            const float v3 = plane[base + dy], v4 = plane[base + dy + dx];
-            const float top = fmaf(lx, v2, hx * v1);
-            const float bot = fmaf(lx, v4, hx * v3);
-            sum = fmaf(hy, top, sum);
-            sum = fmaf(ly, bot, sum);
-          }
-        }
-        res = __fdiv_rn(sum, count);
-        output[((int64_t)n * C + (pl - b * C)) * nbins + bin] = res;
-      }
+      for (int i = 0; i < SR; ++i) { ey[i] = __ldg(ge + gy + i); ex[i] = __ldg(ge + gx + i); }
     }
-    __syncthreads();   // plane buffer may be overwritten by the next bulk copy
+    float* __restrict__ outp = output + ((int64_t)n * C + (pl - b * C)) * nbins + bin;
+    const int64_t ostep = (int64_t)rstep * C * nbins;
+    for (; n < r1; n += rstep, outp += ostep) {
+      uint2 cy[SR], cx[SR];
+#pragma unroll
+      for (int i = 0; i < SR; ++i) { cy[i] = ey[i]; cx[i] = ex[i]; }
+      const int nn = n + rstep;
+      if (nn < r1) {                                   // prefetch the next RoI's entries
+        const uint2* ge = reinterpret_cast<const uint2*>(geo + (int64_t)nn * ent_per_roi);
+#pragma unroll
+        for (int i = 0; i < SR; ++i) { ey[i] = __ldg(ge + gy + i); ex[i] = __ldg(ge + gx + i); }
+      }
+      if (B > 1 && __ldg(roi_batch + n) != b) continue;
+      float sum = 0.f;
+#pragma unroll
+      for (int iy = 0; iy < SR; ++iy) {
+        const float ly = __uint_as_float(cy[iy].y), hy = 1.f - ly;
+        const float* __restrict__ rowp = plane + cy[iy].x;
+#pragma unroll
+        for (int ix = 0; ix < SR; ++ix) {
+          const float lx = __uint_as_float(cx[ix].y), hx = 1.f - lx;
+          const float* __restrict__ q = rowp + cx[ix].x;
+          const float v1 = q[0], v2 = q[1];
+          const float v3 = q[pitch], v4 = q[pitch + 1];
+          const float top = fmaf(lx, v2, hx * v1);
+          const float bot = fmaf(lx, v4, hx * v3);
+          sum = fmaf(hy, top, sum);
+          sum = fmaf(ly, bot, sum);
+        }
+      }
+      *outp = pow2 ? sum * inv_count : __fdiv_rn(sum, count);
+    }
+    __syncthreads();   // plane buffer may be overwritten by the next bulk copies
     w += (r1 - r0);
   }
-  (void)plane_stride_f;
 }
 
 // ---------------------------------------------------------------------------
@@ -389,10 +392,11 @@ namespace {
 bool roi_align_use_plane(int dtype, const void* input, int batch, int channels, int height, int width,
                          int num_rois, int sampling_ratio) {
   if (dtype != VB200_F32) return false;
-  const size_t plane_bytes = (size_t)height * width * 4;
+  if (height < 2 || width < 2) return false;
+  const size_t plane_bytes = ((size_t)(height + 2) * plane_pitch(width) + 2) * 4;
   const bool fits = plane_bytes + 1024 <= (size_t)max_smem_optin();
   const bool sr_ok = sampling_ratio >= 1 && sampling_ratio <= 4;
-  const bool align_ok = plane_bytes % 16 == 0 && (input == nullptr || ((uintptr_t)input % 16) == 0);
+  const bool align_ok = width % 4 == 0 && (input == nullptr || ((uintptr_t)input % 16) == 0);
   const int64_t pairs = (int64_t)batch * channels * num_rois;
   bool use_plane = fits && sr_ok && align_ok && pairs >= 4096;
   const char* force = getenv("VB200_ROI_ALIGN_PATH");   // "generic" | "plane" (testing / profiling)
@@ -430,9 +434,12 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
     const size_t geo_pad = roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio);
     const bool use_plane = roi_align_use_plane(dtype, input, batch, channels, height, width, num_rois, sampling_ratio) &&
                            workspace != nullptr && workspace_bytes >= geo_pad + (size_t)num_rois * 4 &&
-                           ((uintptr_t)workspace % 16) == 0;
+                           ((uintptr_t)workspace % 16) == 0 && pooled_h * pooled_w <= kPlaneMaxThreads;
     if (use_plane) {
-      const size_t plane_bytes = (size_t)height * width * 4;
+      const int pitch = plane_pitch(width);
+      const size_t plane_bytes = ((size_t)(height + 2) * pitch + 2) * 4;
+      const int nbins = pooled_h * pooled_w;
+      const int nthreads = nbins <= kPlaneMaxThreads ? (kPlaneMaxThreads / nbins) * nbins : 0;
       const int64_t pairs = (int64_t)batch * channels * num_rois;
       const int ent = (pooled_h + pooled_w) * sampling_ratio;
       PackedEnt* geo = (PackedEnt*)workspace;
@@ -440,7 +447,7 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       const int nt = num_rois * ent;
       roi_align_geometry_kernel<<<ceil_div(nt, 256), 256, 0, st>>>((const float*)rois, geo, rb, num_rois, height,
                                                                    width, pooled_h, pooled_w, (float)spatial_scale,
-                                                                   sampling_ratio, aligned);
+                                                                   sampling_ratio, aligned, pitch);
       int rc = check_launch("roi_align_geometry_kernel");
       if (rc) return rc;
       const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
@@ -449,9 +456,9 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
   {                                                                                                                \
     VB200_CUDA_TRY(cudaFuncSetAttribute(roi_align_plane_kernel<SR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                         (int)smem));                                                               \
-    roi_align_plane_kernel<SR><<<grid, kPlaneThreads, smem, st>>>((const float*)input, geo, rb, (float*)output,    \
-                                                                  batch, channels, height, width, num_rois,       \
-                                                                  pooled_h, pooled_w, 0);                         \
+    roi_align_plane_kernel<SR><<<grid, nthreads, smem, st>>>((const float*)input, geo, rb, (float*)output,         \
+                                                             batch, channels, height, width, num_rois,            \
+                                                             pooled_h, pooled_w, pitch);                          \
   }
       switch (sampling_ratio) {
         case 1: VB200_LAUNCH_PLANE(1) break;
