@@ -39,10 +39,10 @@ else:
 for _ in range(2):
     fn()
 torch.cuda.synchronize()
-s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-s.record()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
 for _ in range(iters):
     fn()
-e.record()
+ev1.record()
 torch.cuda.synchronize()
-print(f"{op}: {s.elapsed_time(e) / iters:.4f} ms/iter over {iters} iters (warm L2)")
+print(f"{op}: {ev0.elapsed_time(ev1) / iters:.4f} ms/iter over {iters} iters (warm L2)")

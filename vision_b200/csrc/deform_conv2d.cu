@@ -17,13 +17,10 @@
 //   * tcgen05 kernel (deform_conv2d_tc.cu): same decomposition with the B slab written
 //     as a swizzled bf16 K-major tile and the contraction on the 5th-gen tensor cores.
 #include "common.cuh"
+#include "dcn_params.h"
 
 namespace vb200 {
 
-struct DcnParams {
-  int batch, c_in, in_h, in_w, c_out, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
-  int groups, offset_groups, use_mask, out_h, out_w;
-};
 
 namespace {
 

@@ -1,9 +1,380 @@
-// deform_conv2d_tc.cu — tcgen05 tensor-core path for deform_conv2d (placeholder: not yet enabled).
+// deform_conv2d_tc.cu — tcgen05 (5th-gen tensor core) path for deform_conv2d, 16-bit storage types.
+//
+// Reference: csrc/ops/cuda/deform_conv2d_kernel.cu:136-209 (deformable_im2col writes a
+// [C_in*kh*kw, pixels] buffer to HBM) + :1234-1239 (cuBLAS addmm) + transpose/copy/bias passes.
+//
+// Here the op is ONE implicit GEMM whose gathered operand never touches HBM:
+//     D[pixel, cout] = sum_k A[pixel, k] * Wt[cout, k],   k = (channel slab, tap, channel in slab)
+//   * M = 128 output pixels (TMEM lanes), N = BN output channels (TMEM fp32 columns), K step 64;
+//   * A tiles are SYNTHESISED by 8 gather warps: per (pixel, tap) the 4 bilinear corner offsets and
+//     weights (x modulation mask) come from a per-CTA table built once; channels are the fastest
+//     axis of a channels-last staging copy of the input, so every corner read is a 128-bit vector
+//     load of 8 consecutive channels; the fp32 blend is rounded to bf16/fp16 and stored into the
+//     128B-swizzled K-major shared-memory tile the tensor core descriptor expects;
+//   * B (weights) tiles are pre-packed once per call into the exact swizzled shared-memory image,
+//     so a stage is filled by one 1-D bulk async copy (TMA engine) completing on an mbarrier;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, fp32 accumulate in TMEM);
+//     tcgen05.commit hands stages back to the producers and signals the epilogue;
+//   * epilogue: tcgen05.ld 32 lanes x 16 columns, + bias, round, coalesced NCHW stores.
+// Pipeline: 3 stages x (A 16 KB + B BN*128 B), full(A)/full(B)/empty mbarriers per stage.
+#include "async_copy.cuh"
 #include "common.cuh"
+#include "dcn_params.h"
 
 namespace vb200 {
-struct DcnParams;
-int deform_conv2d_tc_try(const void*, const void*, const void*, const void*, const void*, void*, int, const DcnParams&,
-                         void*, size_t, cudaStream_t) { return 0; }
-size_t deform_conv2d_tc_workspace(int, const DcnParams&) { return 0; }
+
+
+namespace {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_GATHER_WARPS = 8;
+constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
+constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp
+constexpr int TC_A_BYTES = TC_BM * 128;                      // 128 rows x 64 x 2 B
+
+// ---- pre-pass 1: NCHW -> NHWC (16-bit elements) -------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int HW) {
+  __shared__ T tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const T* __restrict__ src = in + (int64_t)b * C * HW;
+  T* __restrict__ dst = out + (int64_t)b * C * HW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, p = p0 + tx;
+    if (c < C && p < HW) tile[ty + i * 8][tx] = src[(int64_t)c * HW + p];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + i * 8, c = c0 + tx;
+    if (c < C && p < HW) dst[(int64_t)p * C + c] = tile[tx][ty + i * 8];
+  }
+}
+
+// ---- pre-pass 2: weights [Cout][Cin][KK] -> swizzled K-major tiles ---------------------------
+// tile (nt, s): BN rows x 64 k, byte offset inside = r*128 + ((kc/8) ^ (r&7))*16 + (kc%8)*2,
+// slab s = cslab*KK + tap holds k = channels [cslab*64, +64) of tap `tap`.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const T* __restrict__ w, T* __restrict__ packed, int Cout, int Cin, int KK, int BN) {
+  const int64_t total = (int64_t)Cout * Cin * KK;
+  const int n_slabs = (Cin / 64) * KK;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % KK);
+    const int ci = (int)((e / KK) % Cin);
+    const int co = (int)(e / KK / Cin);
+    const int nt = co / BN, r = co % BN;
+    const int cslab = ci / 64, kc = ci % 64;
+    const int s = cslab * KK + tap;
+    const int64_t tile_base = ((int64_t)nt * n_slabs + s) * BN * 64;
+    const int off_bytes = r * 128 + (((kc >> 3) ^ (r & 7)) << 4) + ((kc & 7) << 1);
+    packed[tile_base + (off_bytes >> 1)] = w[e];
+  }
+}
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major: 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr uint32_t kFmt = 1;
+  static __device__ __forceinline__ float2 up(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+  static __device__ __forceinline__ uint32_t pk(float a, float b) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+};
+template <> struct Elem<__half> {
+  static constexpr uint32_t kFmt = 0;
+  static __device__ __forceinline__ float2 up(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+  static __device__ __forceinline__ uint32_t pk(float a, float b) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
+};
+
+struct TcEnt { int o[4]; float w[4]; };   // clamped corner pixel indices (y*W+x) + bilinear weights x mask
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacked, const T* __restrict__ offset,
+                        const T* __restrict__ mask, const T* __restrict__ bias, T* __restrict__ out, DcnParams p) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* stages = smem;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(stages + TC_STAGES * STAGE_BYTES);
+  uint64_t* fullB = fullA + TC_STAGES;
+  uint64_t* empty = fullB + TC_STAGES;
+  uint64_t* accum_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  TcEnt* tab = reinterpret_cast<TcEnt*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);   // [KK][128]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KK = p.kh * p.kw;
+  const int HWo = p.out_h * p.out_w, HWi = p.in_h * p.in_w;
+  const int tiles_per_img = ceil_div(HWo, TC_BM);
+  const int b = blockIdx.x / tiles_per_img;
+  const int pix0 = (blockIdx.x % tiles_per_img) * TC_BM;
+  const int nt = blockIdx.y;
+  const int c_per_off = p.c_in / p.offset_groups;
+  const int slabs_per_og = (c_per_off / 64) * KK;
+  const int n_slabs = (p.c_in / 64) * KK;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&fullA[s], TC_GATHER_WARPS); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == TC_GATHER_WARPS + 1) tmem_alloc(tmem_slot, BN);     // whole warp, .sync.aligned
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_GATHER_WARPS) {
+    // ================= gather warps: build A tiles =================
+    const int prow = tid >> 1, half = tid & 1;               // pixel row of the tile, 32-channel half
+    const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
+    int slab = 0;
+    for (int og = 0; og < p.offset_groups; ++og) {
+      // ---- sampling table for this offset group: [KK][128] ----
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));      // previous table no longer read
+      const T* __restrict__ off_b = offset + ((int64_t)b * p.offset_groups + og) * 2 * KK * HWo;
+      const T* __restrict__ msk_b = p.use_mask ? mask + ((int64_t)b * p.offset_groups + og) * KK * HWo : nullptr;
+      for (int e = tid; e < KK * TC_BM; e += TC_GATHER_THREADS) {
+        const int tap = e / TC_BM, px = e - tap * TC_BM;
+        const int pix = pix0 + px;
+        TcEnt se;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { se.o[q] = 0; se.w[q] = 0.f; }
+        if (pix < HWo) {
+          const int oy = pix / p.out_w, ox = pix - oy * p.out_w;
+          const int i = tap / p.kw, j = tap - i * p.kw;
+          const float oh = to_acc(off_b[(int64_t)(2 * tap) * HWo + pix]);
+          const float ow = to_acc(off_b[(int64_t)(2 * tap + 1) * HWo + pix]);
+          const float mv = p.use_mask ? to_acc(msk_b[(int64_t)tap * HWo + pix]) : 1.f;
+          const float y = add_rn((float)(oy * p.stride_h - p.pad_h + i * p.dil_h), oh);
+          const float x = add_rn((float)(ox * p.stride_w - p.pad_w + j * p.dil_w), ow);
+          if (!(y <= -1.f || (float)p.in_h <= y || x <= -1.f || (float)p.in_w <= x)) {
+            const int hl = (int)floorf(y), wl = (int)floorf(x);
+            const int hh_i = hl + 1, wh_i = wl + 1;
+            const float lh = y - (float)hl, lw = x - (float)wl;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
+            const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
+            se.o[0] = hlc * p.in_w + wlc; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = hlc * p.in_w + whc; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = hhc * p.in_w + wlc; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = hhc * p.in_w + whc; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+          }
+        }
+        tab[e] = se;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
+      // ---- slabs of this offset group: channel slab outer, tap inner (L1 reuse across taps) ----
+      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
+        const int cs_local = sl / KK, tap = sl - cs_local * KK;
+        const int ch0 = og * c_per_off + cs_local * 64 + half * 32;
+        const int st = slab % TC_STAGES;
+        const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        const TcEnt se = tab[tap * TC_BM + prow];
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float wq = se.w[q];
+          const uint4* __restrict__ src = reinterpret_cast<const uint4*>(in_b + (int64_t)se.o[q] * p.c_in + ch0);
+          uint4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = Elem<T>::up(u[k]);
+              acc[j * 8 + k * 2] = fmaf(wq, f.x, acc[j * 8 + k * 2]);
+              acc[j * 8 + k * 2 + 1] = fmaf(wq, f.y, acc[j * 8 + k * 2 + 1]);
+            }
+          }
+        }
+        unsigned char* a_row = stages + st * STAGE_BYTES + prow * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = Elem<T>::pk(acc[j * 8 + 0], acc[j * 8 + 1]);
+          o.y = Elem<T>::pk(acc[j * 8 + 2], acc[j * 8 + 3]);
+          o.z = Elem<T>::pk(acc[j * 8 + 4], acc[j * 8 + 5]);
+          o.w = Elem<T>::pk(acc[j * 8 + 6], acc[j * 8 + 7]);
+          const int chunk = half * 4 + j;
+          *reinterpret_cast<uint4*>(a_row + ((chunk ^ (prow & 7)) << 4)) = o;
+        }
+        fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&fullA[st]);
+      }
+    }
+    // ================= epilogue: TMEM -> registers -> NCHW =================
+    mbar_wait(accum_full, 0u);
+    tc_fence_after();
+    const int lane_base = (warp & 3) * 32;
+    const int col_half = warp >> 2;                           // warps 0-3: first half of the columns, 4-7: second
+    const int pix = pix0 + lane_base + lane;
+    constexpr int COLS_PER_WARP = BN / 2;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
+      const int col = col_half * COLS_PER_WARP + c0;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
+      if (pix < HWo) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = nt * BN + col + j;
+          const float bv = bias ? to_acc(bias[co]) : 0.f;
+          out[((int64_t)b * p.c_out + co) * HWo + pix] = from_acc<T, float>(__uint_as_float(r[j]) + bv);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == TC_GATHER_WARPS) {
+    // ================= weight tiles: one bulk copy per stage =================
+    if (lane == 0) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wpacked) + (int64_t)nt * n_slabs * B_BYTES;
+      for (int slab = 0; slab < n_slabs; ++slab) {
+        const int st = slab % TC_STAGES;
+        const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_expect_tx(&fullB[st], (uint32_t)B_BYTES);
+        bulk_g2s(stages + st * STAGE_BYTES + TC_A_BYTES, wsrc + (int64_t)slab * B_BYTES, (uint32_t)B_BYTES, &fullB[st]);
+      }
+    }
+  } else {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | K-major A,B |
+      // n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (Elem<T>::kFmt << 7) | (Elem<T>::kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int slab = 0; slab < n_slabs; ++slab) {
+        const int st = slab % TC_STAGES;
+        const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
+        mbar_wait(&fullA[st], ph);
+        mbar_wait(&fullB[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(stages + st * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)
+          umma_f16(tmem_base, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + k * 32), idesc, (slab | k) ? 1u : 0u);
+        umma_commit(&empty[st]);               // stage reusable once these MMAs have read it
+      }
+      umma_commit(accum_full);                 // all MMAs complete -> epilogue may read TMEM
+    }
+  }
+  __syncthreads();
+  if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+template <int BN> constexpr size_t tc_smem_bytes(int KK) {
+  return (size_t)TC_STAGES * (TC_A_BYTES + BN * 128) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
+}
+
+bool tc_eligible(int dtype, const DcnParams& p) {
+  if (dtype != VB200_BF16 && dtype != VB200_F16) return false;
+  if (p.groups != 1) return false;
+  if (p.c_in % p.offset_groups != 0 || (p.c_in / p.offset_groups) % 64 != 0) return false;
+  if (p.c_out % 128 != 0) return false;
+  const int KK = p.kh * p.kw;
+  const size_t smem = (p.c_out % 256 == 0) ? tc_smem_bytes<256>(KK) : tc_smem_bytes<128>(KK);
+  if (smem > (size_t)max_smem_optin()) return false;
+  if ((int64_t)p.in_h * p.in_w * p.c_in >= (1ll << 31)) return false;
+  const char* env = getenv("VB200_DCN_PATH");
+  if (env && env[0] == 's') return false;
+  return true;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+template <typename T>
+int launch_tc(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
+              const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
+  const size_t nhwc_bytes = align256((size_t)p.batch * HWi * p.c_in * sizeof(T));
+  const size_t w_bytes = align256((size_t)p.c_out * p.c_in * KK * sizeof(T));
+  if (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0) {
+    set_error("deform_conv2d: tensor-core path needs %zu bytes of 256-byte aligned workspace", nhwc_bytes + w_bytes);
+    return VB200_EWORKSPACE;
+  }
+  T* nhwc = (T*)workspace;
+  T* wpacked = (T*)((char*)workspace + nhwc_bytes);
+  dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
+  nchw_to_nhwc_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
+  int rc = check_launch("nchw_to_nhwc_kernel");
+  if (rc) return rc;
+  const int BN = (p.c_out % 256 == 0) ? 256 : 128;
+  pack_weights_kernel<T><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+  rc = check_launch("pack_weights_kernel");
+  if (rc) return rc;
+  dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
+  if (BN == 256) {
+    const size_t smem = tc_smem_bytes<256>(KK);
+    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    deform_conv2d_tc_kernel<T, 256><<<grid, TC_THREADS, smem, st>>>(nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);
+  } else {
+    const size_t smem = tc_smem_bytes<128>(KK);
+    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    deform_conv2d_tc_kernel<T, 128><<<grid, TC_THREADS, smem, st>>>(nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);
+  }
+  rc = check_launch("deform_conv2d_tc_kernel");
+  return rc ? rc : 1;
+}
+
+}  // namespace
+
+size_t deform_conv2d_tc_workspace(int dtype, const DcnParams& p) {
+  if (!tc_eligible(dtype, p)) return 0;
+  const size_t nhwc = align256((size_t)p.batch * p.in_h * p.in_w * p.c_in * 2);
+  const size_t w = align256((size_t)p.c_out * p.c_in * p.kh * p.kw * 2);
+  return nhwc + w;
+}
+
+int deform_conv2d_tc_try(const void* input, const void* weight, const void* offset, const void* mask, const void* bias,
+                         void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!tc_eligible(dtype, p)) return 0;
+  if (dtype == VB200_BF16)
+    return launch_tc<__nv_bfloat16>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);
+  return launch_tc<__half>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);
+}
+
 }  // namespace vb200

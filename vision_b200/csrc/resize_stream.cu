@@ -78,8 +78,9 @@ template <> struct Pair<__nv_bfloat16> {
 };
 
 // T: 16-bit storage type.  LW: 32-bit words (pixel pairs) each thread reads per row.
-template <typename T, int LW>
-__global__ void __launch_bounds__((kMaxConsumerWarps + 1) * 32, 1)
+// NW: consumer warps the kernel is compiled for (block = (n_cwarps + 1) * 32 <= (NW + 1) * 32).
+template <typename T, int LW, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 && LW <= 10) ? 3 : 1)
 resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamParams p, int n_cwarps) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [stages][row_pitch] | full[S] empty[S] | totx[OW] xminx[OW] xmcx[OW] | toty.. | rowA[band] rowB[band] rowK[band]
@@ -136,12 +137,13 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   if (warp == n_cwarps) {
     // ===== producer warp: one elected lane streams the band's rows through the ring =====
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int rl = 0; rl < nrows; ++rl) {
-        const int s = rl % p.n_stages;
-        const uint32_t ph = (uint32_t)(rl / p.n_stages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], row_bytes);
         bulk_g2s(stages + (size_t)s * p.row_pitch, src + (int64_t)rl * p.in_w, row_bytes, &full[s]);
+        if (++s == p.n_stages) { s = 0; ph ^= 1u; }
       }
     }
     return;
@@ -168,11 +170,12 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
 
   float acc_lo = 0.f, acc_hi = 0.f;
   int k_cur = oy0;
+  int s = 0;
+  uint32_t ph = 0;
+  const unsigned char* stage_ptr = stages + (size_t)word0 * 4;
   for (int rl = 0; rl < nrows; ++rl) {
-    const int s = rl % p.n_stages;
-    const uint32_t ph = (uint32_t)(rl / p.n_stages) & 1u;
     mbar_wait(&full[s], ph);
-    const uint32_t* __restrict__ rowp = reinterpret_cast<const uint32_t*>(stages + (size_t)s * p.row_pitch) + word0;
+    const uint32_t* __restrict__ rowp = reinterpret_cast<const uint32_t*>(stage_ptr);
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
     for (int t = 0; t < LW; ++t) {
@@ -182,6 +185,7 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == p.n_stages) { s = 0; ph ^= 1u; stage_ptr = stages + (size_t)word0 * 4; } else stage_ptr += p.row_pitch;
     const float A = a0 + a1, B = b0 + b1;
     const float h = A + __shfl_down_sync(0xffffffffu, B, 1);
     const int k = rowK[rl];
@@ -198,14 +202,14 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   if (writer && k_cur < oy1 && k_cur >= oy0) dst[(int64_t)k_cur * p.out_w] = from_acc<T, float>(acc_hi);
 }
 
-template <typename T, int LW>
+template <typename T, int LW, int NW>
 int launch_stream(const void* in, void* out, int64_t planes, const StreamParams& p0, cudaStream_t st) {
   StreamParams p = p0;
   const int n_cwarps = ceil_div(p.out_w + 1, 31);
   const uint32_t row_bytes = (uint32_t)p.in_w * sizeof(T);
   p.row_pitch = (int)((row_bytes + LW * 4 + 4 + 127) & ~127u);
   // split the output rows so that the grid has a few waves of CTAs even for small batches
-  const int64_t want_ctas = (int64_t)sm_count() * 2 * 3;
+  const int64_t want_ctas = (int64_t)sm_count() * 3 * 2;
   int splits = (int)((want_ctas + planes - 1) / planes);
   splits = splits < 1 ? 1 : (splits > p.out_h ? p.out_h : splits);
   if (splits > 1 && p.out_h / splits < 8) splits = p.out_h / 8 > 0 ? p.out_h / 8 : 1;   // keep halo overhead <= ~12 %
@@ -220,18 +224,20 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
   }
   p.band_cap = (band_rows + 31) & ~31;
   const size_t fixed = (size_t)(p.out_w + p.out_h) * 12 + (size_t)p.band_cap * 12 + 256;
-  const size_t budget = ((size_t)max_smem_optin() - 2048) / 2;            // two CTAs per SM
+  const int ctas_per_sm = (NW <= 8 && LW <= 10) ? 3 : 2;
+  const size_t budget = ((size_t)max_smem_optin() - 3072) / ctas_per_sm - 1024;   // smem per CTA (1 KB reserved each)
+  if (budget < fixed + 3 * (size_t)p.row_pitch) return 0;
   int stages = (int)((budget - fixed) / p.row_pitch);
-  stages = stages > 12 ? 12 : stages;
+  stages = stages > 8 ? 8 : stages;
   if (stages < 3) return 0;
   p.n_stages = stages;
   const size_t smem = (size_t)stages * p.row_pitch + (size_t)stages * 16 + fixed;
-  VB200_CUDA_TRY(cudaFuncSetAttribute(resize_aa_stream_kernel<T, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VB200_CUDA_TRY(cudaFuncSetAttribute(resize_aa_stream_kernel<T, LW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t done = 0;
   while (done < planes) {
     const int64_t chunk = planes - done < 65535 ? planes - done : 65535;
     dim3 grid((unsigned)splits, (unsigned)chunk);
-    resize_aa_stream_kernel<T, LW><<<grid, (n_cwarps + 1) * 32, smem, st>>>(
+    resize_aa_stream_kernel<T, LW, NW><<<grid, (n_cwarps + 1) * 32, smem, st>>>(
         (const T*)in + done * (int64_t)p.in_h * p.in_w, (T*)out + done * (int64_t)p.out_h * p.out_w, p, n_cwarps);
     int rc = check_launch("resize_aa_stream_kernel");
     if (rc) return rc;
@@ -244,10 +250,18 @@ template <typename T>
 int dispatch_lw(const void* in, void* out, int64_t planes, const StreamParams& p, cudaStream_t st) {
   // a thread owns at most floor(scale)+1 pixels, +1 slot for word alignment
   const int need = ((int)floorf(p.scale_w) + 1 + 1 + 1) / 2;
-  if (need <= 4) return launch_stream<T, 4>(in, out, planes, p, st);
-  if (need <= 6) return launch_stream<T, 6>(in, out, planes, p, st);
-  if (need <= 10) return launch_stream<T, 10>(in, out, planes, p, st);
-  if (need <= 16) return launch_stream<T, 16>(in, out, planes, p, st);
+  const bool small = ceil_div(p.out_w + 1, 31) <= 8;
+  if (small) {
+    if (need <= 4) return launch_stream<T, 4, 8>(in, out, planes, p, st);
+    if (need <= 6) return launch_stream<T, 6, 8>(in, out, planes, p, st);
+    if (need <= 10) return launch_stream<T, 10, 8>(in, out, planes, p, st);
+    if (need <= 16) return launch_stream<T, 16, 8>(in, out, planes, p, st);
+    return 0;
+  }
+  if (need <= 4) return launch_stream<T, 4, kMaxConsumerWarps>(in, out, planes, p, st);
+  if (need <= 6) return launch_stream<T, 6, kMaxConsumerWarps>(in, out, planes, p, st);
+  if (need <= 10) return launch_stream<T, 10, kMaxConsumerWarps>(in, out, planes, p, st);
+  if (need <= 16) return launch_stream<T, 16, kMaxConsumerWarps>(in, out, planes, p, st);
   return 0;
 }
 
