@@ -23,7 +23,7 @@ namespace vb200 {
 namespace {
 
 constexpr int kMaxConsumerWarps = 16;
-constexpr int kMaxBandRows = 4096;   // upper bound on band_cap
+constexpr int kMaxBandRows = 1024;   // upper bound on band_cap (keeps the per-row tables at 12 KB)
 
 struct StreamParams {
   int in_h, in_w, out_h, out_w;
