@@ -26,7 +26,7 @@ namespace vb200 {
 
 namespace {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_GATHER_WARPS = 8;
+constexpr int TC_BM = 128, TC_BK = 64, TC_GATHER_WARPS = 8;
 constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
 constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp
 constexpr int TC_A_BYTES = TC_BM * 128;                      // 128 rows x 64 x 2 B
@@ -124,7 +124,9 @@ template <> struct Elem<__half> {
 
 struct TcEnt { int o[4]; float w[4]; };   // clamped corner pixel indices (y*W+x) + bilinear weights x mask
 
-template <typename T, int BN>
+// BN = output channels per CTA: 128 / 256 (one accumulator, 3 stages) or 512 (two 256-column
+// accumulators = all of TMEM, 2 stages; the A tile is then gathered once per pixel tile).
+template <typename T, int BN, int TC_STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacked, const T* __restrict__ offset,
                         const T* __restrict__ mask, const T* __restrict__ bias, T* __restrict__ out, DcnParams p) {
@@ -163,7 +165,10 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 
   if (warp < TC_GATHER_WARPS) {
     // ================= gather warps: build A tiles =================
-    const int prow = tid >> 1, half = tid & 1;               // pixel row of the tile, 32-channel half
+    // lane = (pixel sub-index pq, 16-byte chunk c): one warp load instruction reads four complete
+    // 128-byte lines (4 pixels x 64 channels) instead of sixteen quarter lines.
+    const int cchunk = lane & 7, pq = lane >> 3;
+    const int prow0 = warp * 16 + pq;                        // + 4 * i, i = 0..3
     const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
     int slab = 0;
     for (int og = 0; og < p.offset_groups; ++og) {
@@ -192,10 +197,10 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
             const float hh = 1.f - lh, hw = 1.f - lw;
             const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
             const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
-            se.o[0] = hlc * p.in_w + wlc; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
-            se.o[1] = hlc * p.in_w + whc; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
-            se.o[2] = hhc * p.in_w + wlc; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
-            se.o[3] = hhc * p.in_w + whc; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+            se.o[0] = (hlc * p.in_w + wlc) * p.c_in; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = (hlc * p.in_w + whc) * p.c_in; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = (hhc * p.in_w + wlc) * p.c_in; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = (hhc * p.in_w + whc) * p.c_in; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
           }
         }
         tab[e] = se;
@@ -204,42 +209,44 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
       // ---- slabs of this offset group: channel slab outer, tap inner (L1 reuse across taps) ----
       for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
         const int cs_local = sl / KK, tap = sl - cs_local * KK;
-        const int ch0 = og * c_per_off + cs_local * 64 + half * 32;
+        const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
         const int st = slab % TC_STAGES;
         const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
+        uint4 v[4][4];                                       // [pixel][corner]
+        float4 wq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                        // all 16 loads in flight before the blend
+          const TcEnt* se = tab + tap * TC_BM + prow0 + 4 * i;
+          const int4 o = *reinterpret_cast<const int4*>(se->o);
+          wq[i] = *reinterpret_cast<const float4*>(se->w);
+          v[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c + o.x));
+          v[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c + o.y));
+          v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + o.z));
+          v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + o.w));
+        }
         mbar_wait(&empty[st], ph ^ 1u);
-        const TcEnt se = tab[tap * TC_BM + prow];
-        float acc[32];
+        unsigned char* a_tile = stages + st * STAGE_BYTES;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        for (int i = 0; i < 4; ++i) {
+          const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
+          float acc[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float wq = se.w[q];
-          const uint4* __restrict__ src = reinterpret_cast<const uint4*>(in_b + (int64_t)se.o[q] * p.c_in + ch0);
-          uint4 v[4];
+          for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t u[4] = {v[i][q].x, v[i][q].y, v[i][q].z, v[i][q].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = Elem<T>::up(u[k]);
-              acc[j * 8 + k * 2] = fmaf(wq, f.x, acc[j * 8 + k * 2]);
-              acc[j * 8 + k * 2 + 1] = fmaf(wq, f.y, acc[j * 8 + k * 2 + 1]);
+              acc[2 * k] = fmaf(wv[q], f.x, acc[2 * k]);
+              acc[2 * k + 1] = fmaf(wv[q], f.y, acc[2 * k + 1]);
             }
           }
-        }
-        unsigned char* a_row = stages + st * STAGE_BYTES + prow * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
           uint4 o;
-          o.x = Elem<T>::pk(acc[j * 8 + 0], acc[j * 8 + 1]);
-          o.y = Elem<T>::pk(acc[j * 8 + 2], acc[j * 8 + 3]);
-          o.z = Elem<T>::pk(acc[j * 8 + 4], acc[j * 8 + 5]);
-          o.w = Elem<T>::pk(acc[j * 8 + 6], acc[j * 8 + 7]);
-          const int chunk = half * 4 + j;
-          *reinterpret_cast<uint4*>(a_row + ((chunk ^ (prow & 7)) << 4)) = o;
+          o.x = Elem<T>::pk(acc[0], acc[1]); o.y = Elem<T>::pk(acc[2], acc[3]);
+          o.z = Elem<T>::pk(acc[4], acc[5]); o.w = Elem<T>::pk(acc[6], acc[7]);
+          const int prow = prow0 + 4 * i;
+          *reinterpret_cast<uint4*>(a_tile + prow * 128 + ((cchunk ^ (prow & 7)) << 4)) = o;
         }
         fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -285,7 +292,8 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     if (lane == 0) {
       // cute::UMMA::InstrDescriptor: c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | K-major A,B |
       // n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (Elem<T>::kFmt << 7) | (Elem<T>::kFmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      constexpr int MMA_N = BN > 256 ? 256 : BN;
+      const uint32_t idesc = (1u << 4) | (Elem<T>::kFmt << 7) | (Elem<T>::kFmt << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int slab = 0; slab < n_slabs; ++slab) {
         const int st = slab % TC_STAGES;
         const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
@@ -295,8 +303,12 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         const uint32_t a_addr = smem_u32(stages + st * STAGE_BYTES);
         const uint32_t b_addr = a_addr + TC_A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
+        for (int k = 0; k < TC_BK / 16; ++k) {
           umma_f16(tmem_base, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + k * 32), idesc, (slab | k) ? 1u : 0u);
+          if constexpr (BN > 256)       // second accumulator: output channels [256, 512) -> TMEM columns [256, 512)
+            umma_f16(tmem_base + 256u, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + 256 * 128 + k * 32), idesc,
+                     (slab | k) ? 1u : 0u);
+        }
         umma_commit(&empty[st]);               // stage reusable once these MMAs have read it
       }
       umma_commit(accum_full);                 // all MMAs complete -> epilogue may read TMEM
@@ -306,8 +318,22 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
   if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
-template <int BN> constexpr size_t tc_smem_bytes(int KK) {
-  return (size_t)TC_STAGES * (TC_A_BYTES + BN * 128) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
+constexpr int tc_stages(int BN) { return BN > 256 ? 2 : 3; }
+size_t tc_smem_bytes(int BN, int KK) {
+  return (size_t)tc_stages(BN) * (TC_A_BYTES + BN * 128) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
+}
+int tc_pick_bn(const DcnParams& p) {
+  const char* env = getenv("VB200_DCN_BN");           // profiling override: 128 / 256 / 512
+  const int KK = p.kh * p.kw;
+  const int cands[3] = {512, 256, 128};
+  for (int c = 0; c < 3; ++c) {
+    const int bn = cands[c];
+    if (env && atoi(env) != bn) continue;
+    if (p.c_out % bn == 0 && tc_smem_bytes(bn, KK) <= (size_t)max_smem_optin()) return bn;
+  }
+  for (int c = 0; c < 3; ++c)
+    if (p.c_out % cands[c] == 0 && tc_smem_bytes(cands[c], KK) <= (size_t)max_smem_optin()) return cands[c];
+  return 0;
 }
 
 bool tc_eligible(int dtype, const DcnParams& p) {
@@ -315,9 +341,7 @@ bool tc_eligible(int dtype, const DcnParams& p) {
   if (p.groups != 1) return false;
   if (p.c_in % p.offset_groups != 0 || (p.c_in / p.offset_groups) % 64 != 0) return false;
   if (p.c_out % 128 != 0) return false;
-  const int KK = p.kh * p.kw;
-  const size_t smem = (p.c_out % 256 == 0) ? tc_smem_bytes<256>(KK) : tc_smem_bytes<128>(KK);
-  if (smem > (size_t)max_smem_optin()) return false;
+  if (tc_pick_bn(p) == 0) return false;
   if ((int64_t)p.in_h * p.in_w * p.c_in >= (1ll << 31)) return false;
   const char* env = getenv("VB200_DCN_PATH");
   if (env && env[0] == 's') return false;
@@ -342,20 +366,21 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   nchw_to_nhwc_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
   int rc = check_launch("nchw_to_nhwc_kernel");
   if (rc) return rc;
-  const int BN = (p.c_out % 256 == 0) ? 256 : 128;
+  const int BN = tc_pick_bn(p);
   pack_weights_kernel<T><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
   rc = check_launch("pack_weights_kernel");
   if (rc) return rc;
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
-  if (BN == 256) {
-    const size_t smem = tc_smem_bytes<256>(KK);
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    deform_conv2d_tc_kernel<T, 256><<<grid, TC_THREADS, smem, st>>>(nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);
-  } else {
-    const size_t smem = tc_smem_bytes<128>(KK);
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    deform_conv2d_tc_kernel<T, 128><<<grid, TC_THREADS, smem, st>>>(nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);
+  const size_t smem = tc_smem_bytes(BN, KK);
+#define VB200_TC_LAUNCH(BN_)                                                                                              \
+  {                                                                                                                       \
+    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_)>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+    deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_)><<<grid, TC_THREADS, smem, st>>>(                                      \
+        nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);                                     \
   }
+  if (BN == 512) VB200_TC_LAUNCH(512) else if (BN == 256) VB200_TC_LAUNCH(256) else VB200_TC_LAUNCH(128)
+#undef VB200_TC_LAUNCH
   rc = check_launch("deform_conv2d_tc_kernel");
   return rc ? rc : 1;
 }

@@ -169,10 +169,17 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
           const float4 bj = boxes[s + j];
           unsigned long long k = kept & (half ? 0xaaaaaaaaaaaaaaaaull : 0x5555555555555555ull);
           bool dead = false;
-          while (k && !dead) {
-            const int i = __ffsll((long long)k) - 1;
-            k &= k - 1;
-            dead = iou_gt(sb[i], sarea[i], bj, prm);
+          while (k && !dead) {                 // four independent IoU tests per trip (ILP over the fp32 divides)
+            bool d[4] = {false, false, false, false};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (k) {
+                const int i = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                d[u] = iou_gt(sb[i], sarea[i], bj, prm);
+              }
+            }
+            dead = d[0] | d[1] | d[2] | d[3];
           }
           if (dead) suppressed[s + j] = 1;
         }

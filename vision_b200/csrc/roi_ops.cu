@@ -188,6 +188,27 @@ __global__ void roi_align_geometry_kernel(const float* __restrict__ rois, Packed
 
 constexpr int kPlaneMaxThreads = 1024;
 
+// A thread's SR row entries and SR column entries of one RoI.  Entries of one bin row / column are
+// adjacent, and for even SR their group is 16-byte aligned (ent_per_roi * 8 B and SR * 8 B are
+// multiples of 16): two 128-bit loads instead of four 64-bit ones for the common SR = 2.
+template <int SR>
+__device__ __forceinline__ void load_entries(const PackedEnt* __restrict__ ge_, int gy, int gx, uint2 (&ey)[SR], uint2 (&ex)[SR]) {
+  if constexpr (SR % 2 == 0) {
+    const uint4* gy4 = reinterpret_cast<const uint4*>(ge_ + gy);
+    const uint4* gx4 = reinterpret_cast<const uint4*>(ge_ + gx);
+#pragma unroll
+    for (int i = 0; i < SR / 2; ++i) {
+      const uint4 a = __ldg(gy4 + i), b = __ldg(gx4 + i);
+      ey[2 * i] = make_uint2(a.x, a.y); ey[2 * i + 1] = make_uint2(a.z, a.w);
+      ex[2 * i] = make_uint2(b.x, b.y); ex[2 * i + 1] = make_uint2(b.z, b.w);
+    }
+  } else {
+    const uint2* ge = reinterpret_cast<const uint2*>(ge_);
+#pragma unroll
+    for (int i = 0; i < SR; ++i) { ey[i] = __ldg(ge + gy + i); ex[i] = __ldg(ge + gx + i); }
+  }
+}
+
 // Work = all (plane, roi) pairs in plane-major order, split evenly over the persistent CTAs; a
 // CTA (re)loads a plane only when its range crosses into it.  blockDim.x = NT = a multiple of
 // nbins, so a thread keeps ONE bin position (ph, pw) for its whole life and walks RoIs with a
@@ -243,11 +264,7 @@ roi_align_plane_kernel(const float* __restrict__ input, const PackedEnt* __restr
 
     int n = r0 + rl0;
     uint2 ey[SR], ex[SR];
-    if (n < r1) {
-      const uint2* ge = reinterpret_cast<const uint2*>(geo + (int64_t)n * ent_per_roi);
-#pragma unroll
-      for (int i = 0; i < SR; ++i) { ey[i] = __ldg(ge + gy + i); ex[i] = __ldg(ge + gx + i); }
-    }
+    if (n < r1) load_entries<SR>(geo + (int64_t)n * ent_per_roi, gy, gx, ey, ex);
     float* __restrict__ outp = output + ((int64_t)n * C + (pl - b * C)) * nbins + bin;
     const int64_t ostep = (int64_t)rstep * C * nbins;
     for (; n < r1; n += rstep, outp += ostep) {
@@ -255,11 +272,7 @@ roi_align_plane_kernel(const float* __restrict__ input, const PackedEnt* __restr
 #pragma unroll
       for (int i = 0; i < SR; ++i) { cy[i] = ey[i]; cx[i] = ex[i]; }
       const int nn = n + rstep;
-      if (nn < r1) {                                   // prefetch the next RoI's entries
-        const uint2* ge = reinterpret_cast<const uint2*>(geo + (int64_t)nn * ent_per_roi);
-#pragma unroll
-        for (int i = 0; i < SR; ++i) { ey[i] = __ldg(ge + gy + i); ex[i] = __ldg(ge + gx + i); }
-      }
+      if (nn < r1) load_entries<SR>(geo + (int64_t)nn * ent_per_roi, gy, gx, ey, ex);   // prefetch next RoI
       if (B > 1 && __ldg(roi_batch + n) != b) continue;
       float sum = 0.f;
 #pragma unroll
