@@ -328,6 +328,14 @@ def test_deform_conv2d_cfg4_reduced_vs_oracle(vb, oracle, dtype, tol):
     from vision_b200 import workloads
 
     x, off, w, b, m = workloads.cfg4_deform_conv2d(batch=2, c_in=64, c_out=128, hw=32, dtype=dtype)
+    if dtype != torch.float32:
+        # one accumulator (BN 128/256, 3 stages) and two accumulators (BN 512, 2 stages) of the tcgen05 kernel
+        for c_out, hw in ((256, 16), (512, 12)):
+            x2, off2, w2, b2, m2 = workloads.cfg4_deform_conv2d(seed=c_out, batch=1, c_in=128, c_out=c_out, hw=hw, dtype=dtype)
+            want2 = oracle.deform_conv2d(x2.float().numpy(), off2.float().numpy(), w2.float().numpy(), b2.float().numpy(),
+                                         (1, 1), (1, 1), (1, 1), m2.float().numpy())
+            got2 = vb.ops.deform_conv2d(x2.to(DEV), off2.to(DEV), w2.to(DEV), b2.to(DEV), 1, 1, 1, m2.to(DEV))
+            np.testing.assert_allclose(npy(got2), want2, rtol=tol, atol=tol)
     want = oracle.deform_conv2d(x.float().numpy(), off.float().numpy(), w.float().numpy(), b.float().numpy(), (1, 1), (1, 1), (1, 1),
                                 m.float().numpy())
     got = vb.ops.deform_conv2d(x.to(DEV), off.to(DEV), w.to(DEV), b.to(DEV), 1, 1, 1, m.to(DEV))

@@ -32,7 +32,7 @@ elif op in ("resize", "resize_noaa"):
     fn = lambda: vb.transforms.resize(x, [224, 224], antialias=(op == "resize"))
 elif op in ("deform", "deform_f32"):
     dt = torch.bfloat16 if op == "deform" else torch.float32
-    xi, off, w, bi, m = [t.to(dev) for t in workloads.cfg4_deform_conv2d(batch=8, dtype=dt)]
+    xi, off, w, bi, m = [t.to(dev) for t in workloads.cfg4_deform_conv2d(batch=int(os.environ.get('DCN_BATCH', '8')), dtype=dt)]
     fn = lambda: vb.ops.deform_conv2d(xi, off, w, bi, 1, 1, 1, m)
 else:
     raise SystemExit(f"unknown op {op}")
