@@ -229,22 +229,20 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
-          float acc[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+          unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};   // 8 channels as 4 packed fp32 pairs (FFMA2)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t u[4] = {v[i][q].x, v[i][q].y, v[i][q].z, v[i][q].w};
+            const unsigned long long w2 = pack2(wv[q], wv[q]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = Elem<T>::up(u[k]);
-              acc[2 * k] = fmaf(wv[q], f.x, acc[2 * k]);
-              acc[2 * k + 1] = fmaf(wv[q], f.y, acc[2 * k + 1]);
+              acc[k] = fma2(w2, pack2(f.x, f.y), acc[k]);
             }
           }
           uint4 o;
-          o.x = Elem<T>::pk(acc[0], acc[1]); o.y = Elem<T>::pk(acc[2], acc[3]);
-          o.z = Elem<T>::pk(acc[4], acc[5]); o.w = Elem<T>::pk(acc[6], acc[7]);
+          o.x = Elem<T>::pk(lo32(acc[0]), hi32(acc[0])); o.y = Elem<T>::pk(lo32(acc[1]), hi32(acc[1]));
+          o.z = Elem<T>::pk(lo32(acc[2]), hi32(acc[2])); o.w = Elem<T>::pk(lo32(acc[3]), hi32(acc[3]));
           const int prow = prow0 + 4 * i;
           *reinterpret_cast<uint4*>(a_tile + prow * 128 + ((cchunk ^ (prow & 7)) << 4)) = o;
         }

@@ -156,13 +156,21 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   const int lo = have ? interval_lo(p.scale_w, i, p.in_w) : p.in_w;
   const int hi = have ? ((i >= p.out_w) ? p.in_w : interval_lo(p.scale_w, i + 1, p.in_w)) : p.in_w;
   const int e = lo & ~1;                          // word-aligned first pixel slot
-  float wA[2 * LW], wB[2 * LW];
+  // weights kept as packed fp32 pairs: the inner loop is FFMA2 (fma.rn.f32x2, sm_100) — one issue slot
+  // for the two pixels of a 32-bit word
+  unsigned long long wA2[LW], wB2[LW];
 #pragma unroll
-  for (int t = 0; t < 2 * LW; ++t) {
-    const int x = e + t;
-    const bool in_iv = have && x >= lo && x < hi;
-    wA[t] = (in_iv && i < p.out_w) ? aa_weight(p.scale_w, x, xminx[i], xmcx[i], totx[i]) : 0.f;
-    wB[t] = (in_iv && i >= 1) ? aa_weight(p.scale_w, x, xminx[i - 1], xmcx[i - 1], totx[i - 1]) : 0.f;
+  for (int t = 0; t < LW; ++t) {
+    float wa[2], wb[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int x = e + 2 * t + h;
+      const bool in_iv = have && x >= lo && x < hi;
+      wa[h] = (in_iv && i < p.out_w) ? aa_weight(p.scale_w, x, xminx[i], xmcx[i], totx[i]) : 0.f;
+      wb[h] = (in_iv && i >= 1) ? aa_weight(p.scale_w, x, xminx[i - 1], xmcx[i - 1], totx[i - 1]) : 0.f;
+    }
+    wA2[t] = pack2(wa[0], wa[1]);
+    wB2[t] = pack2(wb[0], wb[1]);
   }
   const int word0 = min(e >> 1, (int)(row_bytes >> 2));     // beyond the row: the zeroed pad
   const bool writer = have && lane < 31 && i < p.out_w;     // lane 31 only supplies B to lane 30
@@ -176,13 +184,15 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   for (int rl = 0; rl < nrows; ++rl) {
     mbar_wait(&full[s], ph);
     const uint32_t* __restrict__ rowp = reinterpret_cast<const uint32_t*>(stage_ptr);
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    unsigned long long accA = 0ull, accB = 0ull;             // (a0, a1), (b0, b1) as fp32 pairs
 #pragma unroll
     for (int t = 0; t < LW; ++t) {
       const float2 v = Pair<T>::cvt(rowp[t]);
-      a0 = fmaf(wA[2 * t], v.x, a0); a1 = fmaf(wA[2 * t + 1], v.y, a1);
-      b0 = fmaf(wB[2 * t], v.x, b0); b1 = fmaf(wB[2 * t + 1], v.y, b1);
+      const unsigned long long v2 = pack2(v.x, v.y);
+      accA = fma2(wA2[t], v2, accA);
+      accB = fma2(wB2[t], v2, accB);
     }
+    const float a0 = lo32(accA), a1 = hi32(accA), b0 = lo32(accB), b1 = hi32(accB);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
     if (++s == p.n_stages) { s = 0; ph ^= 1u; stage_ptr = stages + (size_t)word0 * 4; } else stage_ptr += p.row_pitch;
