@@ -122,7 +122,7 @@ template <> struct Elem<__half> {
   static __device__ __forceinline__ uint32_t pk(float a, float b) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
 };
 
-struct TcEnt { int o[4]; float w[4]; };   // clamped corner pixel indices (y*W+x) + bilinear weights x mask
+struct __align__(16) TcEnt { int o[4]; float w[4]; };   // clamped corner pixel indices (y*W+x) + bilinear weights x mask
 
 // BN = output channels per CTA: 128 / 256 (one accumulator, 3 stages) or 512 (two 256-column
 // accumulators = all of TMEM, 2 stages; the A tile is then gathered once per pixel tile).
@@ -139,7 +139,8 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
   uint64_t* empty = fullB + TC_STAGES;
   uint64_t* accum_full = empty + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
-  TcEnt* tab = reinterpret_cast<TcEnt*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);   // [KK][128]
+  // [KK][128] sampling table, 32-byte aligned (entries are read as int4 + float4)
+  TcEnt* tab = reinterpret_cast<TcEnt*>(stages + ((TC_STAGES * STAGE_BYTES + (3 * TC_STAGES + 1) * 8 + 16 + 31) & ~31));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int KK = p.kh * p.kw;

@@ -25,6 +25,9 @@
 // reproduced bit for bit regardless of compiler contraction decisions.
 #include <cub/cub.cuh>
 
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vb200 {
@@ -37,7 +40,40 @@ struct IouParams {
   float thr_f;
   double thr_d;
   int semantics;
+  // division-free exact form of "RN_f32(inter / den) > threshold" (see make_iou_params)
+  double mid;
+  int s_even;
+  int use_div;
 };
+
+// Both reference predicates have the form  q >= S  with q = RN_f32(inter/den) and S a float:
+//   CUDA: q > (float)thr            -> S = nextafter((float)thr, +inf)
+//   CPU : (double)q > thr (double)  -> S = smallest float whose double value exceeds thr
+// q >= S  <=>  inter/den > m, or == m when the tie rounds up (S has an even mantissa), with
+// m = (pred(S) + S) / 2.  For den > 0 that is  inter > m*den  evaluated EXACTLY in double
+// (m has <= 25 significant bits, den 24: the product fits the 53-bit mantissa).  Verified against
+// float32 division on 8 M borderline cases (tools note in DESIGN.md); den <= 0 / NaN and
+// non-finite thresholds take the literal division path.
+inline IouParams make_iou_params(double thr, int semantics) {
+  IouParams p;
+  p.thr_f = (float)thr;
+  p.thr_d = thr;
+  p.semantics = semantics;
+  float S;
+  if (semantics == VB200_NMS_CUDA) {
+    S = nextafterf(p.thr_f, INFINITY);
+  } else {
+    const float c = (float)thr;
+    S = ((double)c > thr) ? c : nextafterf(c, INFINITY);
+  }
+  const float T = nextafterf(S, -INFINITY);
+  p.use_div = !(isfinite(S) && isfinite(T) && isfinite(thr));
+  p.mid = ((double)T + (double)S) * 0.5;
+  uint32_t bits;
+  memcpy(&bits, &S, 4);
+  p.s_even = (bits & 1u) == 0u;
+  return p;
+}
 
 // a = higher-scoring (suppressor) box, b = candidate.  area_a precomputed = mul_rn(a.z-a.x, a.w-a.y).
 __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const IouParams p) {
@@ -45,17 +81,20 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float w = fmaxf(sub_rn(right, left), 0.f), h = fmaxf(sub_rn(bottom, top), 0.f);
   const float inter = mul_rn(w, h);
+  float den;
   if (p.semantics == VB200_NMS_CUDA) {
     // nms_kernel.cu:50-53 as compiled: Sb's product contracted into (Sa + Sb), float threshold
-    const float t = __fmaf_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y), area_a);
-    const float iou = div_rn(inter, sub_rn(t, inter));
-    return iou > p.thr_f;
+    den = sub_rn(__fmaf_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y), area_a), inter);
   } else {
     // cpu/nms_kernel.cpp:58,86-88: separately rounded areas, double threshold
-    const float area_b = mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y));
-    const float ovr = div_rn(inter, sub_rn(add_rn(area_a, area_b), inter));
-    return (double)ovr > p.thr_d;
+    den = sub_rn(add_rn(area_a, mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y))), inter);
   }
+  if (!p.use_div && den > 0.f) {
+    const double di = (double)inter, rhs = p.mid * (double)den;     // exact
+    return di > rhs || (p.s_even && di == rhs);
+  }
+  const float q = div_rn(inter, den);
+  return p.semantics == VB200_NMS_CUDA ? (q > p.thr_f) : ((double)q > p.thr_d);
 }
 
 __global__ void iota_kernel(int* __restrict__ out, int n) {
@@ -112,6 +151,8 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_removed, s_kept;
   __shared__ unsigned int s_rm[2];
+  __shared__ float4 ksb[64];        // the boxes kept in the current block, compacted
+  __shared__ float karea[64];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nseg = num_seg_ptr ? *num_seg_ptr : 1;
@@ -159,25 +200,30 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
       }
       __syncthreads();
       const unsigned long long kept = s_kept;
-      if (tid < nb) suppressed[s + b0 + tid] = ((kept >> tid) & 1ull) ? 0 : 1;
-      // (3) later boxes vs. the boxes kept in this block.  Two threads per candidate
-      // (even / odd kept bits) to halve the dependent chain.
-      if (kept != 0ull) {
+      const int nkept = __popcll(kept);
+      if (tid < 64) {
+        if (tid < nb) suppressed[s + b0 + tid] = ((kept >> tid) & 1ull) ? 0 : 1;
+        if ((kept >> tid) & 1ull) {
+          const int pos = __popcll(kept & ((1ull << tid) - 1ull));
+          ksb[pos] = sb[tid];
+          karea[pos] = sarea[tid];
+        }
+      }
+      __syncthreads();
+      // (3) later boxes vs. the boxes kept in this block.  Two threads per candidate (even / odd
+      // entries of the compacted kept list), four independent IoU tests per trip.
+      if (nkept > 0 && b0 + 64 < n) {
         const int half = tid & 1;
         for (int j = b0 + 64 + (tid >> 1); j < n; j += kSegThreads / 2) {
           if (suppressed[s + j]) continue;
           const float4 bj = boxes[s + j];
-          unsigned long long k = kept & (half ? 0xaaaaaaaaaaaaaaaaull : 0x5555555555555555ull);
           bool dead = false;
-          while (k && !dead) {                 // four independent IoU tests per trip (ILP over the fp32 divides)
-            bool d[4] = {false, false, false, false};
+          for (int t = half; t < nkept && !dead; t += 8) {
+            bool d[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (k) {
-                const int i = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                d[u] = iou_gt(sb[i], sarea[i], bj, prm);
-              }
+              const int tt = min(t + 2 * u, nkept - 1);         // clamped repeats are harmless
+              d[u] = iou_gt(ksb[tt], karea[tt], bj, prm);
             }
             dead = d[0] | d[1] | d[2] | d[3];
           }
@@ -392,7 +438,7 @@ extern "C" int vb200_nms(const void* boxes, const void* scores, int dtype, int64
   if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
   VB200_REQUIRE(boxes && scores && keep_out && workspace, "nms: null pointer");
   VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "nms: boxes must be 16-byte aligned");
-  IouParams prm{(float)iou_threshold, iou_threshold, semantics};
+  const IouParams prm = make_iou_params(iou_threshold, semantics);
   return nms_core((const float4*)boxes, (const float*)scores, n, prm, workspace, workspace_bytes, keep_out,
                   num_keep_out, st);
 }
@@ -458,7 +504,7 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "batched_nms: boxes must be 16-byte aligned");
   BnmsWs w = carve_bnms(workspace, n);
   if (workspace_bytes < w.total) { set_error("batched_nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
-  IouParams prm{(float)iou_threshold, iou_threshold, semantics};
+  const IouParams prm = make_iou_params(iou_threshold, semantics);
   const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
   if (strategy == VB200_BNMS_AUTO) strategy = (4 * n > 100000) ? VB200_BNMS_VANILLA : VB200_BNMS_TRICK;   // boxes.py:86
 
