@@ -57,6 +57,10 @@ enum { VB200_NMS_CPU = 0, VB200_NMS_CUDA = 1 };
 /* batched_nms strategy (torchvision/ops/boxes.py:86-89). AUTO applies the
  * reference's own switch for CUDA tensors (numel > 100_000 -> VANILLA). */
 enum { VB200_BNMS_AUTO = 0, VB200_BNMS_VANILLA = 1, VB200_BNMS_TRICK = 2 };
+/* OR-ed into `strategy`: sort class ids as full 64-bit keys.  Without it the per-class path
+ * speculates that ids lie in [0, 65536) (2 radix passes instead of 8); if they do not, the call
+ * reports *num_keep_out = -1 and must be repeated with this flag. */
+#define VB200_BNMS_WIDE_KEYS 0x100
 
 enum { VB200_RESIZE_BILINEAR = 0, VB200_RESIZE_BICUBIC = 1 };
 
@@ -119,7 +123,7 @@ VB200_API int vb200_nms(const void* boxes, const void* scores, int dtype, int64_
 /* ---- batched_nms -------------------------------------------------------
  * Replaces the Python torchvision.ops.boxes.batched_nms (boxes.py:57-126):
  * one fused device pipeline instead of a per-class Python loop.  idxs [n] int64.
- * Output as vb200_nms.  strategy: VB200_BNMS_*. */
+ * Output as vb200_nms (or *num_keep_out = -1, see VB200_BNMS_WIDE_KEYS).  strategy: VB200_BNMS_*. */
 VB200_API size_t vb200_batched_nms_workspace_bytes(int64_t n);
 VB200_API int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
                       int64_t n, double iou_threshold, int semantics, int strategy,

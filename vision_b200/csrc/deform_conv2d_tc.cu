@@ -32,6 +32,35 @@ constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp 
 constexpr int TC_A_BYTES = TC_BM * 128;                      // 128 rows x 64 x 2 B
 
 // ---- pre-pass 1: NCHW -> NHWC (16-bit elements) -------------------------------------------
+// 64 channels x 64 pixels per CTA; 32-bit global accesses on both sides (2 pixels in, 2 channels out),
+// 128-byte rows per warp access.  Requires C % 64 == 0 and HW % 2 == 0 (else the scalar kernel below).
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc64_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int HW) {
+  __shared__ __align__(4) unsigned short tile[64][66];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned short* __restrict__ src = reinterpret_cast<const unsigned short*>(in) + (int64_t)b * C * HW;
+  unsigned short* __restrict__ dst = reinterpret_cast<unsigned short*>(out) + (int64_t)b * C * HW;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = warp + i * 8, p = p0 + 2 * lane;
+    uint32_t v = 0u;
+    if (p < HW) v = __ldg(reinterpret_cast<const uint32_t*>(src + (int64_t)(c0 + c) * HW + p));
+    *reinterpret_cast<uint32_t*>(&tile[c][2 * lane]) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pl = warp + i * 8, p = p0 + pl;
+    if (p < HW) {
+      const uint32_t v = (uint32_t)tile[2 * lane][pl] | ((uint32_t)tile[2 * lane + 1][pl] << 16);
+      *reinterpret_cast<uint32_t*>(dst + (int64_t)p * C + c0 + 2 * lane) = v;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int HW) {
@@ -361,8 +390,13 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   }
   T* nhwc = (T*)workspace;
   T* wpacked = (T*)((char*)workspace + nhwc_bytes);
-  dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
-  nchw_to_nhwc_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
+  if (HWi % 2 == 0 && p.c_in % 64 == 0 && ((uintptr_t)input % 4) == 0) {
+    dim3 tg((unsigned)ceil_div(HWi, 64), (unsigned)(p.c_in / 64), (unsigned)p.batch);
+    nchw_to_nhwc64_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
+  } else {
+    dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
+    nchw_to_nhwc_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
+  }
   int rc = check_launch("nchw_to_nhwc_kernel");
   if (rc) return rc;
   const int BN = tc_pick_bn(p);

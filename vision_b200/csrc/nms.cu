@@ -109,11 +109,20 @@ __global__ void gather_boxes_kernel(const float4* __restrict__ boxes, const int*
   if (i < n) out[i] = __ldg(boxes + order[i]);
 }
 
-// class key of the box at score-rank r
+// class key of the box at score-rank r; flags ids outside [0, 2^16) (the narrow-key fast path is then invalid)
 __global__ void gather_class_kernel(const int64_t* __restrict__ idxs, const int* __restrict__ order,
-                                    int64_t* __restrict__ keys, int n) {
+                                    int64_t* __restrict__ keys, int n, int* __restrict__ out_of_range) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = idxs[order[i]];
+  if (i < n) {
+    const int64_t k = idxs[order[i]];
+    keys[i] = k;
+    if ((uint64_t)k >= 65536ull) *out_of_range = 1;        // benign race: every writer stores 1
+  }
+}
+
+// *num_keep = -1 tells the caller to repeat the call with VB200_BNMS_WIDE_KEYS
+__global__ void poison_count_kernel(const int* __restrict__ out_of_range, int64_t* __restrict__ num_keep) {
+  if (*out_of_range) *num_keep = -1;
 }
 
 // class-major gather through two permutations + segment-start flags
@@ -496,6 +505,8 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   VB200_REQUIRE(dtype == VB200_F32, "batched_nms: only float32 boxes are supported by this build (got dtype %d)", dtype);
   VB200_REQUIRE(n >= 0 && n < (1ll << 31), "batched_nms: bad box count");
   VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "batched_nms: bad semantics selector");
+  const bool wide_keys = (strategy & VB200_BNMS_WIDE_KEYS) != 0;
+  strategy &= ~VB200_BNMS_WIDE_KEYS;
   VB200_REQUIRE(strategy >= VB200_BNMS_AUTO && strategy <= VB200_BNMS_TRICK, "batched_nms: bad strategy");
   VB200_REQUIRE(num_keep_out != nullptr, "batched_nms: null num_keep_out");
   cudaStream_t st = (cudaStream_t)stream;
@@ -526,12 +537,17 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   size_t tb = w.cub_bytes;
   VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, (const float*)scores, w.scores_sorted, w.iota, w.order, ni, 0, 32, st));
   g_launch_count.fetch_add(3, std::memory_order_relaxed);
-  gather_class_kernel<<<grd, blk, 0, st>>>(idxs, w.order, w.cls_keys, ni);
+  // num_seg[1] doubles as the "class id outside [0, 2^16)" flag of the narrow-key fast path
+  VB200_CUDA_TRY(cudaMemsetAsync(w.num_seg, 0, 2 * sizeof(int), st));
+  gather_class_kernel<<<grd, blk, 0, st>>>(idxs, w.order, w.cls_keys, ni, w.num_seg + 1);
   rc = check_launch("gather_class_kernel");
   if (rc) return rc;
   tb = w.cub_bytes;
-  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.cls_keys, w.cls_sorted, w.iota, w.rank_cm, ni, 0, 64, st));
-  g_launch_count.fetch_add(9, std::memory_order_relaxed);
+  // Speculate that class ids fit 16 bits (2 radix passes instead of 8); the flag is checked on the
+  // device after the pipeline and turns the result into "-1: call again with wide keys".
+  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.cls_keys, w.cls_sorted, w.iota, w.rank_cm, ni, 0,
+                                                 wide_keys ? 64 : 16, st));
+  g_launch_count.fetch_add(wide_keys ? 9 : 3, std::memory_order_relaxed);
   gather_boxes_cm_kernel<<<grd, blk, 0, st>>>((const float4*)boxes, w.order, w.rank_cm, w.cls_sorted, w.boxes_cm, w.seg_flag, ni);
   rc = check_launch("gather_boxes_cm_kernel");
   if (rc) return rc;
@@ -550,5 +566,10 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   tb = w.cub_bytes;
   VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, in_it, w.keep_by_rank, keep_out, num_keep_out, ni, st));
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  if (!wide_keys) {
+    poison_count_kernel<<<1, 1, 0, st>>>(w.num_seg + 1, num_keep_out);
+    rc = check_launch("poison_count_kernel");
+    if (rc) return rc;
+  }
   return 0;
 }

@@ -162,11 +162,17 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
   at::Tensor ws = workspace(wsb, boxes);
   at::Tensor keep = at::empty({n}, boxes.options().dtype(at::kLong));
   at::Tensor count = at::empty({1}, boxes.options().dtype(at::kLong));
-  check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), VB200_F32, n, iou_threshold,
-                             g_nms_semantics.load(), VB200_BNMS_AUTO, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
-                             count.data_ptr<int64_t>(), cur_stream()),
-           "batched_nms");
-  const int64_t k = count.item<int64_t>();
+  int64_t k = -1;
+  for (int attempt = 0; attempt < 2 && k < 0; ++attempt) {
+    // first attempt speculates 16-bit class ids; -1 asks for the wide-key repeat (arbitrary int64 ids)
+    const int strategy = VB200_BNMS_AUTO | (attempt ? VB200_BNMS_WIDE_KEYS : 0);
+    check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), VB200_F32, n, iou_threshold,
+                               g_nms_semantics.load(), strategy, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
+                               count.data_ptr<int64_t>(), cur_stream()),
+             "batched_nms");
+    k = count.item<int64_t>();
+  }
+  TORCH_CHECK(k >= 0, "batched_nms: internal error (negative kept count)");
   return keep.narrow(0, 0, k);
 }
 
