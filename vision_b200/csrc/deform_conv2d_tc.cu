@@ -26,10 +26,13 @@ namespace vb200 {
 
 namespace {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_GATHER_WARPS = 8;
+constexpr int TC_BM = 128, TC_GATHER_WARPS = 8;
 constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
 constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp
-constexpr int TC_A_BYTES = TC_BM * 128;                      // 128 rows x 64 x 2 B
+// KB = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B).
+// The gather always works on 64-channel slabs (whole 128-byte lines); with KB = 32 one gather step
+// fills two consecutive stages.  16-byte chunk c of row r is stored at chunk c ^ swz(r).
+template <int KB> __host__ __device__ constexpr int tc_swz(int r) { return KB == 64 ? (r & 7) : ((r >> 1) & 3); }
 
 // ---- pre-pass 1: NCHW -> NHWC (16-bit elements) -------------------------------------------
 // 64 channels x 64 pixels per CTA; 32-bit global accesses on both sides (2 pixels in, 2 channels out),
@@ -84,22 +87,24 @@ nchw_to_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int C, int HW
 }
 
 // ---- pre-pass 2: weights [Cout][Cin][KK] -> swizzled K-major tiles ---------------------------
-// tile (nt, s): BN rows x 64 k, byte offset inside = r*128 + ((kc/8) ^ (r&7))*16 + (kc%8)*2,
-// slab s = cslab*KK + tap holds k = channels [cslab*64, +64) of tap `tap`.
-template <typename T>
+// K order: (64-channel slab, tap, half) -> stage q = (cslab*KK + tap) * (64/KB) + half; tile (nt, q) holds
+// BN rows x KB k as the exact shared-memory image: byte = r*(2*KB) + ((kc/8) ^ swz(r))*16 + (kc%8)*2.
+template <typename T, int KB>
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const T* __restrict__ w, T* __restrict__ packed, int Cout, int Cin, int KK, int BN) {
   const int64_t total = (int64_t)Cout * Cin * KK;
-  const int n_slabs = (Cin / 64) * KK;
+  constexpr int SPLIT = 64 / KB;
+  const int n_q = (Cin / 64) * KK * SPLIT;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int tap = (int)(e % KK);
     const int ci = (int)((e / KK) % Cin);
     const int co = (int)(e / KK / Cin);
     const int nt = co / BN, r = co % BN;
-    const int cslab = ci / 64, kc = ci % 64;
-    const int s = cslab * KK + tap;
-    const int64_t tile_base = ((int64_t)nt * n_slabs + s) * BN * 64;
-    const int off_bytes = r * 128 + (((kc >> 3) ^ (r & 7)) << 4) + ((kc & 7) << 1);
+    const int cslab = ci / 64, kc64 = ci % 64;
+    const int half = kc64 / KB, kc = kc64 % KB;
+    const int q = (cslab * KK + tap) * SPLIT + half;
+    const int64_t tile_base = ((int64_t)nt * n_q + q) * BN * KB;
+    const int off_bytes = r * (2 * KB) + (((kc >> 3) ^ tc_swz<KB>(r)) << 4) + ((kc & 7) << 1);
     packed[tile_base + (off_bytes >> 1)] = w[e];
   }
 }
@@ -132,11 +137,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major: 1) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major: 1) | SBO>>4 [32,46) = bytes between 8-row
+// groups (8 * row bytes) | version=1 [46,48) | layout_type [61,64): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+template <int KB>
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t smem_addr) {
+  constexpr uint64_t sbo = (uint64_t)(8 * 2 * KB) >> 4;
+  constexpr uint64_t layout = KB == 64 ? 2ull : 4ull;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
 template <typename T> struct Elem;
@@ -155,12 +163,15 @@ struct __align__(16) TcEnt { int o[4]; float w[4]; };   // clamped corner pixel 
 
 // BN = output channels per CTA: 128 / 256 (one accumulator, 3 stages) or 512 (two 256-column
 // accumulators = all of TMEM, 2 stages; the A tile is then gathered once per pixel tile).
-template <typename T, int BN, int TC_STAGES>
+template <typename T, int BN, int TC_STAGES, int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacked, const T* __restrict__ offset,
                         const T* __restrict__ mask, const T* __restrict__ bias, T* __restrict__ out, DcnParams p) {
-  constexpr int B_BYTES = BN * 128;
+  constexpr int ROW_BYTES = 2 * KB;
+  constexpr int TC_A_BYTES = TC_BM * ROW_BYTES;
+  constexpr int B_BYTES = BN * ROW_BYTES;
   constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  constexpr int SPLIT = 64 / KB;                       // stages filled per 64-channel gather step
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stages = smem;
   uint64_t* fullA = reinterpret_cast<uint64_t*>(stages + TC_STAGES * STAGE_BYTES);
@@ -179,8 +190,8 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
   const int pix0 = (blockIdx.x % tiles_per_img) * TC_BM;
   const int nt = blockIdx.y;
   const int c_per_off = p.c_in / p.offset_groups;
-  const int slabs_per_og = (c_per_off / 64) * KK;
-  const int n_slabs = (p.c_in / 64) * KK;
+  const int slabs_per_og = (c_per_off / 64) * KK;      // 64-channel gather steps per offset group
+  const int n_q = (p.c_in / 64) * KK * SPLIT;          // pipeline stages consumed per tile
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&fullA[s], TC_GATHER_WARPS); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
@@ -240,8 +251,6 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
       for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
         const int cs_local = sl / KK, tap = sl - cs_local * KK;
         const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
-        const int st = slab % TC_STAGES;
-        const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
         uint4 v[4][4];                                       // [pixel][corner]
         float4 wq[4];
 #pragma unroll
@@ -254,8 +263,16 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
           v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + o.z));
           v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + o.w));
         }
-        mbar_wait(&empty[st], ph ^ 1u);
-        unsigned char* a_tile = stages + st * STAGE_BYTES;
+        // this thread's 8 channels land in sub-stage (cchunk / (KB/8)) of the SPLIT stages of this step
+        const int q0 = slab * SPLIT;
+#pragma unroll
+        for (int h = 0; h < SPLIT; ++h) {
+          const int qq = q0 + h;
+          mbar_wait(&empty[qq % TC_STAGES], ((uint32_t)(qq / TC_STAGES) & 1u) ^ 1u);
+        }
+        constexpr int CH_PER_ROW = KB / 8;                   // 16-byte chunks per tile row
+        const int my_q = q0 + cchunk / CH_PER_ROW, my_chunk = cchunk % CH_PER_ROW;
+        unsigned char* a_tile = stages + (my_q % TC_STAGES) * STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
@@ -274,11 +291,14 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
           o.x = Elem<T>::pk(lo32(acc[0]), hi32(acc[0])); o.y = Elem<T>::pk(lo32(acc[1]), hi32(acc[1]));
           o.z = Elem<T>::pk(lo32(acc[2]), hi32(acc[2])); o.w = Elem<T>::pk(lo32(acc[3]), hi32(acc[3]));
           const int prow = prow0 + 4 * i;
-          *reinterpret_cast<uint4*>(a_tile + prow * 128 + ((cchunk ^ (prow & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(a_tile + prow * ROW_BYTES + ((my_chunk ^ tc_swz<KB>(prow)) << 4)) = o;
         }
         fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&fullA[st]);
+        if (lane == 0) {
+#pragma unroll
+          for (int h = 0; h < SPLIT; ++h) mbar_arrive(&fullA[(q0 + h) % TC_STAGES]);
+        }
       }
     }
     // ================= epilogue: TMEM -> registers -> NCHW =================
@@ -306,8 +326,8 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
   } else if (warp == TC_GATHER_WARPS) {
     // ================= weight tiles: one bulk copy per stage =================
     if (lane == 0) {
-      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wpacked) + (int64_t)nt * n_slabs * B_BYTES;
-      for (int slab = 0; slab < n_slabs; ++slab) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wpacked) + (int64_t)nt * n_q * B_BYTES;
+      for (int slab = 0; slab < n_q; ++slab) {
         const int st = slab % TC_STAGES;
         const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
         mbar_wait(&empty[st], ph ^ 1u);
@@ -322,7 +342,7 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
       // n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
       constexpr int MMA_N = BN > 256 ? 256 : BN;
       const uint32_t idesc = (1u << 4) | (Elem<T>::kFmt << 7) | (Elem<T>::kFmt << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int slab = 0; slab < n_slabs; ++slab) {
+      for (int slab = 0; slab < n_q; ++slab) {
         const int st = slab % TC_STAGES;
         const uint32_t ph = (uint32_t)(slab / TC_STAGES) & 1u;
         mbar_wait(&fullA[st], ph);
@@ -331,10 +351,10 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         const uint32_t a_addr = smem_u32(stages + st * STAGE_BYTES);
         const uint32_t b_addr = a_addr + TC_A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          umma_f16(tmem_base, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + k * 32), idesc, (slab | k) ? 1u : 0u);
+        for (int k = 0; k < KB / 16; ++k) {
+          umma_f16(tmem_base, smem_desc_k<KB>(a_addr + k * 32), smem_desc_k<KB>(b_addr + k * 32), idesc, (slab | k) ? 1u : 0u);
           if constexpr (BN > 256)       // second accumulator: output channels [256, 512) -> TMEM columns [256, 512)
-            umma_f16(tmem_base + 256u, smem_desc_sw128(a_addr + k * 32), smem_desc_sw128(b_addr + 256 * 128 + k * 32), idesc,
+            umma_f16(tmem_base + 256u, smem_desc_k<KB>(a_addr + k * 32), smem_desc_k<KB>(b_addr + 256 * ROW_BYTES + k * 32), idesc,
                      (slab | k) ? 1u : 0u);
         }
         umma_commit(&empty[st]);               // stage reusable once these MMAs have read it
@@ -346,9 +366,12 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
   if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
-constexpr int tc_stages(int BN) { return BN > 256 ? 2 : 3; }
+// BN <= 256: K depth 64, 3 stages.  BN = 512: K depth 32, 4 stages (the 64 KB weight tile of a 64-deep
+// stage leaves room for only 2 stages, which exposes the L2 latency of every refill).
+constexpr int tc_kb(int BN) { return BN > 256 ? 32 : 64; }
+constexpr int tc_stages(int BN) { return BN > 256 ? 4 : 3; }
 size_t tc_smem_bytes(int BN, int KK) {
-  return (size_t)tc_stages(BN) * (TC_A_BYTES + BN * 128) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
+  return (size_t)tc_stages(BN) * (TC_BM + BN) * 2 * tc_kb(BN) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
 }
 int tc_pick_bn(const DcnParams& p) {
   const char* env = getenv("VB200_DCN_BN");           // profiling override: 128 / 256 / 512
@@ -400,16 +423,19 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   int rc = check_launch("nchw_to_nhwc_kernel");
   if (rc) return rc;
   const int BN = tc_pick_bn(p);
-  pack_weights_kernel<T><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+  if (tc_kb(512) == 32 && BN == 512)
+    pack_weights_kernel<T, 32><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+  else
+    pack_weights_kernel<T, 64><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
   rc = check_launch("pack_weights_kernel");
   if (rc) return rc;
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
   const size_t smem = tc_smem_bytes(BN, KK);
 #define VB200_TC_LAUNCH(BN_)                                                                                              \
   {                                                                                                                       \
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_)>,                                  \
+    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_), tc_kb(BN_)>,                      \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
-    deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_)><<<grid, TC_THREADS, smem, st>>>(                                      \
+    deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_), tc_kb(BN_)><<<grid, TC_THREADS, smem, st>>>(                          \
         nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);                                     \
   }
   if (BN == 512) VB200_TC_LAUNCH(512) else if (BN == 256) VB200_TC_LAUNCH(256) else VB200_TC_LAUNCH(128)
