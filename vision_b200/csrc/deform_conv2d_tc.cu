@@ -26,7 +26,7 @@ namespace vb200 {
 
 namespace {
 
-constexpr int TC_BM = 128, TC_GATHER_WARPS = 8;
+constexpr int TC_BM = 128, TC_GATHER_WARPS = 16;
 constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
 constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp
 // KB = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B).
@@ -208,8 +208,12 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     // ================= gather warps: build A tiles =================
     // lane = (pixel sub-index pq, 16-byte chunk c): one warp load instruction reads four complete
     // 128-byte lines (4 pixels x 64 channels) instead of sixteen quarter lines.
+    // 16 gather warps x 8 pixel rows; a thread owns 2 pixels (i = 0, 1) x 8 channels per 64-channel step.
+    // The 8 corner loads of step g+1 are issued before step g is blended (register double buffer), so
+    // every thread always has L2 requests in flight — the gather is latency-, not issue-bound.
     const int cchunk = lane & 7, pq = lane >> 3;
-    const int prow0 = warp * 16 + pq;                        // + 4 * i, i = 0..3
+    const int prow0 = warp * 8 + pq;                         // + 4 * i, i = 0..1
+    constexpr int PXT = 2;                                   // pixels per thread per step
     const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
     int slab = 0;
     for (int og = 0; og < p.offset_groups; ++og) {
@@ -247,22 +251,28 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         tab[e] = se;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
-      // ---- slabs of this offset group: channel slab outer, tap inner (L1 reuse across taps) ----
-      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
-        const int cs_local = sl / KK, tap = sl - cs_local * KK;
-        const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
-        uint4 v[4][4];                                       // [pixel][corner]
-        float4 wq[4];
+      // ---- slabs of this offset group: channel slab outer, tap inner ----
+      uint4 v[PXT][4];                                       // corner vectors of the CURRENT step
+      float4 wq[PXT];
+      auto issue = [&](int sl_, uint4 (&vv)[PXT][4], float4 (&ww)[PXT]) {
+        const int cs_local_ = sl_ / KK, tap_ = sl_ - cs_local_ * KK;
+        const T* __restrict__ in_c_ = in_b + og * c_per_off + cs_local_ * 64 + cchunk * 8;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                        // all 16 loads in flight before the blend
-          const TcEnt* se = tab + tap * TC_BM + prow0 + 4 * i;
+        for (int i = 0; i < PXT; ++i) {
+          const TcEnt* se = tab + tap_ * TC_BM + prow0 + 4 * i;
           const int4 o = *reinterpret_cast<const int4*>(se->o);
-          wq[i] = *reinterpret_cast<const float4*>(se->w);
-          v[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c + o.x));
-          v[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c + o.y));
-          v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + o.z));
-          v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + o.w));
+          ww[i] = *reinterpret_cast<const float4*>(se->w);
+          vv[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.x));
+          vv[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.y));
+          vv[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.z));
+          vv[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.w));
         }
+      };
+      issue(0, v, wq);
+      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
+        uint4 vn[PXT][4];
+        float4 wn[PXT];
+        if (sl + 1 < slabs_per_og) issue(sl + 1, vn, wn);    // prefetch the next step
         // this thread's 8 channels land in sub-stage (cchunk / (KB/8)) of the SPLIT stages of this step
         const int q0 = slab * SPLIT;
 #pragma unroll
@@ -274,7 +284,7 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         const int my_q = q0 + cchunk / CH_PER_ROW, my_chunk = cchunk % CH_PER_ROW;
         unsigned char* a_tile = stages + (my_q % TC_STAGES) * STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < PXT; ++i) {
           const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
           unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};   // 8 channels as 4 packed fp32 pairs (FFMA2)
 #pragma unroll
@@ -299,15 +309,23 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 #pragma unroll
           for (int h = 0; h < SPLIT; ++h) mbar_arrive(&fullA[(q0 + h) % TC_STAGES]);
         }
+        if (sl + 1 < slabs_per_og) {
+#pragma unroll
+          for (int i = 0; i < PXT; ++i) {
+            wq[i] = wn[i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[i][q] = vn[i][q];
+          }
+        }
       }
     }
     // ================= epilogue: TMEM -> registers -> NCHW =================
     mbar_wait(accum_full, 0u);
     tc_fence_after();
-    const int lane_base = (warp & 3) * 32;
-    const int col_half = warp >> 2;                           // warps 0-3: first half of the columns, 4-7: second
+    const int lane_base = (warp & 3) * 32;                    // TMEM lane quadrant this warp may access
+    const int col_half = warp >> 2;                           // 4 groups of 4 warps: one quarter of the columns each
     const int pix = pix0 + lane_base + lane;
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int COLS_PER_WARP = BN / (TC_GATHER_WARPS / 4);
 #pragma unroll 1
     for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
       const int col = col_half * COLS_PER_WARP + c0;
