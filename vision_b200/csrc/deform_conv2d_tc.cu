@@ -26,7 +26,7 @@ namespace vb200 {
 
 namespace {
 
-constexpr int TC_BM = 128, TC_GATHER_WARPS = 16;
+constexpr int TC_BM = 128, TC_GATHER_WARPS = 8;
 constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
 constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp
 // KB = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B).
@@ -208,12 +208,12 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     // ================= gather warps: build A tiles =================
     // lane = (pixel sub-index pq, 16-byte chunk c): one warp load instruction reads four complete
     // 128-byte lines (4 pixels x 64 channels) instead of sixteen quarter lines.
-    // 16 gather warps x 8 pixel rows; a thread owns 2 pixels (i = 0, 1) x 8 channels per 64-channel step.
-    // The 8 corner loads of step g+1 are issued before step g is blended (register double buffer), so
-    // every thread always has L2 requests in flight — the gather is latency-, not issue-bound.
+    // 8 gather warps x 16 pixel rows; a thread owns 4 pixels (i = 0..3) x 8 channels per 64-channel step.
+    // The 16 corner loads of step g+1 are issued before step g is blended (two register buffers,
+    // ping-pong over a loop unrolled by two), so L2 requests are always in flight.
     const int cchunk = lane & 7, pq = lane >> 3;
-    const int prow0 = warp * 8 + pq;                         // + 4 * i, i = 0..1
-    constexpr int PXT = 2;                                   // pixels per thread per step
+    const int prow0 = warp * 16 + pq;                        // + 4 * i, i = 0..3
+    constexpr int PXT = 4;                                   // pixels per thread per step
     const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
     int slab = 0;
     for (int og = 0; og < p.offset_groups; ++og) {
@@ -242,39 +242,36 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
             const float hh = 1.f - lh, hw = 1.f - lw;
             const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
             const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
-            se.o[0] = (hlc * p.in_w + wlc) * p.c_in; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
-            se.o[1] = (hlc * p.in_w + whc) * p.c_in; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
-            se.o[2] = (hhc * p.in_w + wlc) * p.c_in; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
-            se.o[3] = (hhc * p.in_w + whc) * p.c_in; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+            se.o[0] = (hlc * p.in_w + wlc) * p.c_in * 2; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = (hlc * p.in_w + whc) * p.c_in * 2; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = (hhc * p.in_w + wlc) * p.c_in * 2; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = (hhc * p.in_w + whc) * p.c_in * 2; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
           }
         }
         tab[e] = se;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
       // ---- slabs of this offset group: channel slab outer, tap inner ----
-      uint4 v[PXT][4];                                       // corner vectors of the CURRENT step
-      float4 wq[PXT];
-      auto issue = [&](int sl_, uint4 (&vv)[PXT][4], float4 (&ww)[PXT]) {
+      // corner byte offsets are 32-bit (eligibility bounds the image to < 2^30 elements): address =
+      // uniform 64-bit base of the step + 32-bit (corner + lane chunk) offset.
+      auto issue = [&](int sl_, uint4 (&vv)[PXT][4]) {
         const int cs_local_ = sl_ / KK, tap_ = sl_ - cs_local_ * KK;
-        const T* __restrict__ in_c_ = in_b + og * c_per_off + cs_local_ * 64 + cchunk * 8;
+        const char* __restrict__ base_ = reinterpret_cast<const char*>(in_b + og * c_per_off + cs_local_ * 64);
+        const uint32_t lane_off = (uint32_t)cchunk * 16u;
 #pragma unroll
         for (int i = 0; i < PXT; ++i) {
           const TcEnt* se = tab + tap_ * TC_BM + prow0 + 4 * i;
-          const int4 o = *reinterpret_cast<const int4*>(se->o);
-          ww[i] = *reinterpret_cast<const float4*>(se->w);
-          vv[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.x));
-          vv[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.y));
-          vv[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.z));
-          vv[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c_ + o.w));
+          const uint4 o = *reinterpret_cast<const uint4*>(se->o);
+          vv[i][0] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.x + lane_off)));
+          vv[i][1] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.y + lane_off)));
+          vv[i][2] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.z + lane_off)));
+          vv[i][3] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.w + lane_off)));
         }
       };
-      issue(0, v, wq);
-      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
-        uint4 vn[PXT][4];
-        float4 wn[PXT];
-        if (sl + 1 < slabs_per_og) issue(sl + 1, vn, wn);    // prefetch the next step
+      auto blend_store = [&](int slab_, int sl_, const uint4 (&vv)[PXT][4]) {
+        const int tap_ = sl_ % KK;                           // weights are re-read from the table (saves 16 registers per buffer)
         // this thread's 8 channels land in sub-stage (cchunk / (KB/8)) of the SPLIT stages of this step
-        const int q0 = slab * SPLIT;
+        const int q0 = slab_ * SPLIT;
 #pragma unroll
         for (int h = 0; h < SPLIT; ++h) {
           const int qq = q0 + h;
@@ -285,11 +282,12 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         unsigned char* a_tile = stages + (my_q % TC_STAGES) * STAGE_BYTES;
 #pragma unroll
         for (int i = 0; i < PXT; ++i) {
-          const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
+          const float4 wf = *reinterpret_cast<const float4*>(tab[tap_ * TC_BM + prow0 + 4 * i].w);
+          const float wv[4] = {wf.x, wf.y, wf.z, wf.w};
           unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};   // 8 channels as 4 packed fp32 pairs (FFMA2)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t u[4] = {v[i][q].x, v[i][q].y, v[i][q].z, v[i][q].w};
+            const uint32_t u[4] = {vv[i][q].x, vv[i][q].y, vv[i][q].z, vv[i][q].w};
             const unsigned long long w2 = pack2(wv[q], wv[q]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -309,15 +307,18 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 #pragma unroll
           for (int h = 0; h < SPLIT; ++h) mbar_arrive(&fullA[(q0 + h) % TC_STAGES]);
         }
+      };
+      uint4 va[PXT][4], vb[PXT][4];
+      issue(0, va);
+      for (int sl = 0; sl < slabs_per_og; sl += 2, slab += 2) {
+        if (sl + 1 < slabs_per_og) issue(sl + 1, vb);
+        blend_store(slab, sl, va);
         if (sl + 1 < slabs_per_og) {
-#pragma unroll
-          for (int i = 0; i < PXT; ++i) {
-            wq[i] = wn[i];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[i][q] = vn[i][q];
-          }
+          if (sl + 2 < slabs_per_og) issue(sl + 2, va);
+          blend_store(slab + 1, sl + 1, vb);
         }
       }
+      if (slabs_per_og & 1) slab -= 1;                       // the loop advanced `slab` by 2 on a final half trip
     }
     // ================= epilogue: TMEM -> registers -> NCHW =================
     mbar_wait(accum_full, 0u);
