@@ -208,12 +208,8 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     // ================= gather warps: build A tiles =================
     // lane = (pixel sub-index pq, 16-byte chunk c): one warp load instruction reads four complete
     // 128-byte lines (4 pixels x 64 channels) instead of sixteen quarter lines.
-    // 8 gather warps x 16 pixel rows; a thread owns 4 pixels (i = 0..3) x 8 channels per 64-channel step.
-    // The 16 corner loads of step g+1 are issued before step g is blended (two register buffers,
-    // ping-pong over a loop unrolled by two), so L2 requests are always in flight.
     const int cchunk = lane & 7, pq = lane >> 3;
     const int prow0 = warp * 16 + pq;                        // + 4 * i, i = 0..3
-    constexpr int PXT = 4;                                   // pixels per thread per step
     const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
     int slab = 0;
     for (int og = 0; og < p.offset_groups; ++og) {
@@ -242,36 +238,33 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
             const float hh = 1.f - lh, hw = 1.f - lw;
             const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
             const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
-            se.o[0] = (hlc * p.in_w + wlc) * p.c_in * 2; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
-            se.o[1] = (hlc * p.in_w + whc) * p.c_in * 2; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
-            se.o[2] = (hhc * p.in_w + wlc) * p.c_in * 2; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
-            se.o[3] = (hhc * p.in_w + whc) * p.c_in * 2; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+            se.o[0] = (hlc * p.in_w + wlc) * p.c_in; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = (hlc * p.in_w + whc) * p.c_in; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = (hhc * p.in_w + wlc) * p.c_in; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = (hhc * p.in_w + whc) * p.c_in; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
           }
         }
         tab[e] = se;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
-      // ---- slabs of this offset group: channel slab outer, tap inner ----
-      // corner byte offsets are 32-bit (eligibility bounds the image to < 2^30 elements): address =
-      // uniform 64-bit base of the step + 32-bit (corner + lane chunk) offset.
-      auto issue = [&](int sl_, uint4 (&vv)[PXT][4]) {
-        const int cs_local_ = sl_ / KK, tap_ = sl_ - cs_local_ * KK;
-        const char* __restrict__ base_ = reinterpret_cast<const char*>(in_b + og * c_per_off + cs_local_ * 64);
-        const uint32_t lane_off = (uint32_t)cchunk * 16u;
+      // ---- slabs of this offset group: channel slab outer, tap inner (L1 reuse across taps) ----
+      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
+        const int cs_local = sl / KK, tap = sl - cs_local * KK;
+        const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
+        uint4 v[4][4];                                       // [pixel][corner]
+        float4 wq[4];
 #pragma unroll
-        for (int i = 0; i < PXT; ++i) {
-          const TcEnt* se = tab + tap_ * TC_BM + prow0 + 4 * i;
-          const uint4 o = *reinterpret_cast<const uint4*>(se->o);
-          vv[i][0] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.x + lane_off)));
-          vv[i][1] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.y + lane_off)));
-          vv[i][2] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.z + lane_off)));
-          vv[i][3] = __ldg(reinterpret_cast<const uint4*>(base_ + (o.w + lane_off)));
+        for (int i = 0; i < 4; ++i) {                        // all 16 loads in flight before the blend
+          const TcEnt* se = tab + tap * TC_BM + prow0 + 4 * i;
+          const int4 o = *reinterpret_cast<const int4*>(se->o);
+          wq[i] = *reinterpret_cast<const float4*>(se->w);
+          v[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c + o.x));
+          v[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c + o.y));
+          v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + o.z));
+          v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + o.w));
         }
-      };
-      auto blend_store = [&](int slab_, int sl_, const uint4 (&vv)[PXT][4]) {
-        const int tap_ = sl_ % KK;                           // weights are re-read from the table (saves 16 registers per buffer)
         // this thread's 8 channels land in sub-stage (cchunk / (KB/8)) of the SPLIT stages of this step
-        const int q0 = slab_ * SPLIT;
+        const int q0 = slab * SPLIT;
 #pragma unroll
         for (int h = 0; h < SPLIT; ++h) {
           const int qq = q0 + h;
@@ -281,13 +274,12 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         const int my_q = q0 + cchunk / CH_PER_ROW, my_chunk = cchunk % CH_PER_ROW;
         unsigned char* a_tile = stages + (my_q % TC_STAGES) * STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < PXT; ++i) {
-          const float4 wf = *reinterpret_cast<const float4*>(tab[tap_ * TC_BM + prow0 + 4 * i].w);
-          const float wv[4] = {wf.x, wf.y, wf.z, wf.w};
+        for (int i = 0; i < 4; ++i) {
+          const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
           unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};   // 8 channels as 4 packed fp32 pairs (FFMA2)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t u[4] = {vv[i][q].x, vv[i][q].y, vv[i][q].z, vv[i][q].w};
+            const uint32_t u[4] = {v[i][q].x, v[i][q].y, v[i][q].z, v[i][q].w};
             const unsigned long long w2 = pack2(wv[q], wv[q]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -307,26 +299,15 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 #pragma unroll
           for (int h = 0; h < SPLIT; ++h) mbar_arrive(&fullA[(q0 + h) % TC_STAGES]);
         }
-      };
-      uint4 va[PXT][4], vb[PXT][4];
-      issue(0, va);
-      for (int sl = 0; sl < slabs_per_og; sl += 2, slab += 2) {
-        if (sl + 1 < slabs_per_og) issue(sl + 1, vb);
-        blend_store(slab, sl, va);
-        if (sl + 1 < slabs_per_og) {
-          if (sl + 2 < slabs_per_og) issue(sl + 2, va);
-          blend_store(slab + 1, sl + 1, vb);
-        }
       }
-      if (slabs_per_og & 1) slab -= 1;                       // the loop advanced `slab` by 2 on a final half trip
     }
     // ================= epilogue: TMEM -> registers -> NCHW =================
     mbar_wait(accum_full, 0u);
     tc_fence_after();
-    const int lane_base = (warp & 3) * 32;                    // TMEM lane quadrant this warp may access
-    const int col_half = warp >> 2;                           // 4 groups of 4 warps: one quarter of the columns each
+    const int lane_base = (warp & 3) * 32;
+    const int col_half = warp >> 2;                           // warps 0-3: first half of the columns, 4-7: second
     const int pix = pix0 + lane_base + lane;
-    constexpr int COLS_PER_WARP = BN / (TC_GATHER_WARPS / 4);
+    constexpr int COLS_PER_WARP = BN / 2;
 #pragma unroll 1
     for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
       const int col = col_half * COLS_PER_WARP + c0;
@@ -388,7 +369,15 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 // BN <= 256: K depth 64, 3 stages.  BN = 512: K depth 32, 4 stages (the 64 KB weight tile of a 64-deep
 // stage leaves room for only 2 stages, which exposes the L2 latency of every refill).
 constexpr int tc_kb(int BN) { return BN > 256 ? 32 : 64; }
-constexpr int tc_stages(int BN) { return BN > 256 ? 4 : 3; }
+// pipeline depth: BN <= 256 -> 3 x (16 + BN/8) KB; BN = 512 -> N x 40 KB with N = 3 by default: the stages
+// compete with the L1 cache for the same 228 KB, and the gathered corners (4.7 MB per tile) are served by
+// L1 only if ~64 KB of it are left (VB200_DCN_STAGES=2|3|4 overrides, for profiling).
+int tc_stages(int BN) {
+  if (BN <= 256) return 3;
+  const char* env = getenv("VB200_DCN_STAGES");
+  const int n = env ? atoi(env) : 3;
+  return n == 2 || n == 4 ? n : 3;
+}
 size_t tc_smem_bytes(int BN, int KK) {
   return (size_t)tc_stages(BN) * (TC_BM + BN) * 2 * tc_kb(BN) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
 }
@@ -450,14 +439,17 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   if (rc) return rc;
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
   const size_t smem = tc_smem_bytes(BN, KK);
-#define VB200_TC_LAUNCH(BN_)                                                                                              \
+#define VB200_TC_LAUNCH(BN_, ST_)                                                                                         \
   {                                                                                                                       \
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_), tc_kb(BN_)>,                      \
+    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)>,                                 \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
-    deform_conv2d_tc_kernel<T, BN_, tc_stages(BN_), tc_kb(BN_)><<<grid, TC_THREADS, smem, st>>>(                          \
+    deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)><<<grid, TC_THREADS, smem, st>>>(                                     \
         nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);                                     \
   }
-  if (BN == 512) VB200_TC_LAUNCH(512) else if (BN == 256) VB200_TC_LAUNCH(256) else VB200_TC_LAUNCH(128)
+  const int nst = tc_stages(BN);
+  if (BN == 512) {
+    if (nst == 2) VB200_TC_LAUNCH(512, 2) else if (nst == 4) VB200_TC_LAUNCH(512, 4) else VB200_TC_LAUNCH(512, 3)
+  } else if (BN == 256) VB200_TC_LAUNCH(256, 3) else VB200_TC_LAUNCH(128, 3)
 #undef VB200_TC_LAUNCH
   rc = check_launch("deform_conv2d_tc_kernel");
   return rc ? rc : 1;
