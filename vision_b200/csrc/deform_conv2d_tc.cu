@@ -366,6 +366,301 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
   if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
+
+// =================================================================================================
+// CTA-pair variant (cta_group::2): a 2-CTA cluster computes a 256-pixel x 512-channel tile.
+//   * each CTA gathers ITS 128 pixels (A rows) and loads HALF of the weight rows of every stage;
+//     the leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256, two accumulators), each SM's
+//     tensor core reads A and B-half from its own shared memory: per SM the operand reads drop from
+//     96 to 64 B/cycle and the weight bytes written per stage halve — the single-CTA form saturates the
+//     128 B/cycle shared-memory port (profiles/deform_conv2d_r1.md);
+//   * synchronisation: the peer's gather warps arrive REMOTELY on the leader's fullA barrier; each
+//     CTA's weight copy completes on its own fullB and the peer relays that to the leader's peerB;
+//     tcgen05.commit multicasts to the empty / accum_full barriers of both CTAs.
+// K depth 64 (SWIZZLE_128B), 3 stages of (16 KB A + 32 KB B-half) per CTA.
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// weights for the CTA pair: per (cout tile of 512, rank r, slab q) a [256 rows][64 k] SWIZZLE_128B image;
+// row rr = j*128 + i  <->  output channel nt*512 + j*256 + r*128 + i   (j = accumulator, r = CTA rank)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weights2_kernel(const T* __restrict__ w, T* __restrict__ packed, int Cout, int Cin, int KK) {
+  const int64_t total = (int64_t)Cout * Cin * KK;
+  const int n_q = (Cin / 64) * KK;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % KK);
+    const int ci = (int)((e / KK) % Cin);
+    const int co = (int)(e / KK / Cin);
+    const int nt = co / 512, c5 = co % 512;
+    const int j = c5 / 256, r = (c5 % 256) / 128, i = c5 % 128;
+    const int rr = j * 128 + i;
+    const int cslab = ci / 64, kc = ci % 64;
+    const int q = cslab * KK + tap;
+    const int64_t tile_base = (((int64_t)nt * 2 + r) * n_q + q) * 256 * 64;
+    const int off_bytes = rr * 128 + (((kc >> 3) ^ (rr & 7)) << 4) + ((kc & 7) << 1);
+    packed[tile_base + (off_bytes >> 1)] = w[e];
+  }
+}
+
+constexpr int TC2_STAGES = 3;
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+deform_conv2d_tc2_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacked, const T* __restrict__ offset,
+                         const T* __restrict__ mask, const T* __restrict__ bias, T* __restrict__ out, DcnParams p,
+                         int total_tiles) {
+  constexpr int KB = 64, ROW_BYTES = 128;
+  constexpr int A_BYTES = TC_BM * ROW_BYTES;            // 16 KB
+  constexpr int B_BYTES = 256 * ROW_BYTES;              // 32 KB: this CTA's half of both accumulators' weights
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* stages = smem;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(stages + TC2_STAGES * STAGE_BYTES);   // leader: 16 arrivals (8 + 8 remote)
+  uint64_t* fullB = fullA + TC2_STAGES;                 // local weight copy (tx)
+  uint64_t* peerB = fullB + TC2_STAGES;                 // leader: the peer's weight copy has landed
+  uint64_t* empty = peerB + TC2_STAGES;                 // multicast commit
+  uint64_t* accum_full = empty + TC2_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  TcEnt* tab = reinterpret_cast<TcEnt*>(stages + ((TC2_STAGES * STAGE_BYTES + (4 * TC2_STAGES + 1) * 8 + 16 + 31) & ~31));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int KK = p.kh * p.kw;
+  const int HWo = p.out_h * p.out_w, HWi = p.in_h * p.in_w;
+  const int tiles_per_img = ceil_div(HWo, TC_BM);
+  const int tile = blockIdx.x;
+  const bool live = tile < total_tiles;                 // the grid is padded to an even number of tiles
+  const int b = live ? tile / tiles_per_img : 0;
+  const int pix0 = live ? (tile % tiles_per_img) * TC_BM : HWo;
+  const int nt = blockIdx.y;
+  const int c_per_off = p.c_in / p.offset_groups;
+  const int slabs_per_og = (c_per_off / 64) * KK;
+  const int n_q = (p.c_in / 64) * KK;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) {
+      mbar_init(&fullA[s], 2 * TC_GATHER_WARPS);
+      mbar_init(&fullB[s], 1);
+      mbar_init(&peerB[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == TC_GATHER_WARPS + 1) tmem_alloc2(tmem_slot, 512);   // same warp id in both CTAs
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                   // barriers of both CTAs are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC_GATHER_WARPS) {
+    const int cchunk = lane & 7, pq = lane >> 3;
+    const int prow0 = warp * 16 + pq;
+    const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
+    int slab = 0;
+    for (int og = 0; og < p.offset_groups; ++og) {
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
+      const T* __restrict__ off_b = offset + ((int64_t)b * p.offset_groups + og) * 2 * KK * HWo;
+      const T* __restrict__ msk_b = p.use_mask ? mask + ((int64_t)b * p.offset_groups + og) * KK * HWo : nullptr;
+      for (int e = tid; e < KK * TC_BM; e += TC_GATHER_THREADS) {
+        const int tap = e / TC_BM, px = e - tap * TC_BM;
+        const int pix = pix0 + px;
+        TcEnt se;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { se.o[q] = 0; se.w[q] = 0.f; }
+        if (pix < HWo) {
+          const int oy = pix / p.out_w, ox = pix - oy * p.out_w;
+          const int i = tap / p.kw, j = tap - i * p.kw;
+          const float oh = to_acc(off_b[(int64_t)(2 * tap) * HWo + pix]);
+          const float ow = to_acc(off_b[(int64_t)(2 * tap + 1) * HWo + pix]);
+          const float mv = p.use_mask ? to_acc(msk_b[(int64_t)tap * HWo + pix]) : 1.f;
+          const float y = add_rn((float)(oy * p.stride_h - p.pad_h + i * p.dil_h), oh);
+          const float x = add_rn((float)(ox * p.stride_w - p.pad_w + j * p.dil_w), ow);
+          if (!(y <= -1.f || (float)p.in_h <= y || x <= -1.f || (float)p.in_w <= x)) {
+            const int hl = (int)floorf(y), wl = (int)floorf(x);
+            const int hh_i = hl + 1, wh_i = wl + 1;
+            const float lh = y - (float)hl, lw = x - (float)wl;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
+            const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
+            se.o[0] = (hlc * p.in_w + wlc) * p.c_in; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = (hlc * p.in_w + whc) * p.c_in; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = (hhc * p.in_w + wlc) * p.c_in; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = (hhc * p.in_w + whc) * p.c_in; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+          }
+        }
+        tab[e] = se;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
+      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
+        const int cs_local = sl / KK, tap = sl - cs_local * KK;
+        const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
+        const int st = slab % TC2_STAGES;
+        const uint32_t ph = (uint32_t)(slab / TC2_STAGES) & 1u;
+        uint4 v[4][4];
+        float4 wq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const TcEnt* se = tab + tap * TC_BM + prow0 + 4 * i;
+          const int4 o = *reinterpret_cast<const int4*>(se->o);
+          wq[i] = *reinterpret_cast<const float4*>(se->w);
+          v[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c + o.x));
+          v[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c + o.y));
+          v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + o.z));
+          v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + o.w));
+        }
+        mbar_wait(&empty[st], ph ^ 1u);
+        unsigned char* a_tile = stages + st * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
+          unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t u[4] = {v[i][q].x, v[i][q].y, v[i][q].z, v[i][q].w};
+            const unsigned long long w2 = pack2(wv[q], wv[q]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = Elem<T>::up(u[k]);
+              acc[k] = fma2(w2, pack2(f.x, f.y), acc[k]);
+            }
+          }
+          uint4 o;
+          o.x = Elem<T>::pk(lo32(acc[0]), hi32(acc[0])); o.y = Elem<T>::pk(lo32(acc[1]), hi32(acc[1]));
+          o.z = Elem<T>::pk(lo32(acc[2]), hi32(acc[2])); o.w = Elem<T>::pk(lo32(acc[3]), hi32(acc[3]));
+          const int prow = prow0 + 4 * i;
+          *reinterpret_cast<uint4*>(a_tile + prow * ROW_BYTES + ((cchunk ^ (prow & 7)) << 4)) = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&fullA[st]); else mbar_arrive_remote(&fullA[st], 0u);
+        }
+      }
+    }
+    // ---- epilogue: this CTA's 128 pixel rows x 512 channels ----
+    mbar_wait_cluster(accum_full, 0u);
+    tc_fence_after();
+    const int lane_base = (warp & 3) * 32;
+    const int col_half = warp >> 2;
+    const int pix = pix0 + lane_base + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 16) {
+      const int col = col_half * 256 + c0;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
+      if (live && pix < HWo) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = nt * 512 + col + j;
+          const float bv = bias ? to_acc(bias[co]) : 0.f;
+          out[((int64_t)b * p.c_out + co) * HWo + pix] = from_acc<T, float>(__uint_as_float(r[j]) + bv);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == TC_GATHER_WARPS) {
+    // ---- weights: lane 0 streams this CTA's half tiles; on the peer, lane 1 relays "landed" to the leader ----
+    if (lane == 0) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wpacked) + ((int64_t)nt * 2 + rank) * n_q * B_BYTES;
+      for (int q = 0; q < n_q; ++q) {
+        const int st = q % TC2_STAGES;
+        const uint32_t ph = (uint32_t)(q / TC2_STAGES) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_expect_tx(&fullB[st], (uint32_t)B_BYTES);
+        bulk_g2s(stages + st * STAGE_BYTES + A_BYTES, wsrc + (int64_t)q * B_BYTES, (uint32_t)B_BYTES, &fullB[st]);
+      }
+    } else if (lane == 1 && !leader) {
+      for (int q = 0; q < n_q; ++q) {
+        const int st = q % TC2_STAGES;
+        const uint32_t ph = (uint32_t)(q / TC2_STAGES) & 1u;
+        mbar_wait(&fullB[st], ph);
+        mbar_arrive_remote(&peerB[st], 0u);
+      }
+    }
+  } else {
+    // ---- MMA issuer: leader CTA only ----
+    if (lane == 0 && leader) {
+      const uint32_t idesc = (1u << 4) | (Elem<T>::kFmt << 7) | (Elem<T>::kFmt << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int q = 0; q < n_q; ++q) {
+        const int st = q % TC2_STAGES;
+        const uint32_t ph = (uint32_t)(q / TC2_STAGES) & 1u;
+        mbar_wait_cluster(&fullA[st], ph);
+        mbar_wait(&fullB[st], ph);
+        mbar_wait_cluster(&peerB[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(stages + st * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k) {
+          umma2_f16(tmem_base, smem_desc_k<KB>(a_addr + k * 32), smem_desc_k<KB>(b_addr + k * 32), idesc, (q | k) ? 1u : 0u);
+          umma2_f16(tmem_base + 256u, smem_desc_k<KB>(a_addr + k * 32), smem_desc_k<KB>(b_addr + 128 * ROW_BYTES + k * 32), idesc,
+                    (q | k) ? 1u : 0u);
+        }
+        umma2_commit_mc(&empty[st]);
+      }
+      umma2_commit_mc(accum_full);
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();                                   // nobody leaves (or frees TMEM) while the pair is still in use
+  if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
+size_t tc2_smem_bytes(int KK) {
+  return (size_t)TC2_STAGES * (TC_BM + 256) * 128 + 256 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
+}
+bool tc2_enabled(const DcnParams& p) {
+  const char* env = getenv("VB200_DCN_CTA2");
+  if (!(env && env[0] == '1')) return false;
+  return p.c_out % 512 == 0 && tc2_smem_bytes(p.kh * p.kw) <= (size_t)max_smem_optin();
+}
+
 // BN <= 256: K depth 64, 3 stages.  BN = 512: K depth 32, 4 stages (the 64 KB weight tile of a 64-deep
 // stage leaves room for only 2 stages, which exposes the L2 latency of every refill).
 constexpr int tc_kb(int BN) { return BN > 256 ? 32 : 64; }
@@ -430,6 +725,19 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   }
   int rc = check_launch("nchw_to_nhwc_kernel");
   if (rc) return rc;
+  if (tc2_enabled(p)) {
+    pack_weights2_kernel<T><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK);
+    rc = check_launch("pack_weights2_kernel");
+    if (rc) return rc;
+    const int total_tiles = p.batch * ceil_div(HWo, TC_BM);
+    dim3 grid2((unsigned)((total_tiles + 1) & ~1), (unsigned)(p.c_out / 512));
+    const size_t smem2 = tc2_smem_bytes(KK);
+    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    deform_conv2d_tc2_kernel<T><<<grid2, TC_THREADS, smem2, st>>>(nhwc, wpacked, (const T*)offset, (const T*)mask,
+                                                                  (const T*)bias, (T*)out, p, total_tiles);
+    rc = check_launch("deform_conv2d_tc2_kernel");
+    return rc ? rc : 1;
+  }
   const int BN = tc_pick_bn(p);
   if (tc_kb(512) == 32 && BN == 512)
     pack_weights_kernel<T, 32><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
