@@ -28,7 +28,10 @@ namespace {
 
 constexpr int TC_BM = 128, TC_GATHER_WARPS = 8;
 constexpr int TC_GATHER_THREADS = TC_GATHER_WARPS * 32;
-constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp
+constexpr int TC_THREADS = TC_GATHER_THREADS + 64;          // + bulk-copy warp + MMA warp (CTA-pair kernel)
+constexpr int TC1_GATHER_WARPS = 16;                         // single-CTA kernel: two groups of 8 gather warps
+constexpr int TC1_GATHER_THREADS = TC1_GATHER_WARPS * 32;
+constexpr int TC1_THREADS = TC1_GATHER_THREADS + 64;
 // KB = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B).
 // The gather always works on 64-channel slabs (whole 128-byte lines); with KB = 32 one gather step
 // fills two consecutive stages.  16-byte chunk c of row r is stored at chunk c ^ swz(r).
@@ -164,7 +167,7 @@ struct __align__(16) TcEnt { int o[4]; float w[4]; };   // clamped corner pixel 
 // BN = output channels per CTA: 128 / 256 (one accumulator, 3 stages) or 512 (two 256-column
 // accumulators = all of TMEM, 2 stages; the A tile is then gathered once per pixel tile).
 template <typename T, int BN, int TC_STAGES, int KB>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC1_THREADS, 1)
 deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacked, const T* __restrict__ offset,
                         const T* __restrict__ mask, const T* __restrict__ bias, T* __restrict__ out, DcnParams p) {
   constexpr int ROW_BYTES = 2 * KB;
@@ -198,26 +201,29 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     mbar_init(accum_full, 1);
     mbar_fence_init();
   }
-  if (warp == TC_GATHER_WARPS + 1) tmem_alloc(tmem_slot, BN);     // whole warp, .sync.aligned
+  if (warp == TC1_GATHER_WARPS + 1) tmem_alloc(tmem_slot, BN);    // whole warp, .sync.aligned
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < TC_GATHER_WARPS) {
+  if (warp < TC1_GATHER_WARPS) {
     // ================= gather warps: build A tiles =================
+    // Two groups of 8 warps take ALTERNATE 64-channel steps (group g owns the steps whose global index
+    // is g mod 2): twice the warps in flight for the same instruction count — the kernel is bound by the
+    // gather's issue rate (272 k warp instructions per tile at ~1.6 IPC), not by memory or the tensor pipe.
+    const int group = warp >> 3, wg = warp & 7;
     // lane = (pixel sub-index pq, 16-byte chunk c): one warp load instruction reads four complete
     // 128-byte lines (4 pixels x 64 channels) instead of sixteen quarter lines.
     const int cchunk = lane & 7, pq = lane >> 3;
-    const int prow0 = warp * 16 + pq;                        // + 4 * i, i = 0..3
+    const int prow0 = wg * 16 + pq;                          // + 4 * i, i = 0..3
     const T* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
-    int slab = 0;
     for (int og = 0; og < p.offset_groups; ++og) {
       // ---- sampling table for this offset group: [KK][128] ----
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));      // previous table no longer read
+      asm volatile("bar.sync 1, %0;" ::"n"(TC1_GATHER_THREADS));     // previous table no longer read
       const T* __restrict__ off_b = offset + ((int64_t)b * p.offset_groups + og) * 2 * KK * HWo;
       const T* __restrict__ msk_b = p.use_mask ? mask + ((int64_t)b * p.offset_groups + og) * KK * HWo : nullptr;
-      for (int e = tid; e < KK * TC_BM; e += TC_GATHER_THREADS) {
+      for (int e = tid; e < KK * TC_BM; e += TC1_GATHER_THREADS) {
         const int tap = e / TC_BM, px = e - tap * TC_BM;
         const int pix = pix0 + px;
         TcEnt se;
@@ -246,9 +252,11 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         }
         tab[e] = se;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_GATHER_THREADS));
+      asm volatile("bar.sync 1, %0;" ::"n"(TC1_GATHER_THREADS));
       // ---- slabs of this offset group: channel slab outer, tap inner (L1 reuse across taps) ----
-      for (int sl = 0; sl < slabs_per_og; ++sl, ++slab) {
+      const int slab_base = og * slabs_per_og;
+      for (int sl = (slab_base + group) & 1; sl < slabs_per_og; sl += 2) {
+        const int slab = slab_base + sl;
         const int cs_local = sl / KK, tap = sl - cs_local * KK;
         const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
         uint4 v[4][4];                                       // [pixel][corner]
@@ -305,9 +313,9 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     mbar_wait(accum_full, 0u);
     tc_fence_after();
     const int lane_base = (warp & 3) * 32;
-    const int col_half = warp >> 2;                           // warps 0-3: first half of the columns, 4-7: second
+    const int col_half = warp >> 2;                           // four groups of 4 warps: a quarter of the columns each
     const int pix = pix0 + lane_base + lane;
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int COLS_PER_WARP = BN / (TC1_GATHER_WARPS / 4);
 #pragma unroll 1
     for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
       const int col = col_half * COLS_PER_WARP + c0;
@@ -323,7 +331,7 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
       }
     }
     tc_fence_before();
-  } else if (warp == TC_GATHER_WARPS) {
+  } else if (warp == TC1_GATHER_WARPS) {
     // ================= weight tiles: one bulk copy per stage =================
     if (lane == 0) {
       const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wpacked) + (int64_t)nt * n_q * B_BYTES;
@@ -363,7 +371,7 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     }
   }
   __syncthreads();
-  if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+  if (warp == TC1_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
 }
 
 
@@ -664,14 +672,14 @@ bool tc2_enabled(const DcnParams& p) {
 // BN <= 256: K depth 64, 3 stages.  BN = 512: K depth 32, 4 stages (the 64 KB weight tile of a 64-deep
 // stage leaves room for only 2 stages, which exposes the L2 latency of every refill).
 constexpr int tc_kb(int BN) { return BN > 256 ? 32 : 64; }
-// pipeline depth: BN <= 256 -> 3 x (16 + BN/8) KB; BN = 512 -> N x 40 KB with N = 3 by default: the stages
-// compete with the L1 cache for the same 228 KB, and the gathered corners (4.7 MB per tile) are served by
-// L1 only if ~64 KB of it are left (VB200_DCN_STAGES=2|3|4 overrides, for profiling).
+// pipeline depth: BN <= 256 -> 3 x (16 + BN/8) KB; BN = 512 -> N x 40 KB, N = 4 by default
+// (VB200_DCN_STAGES=2|3|4 overrides, for profiling: fewer stages leave more of the 228 KB to L1 — measured:
+// no gain, profiles/deform_conv2d_r1.md).
 int tc_stages(int BN) {
   if (BN <= 256) return 3;
   const char* env = getenv("VB200_DCN_STAGES");
-  const int n = env ? atoi(env) : 3;
-  return n == 2 || n == 4 ? n : 3;
+  const int n = env ? atoi(env) : 4;        // 4: each gather group owns its own pair of K-32 stages
+  return n == 2 || n == 3 ? n : 4;
 }
 size_t tc_smem_bytes(int BN, int KK) {
   return (size_t)tc_stages(BN) * (TC_BM + BN) * 2 * tc_kb(BN) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
@@ -751,7 +759,7 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   {                                                                                                                       \
     VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)>,                                 \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
-    deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)><<<grid, TC_THREADS, smem, st>>>(                                     \
+    deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)><<<grid, TC1_THREADS, smem, st>>>(                                    \
         nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);                                     \
   }
   const int nst = tc_stages(BN);
