@@ -342,6 +342,23 @@ def test_deform_conv2d_cfg4_reduced_vs_oracle(vb, oracle, dtype, tol):
     np.testing.assert_allclose(npy(got), want, rtol=tol, atol=tol)
 
 
+def test_deform_conv2d_cta_pair_variant_matches(vb, oracle):
+    """The cta_group::2 (CTA-pair, M = 256) tcgen05 kernel, enabled by VB200_DCN_CTA2=1: same bits as the
+    single-CTA kernel, incl. an odd tile count (padded cluster) and ragged pixel tiles; oracle parity."""
+    from vision_b200 import workloads
+
+    for batch, cin, cout, hw in ((1, 64, 512, 12), (3, 128, 512, 20)):
+        x, off, w, b, m = workloads.cfg4_deform_conv2d(seed=hw, batch=batch, c_in=cin, c_out=cout, hw=hw, dtype=torch.bfloat16)
+        args = (x.to(DEV), off.to(DEV), w.to(DEV), b.to(DEV), 1, 1, 1, m.to(DEV))
+        one = vb.ops.deform_conv2d(*args)
+        with force_env("VB200_DCN_CTA2", "1"):
+            two = vb.ops.deform_conv2d(*args)
+        assert torch.equal(one, two)
+        want = oracle.deform_conv2d(x.float().numpy(), off.float().numpy(), w.float().numpy(), b.float().numpy(), (1, 1), (1, 1), (1, 1),
+                                    m.float().numpy())
+        np.testing.assert_allclose(npy(two), want, rtol=1e-2, atol=1e-2)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
 def test_deform_conv2d_zero_offset_is_conv2d(vb, dtype, tol):
     """Property at a larger size: offsets 0 and no mask == plain convolution (cuDNN, fp32)."""

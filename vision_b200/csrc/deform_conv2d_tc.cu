@@ -244,10 +244,10 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
             const float hh = 1.f - lh, hw = 1.f - lw;
             const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
             const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
-            se.o[0] = (hlc * p.in_w + wlc) * p.c_in; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
-            se.o[1] = (hlc * p.in_w + whc) * p.c_in; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
-            se.o[2] = (hhc * p.in_w + wlc) * p.c_in; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
-            se.o[3] = (hhc * p.in_w + whc) * p.c_in; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+            se.o[0] = (hlc * p.in_w + wlc) * p.c_in * 2; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = (hlc * p.in_w + whc) * p.c_in * 2; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = (hhc * p.in_w + wlc) * p.c_in * 2; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = (hhc * p.in_w + whc) * p.c_in * 2; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
           }
         }
         tab[e] = se;
@@ -258,18 +258,20 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
       for (int sl = (slab_base + group) & 1; sl < slabs_per_og; sl += 2) {
         const int slab = slab_base + sl;
         const int cs_local = sl / KK, tap = sl - cs_local * KK;
-        const T* __restrict__ in_c = in_b + og * c_per_off + cs_local * 64 + cchunk * 8;
+        // corner offsets are 32-bit BYTE offsets (image < 2^30 elements): uniform 64-bit base + 32-bit offset
+        const char* __restrict__ in_c = reinterpret_cast<const char*>(in_b + og * c_per_off + cs_local * 64);
+        const uint32_t lane_off = (uint32_t)cchunk * 16u;
         uint4 v[4][4];                                       // [pixel][corner]
         float4 wq[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                        // all 16 loads in flight before the blend
           const TcEnt* se = tab + tap * TC_BM + prow0 + 4 * i;
-          const int4 o = *reinterpret_cast<const int4*>(se->o);
+          const uint4 o = *reinterpret_cast<const uint4*>(se->o);
           wq[i] = *reinterpret_cast<const float4*>(se->w);
-          v[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c + o.x));
-          v[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c + o.y));
-          v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + o.z));
-          v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + o.w));
+          v[i][0] = __ldg(reinterpret_cast<const uint4*>(in_c + (o.x + lane_off)));
+          v[i][1] = __ldg(reinterpret_cast<const uint4*>(in_c + (o.y + lane_off)));
+          v[i][2] = __ldg(reinterpret_cast<const uint4*>(in_c + (o.z + lane_off)));
+          v[i][3] = __ldg(reinterpret_cast<const uint4*>(in_c + (o.w + lane_off)));
         }
         // this thread's 8 channels land in sub-stage (cchunk / (KB/8)) of the SPLIT stages of this step
         const int q0 = slab * SPLIT;
@@ -704,7 +706,7 @@ bool tc_eligible(int dtype, const DcnParams& p) {
   if (p.c_in % p.offset_groups != 0 || (p.c_in / p.offset_groups) % 64 != 0) return false;
   if (p.c_out % 128 != 0) return false;
   if (tc_pick_bn(p) == 0) return false;
-  if ((int64_t)p.in_h * p.in_w * p.c_in >= (1ll << 31)) return false;
+  if ((int64_t)p.in_h * p.in_w * p.c_in >= (1ll << 30)) return false;      // 32-bit byte offsets into one image
   const char* env = getenv("VB200_DCN_PATH");
   if (env && env[0] == 's') return false;
   return true;
