@@ -114,7 +114,7 @@ VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, vo
  * Writes the kept ORIGINAL indices, in descending-score order (stable), to
  * keep_out[0..*num_keep_out) — both device memory, keep_out sized n.  The
  * caller reads *num_keep_out (the reference's masked_select sync).
- * dtype: F32 (F16 inputs are widened by the caller, as autocast does). */
+ * dtype: F32 or F64, as the reference dispatches (F16 inputs are widened by the caller). */
 VB200_API size_t vb200_nms_workspace_bytes(int64_t n);
 VB200_API int vb200_nms(const void* boxes, const void* scores, int dtype, int64_t n, double iou_threshold,
               int semantics, void* workspace, size_t workspace_bytes, int64_t* keep_out,

@@ -32,6 +32,8 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.orc_nms_f32.restype = ctypes.c_int64
         _lib.orc_batched_nms_f32.restype = ctypes.c_int64
+        _lib.orc_nms_f64.restype = ctypes.c_int64
+        _lib.orc_batched_nms_f64.restype = ctypes.c_int64
         _lib.orc_deform_conv2d_f32.restype = ctypes.c_int
     return _lib
 
@@ -48,11 +50,19 @@ NMS_MODE_CPU = 0   # arithmetic of csrc/ops/cpu/nms_kernel.cpp
 NMS_MODE_CUDA = 1  # arithmetic of the compiled csrc/ops/cuda/nms_kernel.cu (FMA-contracted Sa+Sb, float thr)
 
 
+def _is_f64(a) -> bool:
+    return getattr(a, "dtype", None) == np.float64
+
+
 def nms(boxes, scores, iou_threshold: float, mode: int = NMS_MODE_CPU) -> np.ndarray:
-    boxes, scores = _f32(boxes).reshape(-1, 4), _f32(scores).reshape(-1)
+    """float64 inputs use the double twin (the reference dispatches nms on float and double)."""
+    f64 = _is_f64(boxes)
+    cast = (lambda a: np.ascontiguousarray(a, dtype=np.float64)) if f64 else _f32
+    boxes, scores = cast(boxes).reshape(-1, 4), cast(scores).reshape(-1)
     n = boxes.shape[0]
     keep = np.empty(max(n, 1), dtype=np.int64)
-    k = lib().orc_nms_f32(_p(boxes), _p(scores), ctypes.c_int64(n), ctypes.c_double(iou_threshold),
+    fn = lib().orc_nms_f64 if f64 else lib().orc_nms_f32
+    k = fn(_p(boxes), _p(scores), ctypes.c_int64(n), ctypes.c_double(iou_threshold),
                           ctypes.c_int(mode), _p(keep))
     return keep[:k].copy()
 
@@ -60,11 +70,14 @@ def nms(boxes, scores, iou_threshold: float, mode: int = NMS_MODE_CPU) -> np.nda
 def batched_nms(boxes, scores, idxs, iou_threshold: float, mode: int = NMS_MODE_CPU,
                 strategy: int = 0, device_is_cuda: bool = False) -> np.ndarray:
     """strategy: 0 = reference's own switch, 1 = vanilla, 2 = coordinate trick."""
-    boxes, scores = _f32(boxes).reshape(-1, 4), _f32(scores).reshape(-1)
+    f64 = _is_f64(boxes)
+    cast = (lambda a: np.ascontiguousarray(a, dtype=np.float64)) if f64 else _f32
+    boxes, scores = cast(boxes).reshape(-1, 4), cast(scores).reshape(-1)
     idxs = np.ascontiguousarray(idxs, dtype=np.int64).reshape(-1)
     n = boxes.shape[0]
     keep = np.empty(max(n, 1), dtype=np.int64)
-    k = lib().orc_batched_nms_f32(_p(boxes), _p(scores), _p(idxs), ctypes.c_int64(n),
+    fn = lib().orc_batched_nms_f64 if f64 else lib().orc_batched_nms_f32
+    k = fn(_p(boxes), _p(scores), _p(idxs), ctypes.c_int64(n),
                                   ctypes.c_double(iou_threshold), ctypes.c_int(mode),
                                   ctypes.c_int(strategy), ctypes.c_int(int(device_is_cuda)), _p(keep))
     return keep[:k].copy()

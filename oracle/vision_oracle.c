@@ -177,6 +177,151 @@ ORC_API int64_t orc_batched_nms_f32(const float* boxes, const float* scores, con
 }
 
 /* ------------------------------------------------------------------------ */
+/* float64 twins of the block above (the reference dispatches nms on float and double) */
+/* ------------------------------------------------------------------------ */
+static void merge_sort_desc_f64(const double* key, int64_t* idx, int64_t* tmp, int64_t n) {
+  if (n < 2) return;
+  int64_t h = n / 2;
+  merge_sort_desc_f64(key, idx, tmp, h);
+  merge_sort_desc_f64(key, idx + h, tmp, n - h);
+  int64_t i = 0, j = h, k = 0;
+  while (i < h && j < n) {
+    /* take right only if strictly greater: keeps equal keys in index order */
+    if (key[idx[j]] > key[idx[i]]) tmp[k++] = idx[j++];
+    else tmp[k++] = idx[i++];
+  }
+  while (i < h) tmp[k++] = idx[i++];
+  while (j < n) tmp[k++] = idx[j++];
+  memcpy(idx, tmp, (size_t)n * sizeof(int64_t));
+}
+
+ORC_API void orc_argsort_desc_stable_f64(const double* key, int64_t n, int64_t* order) {
+  int64_t* tmp = (int64_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
+  for (int64_t i = 0; i < n; ++i) order[i] = i;
+  merge_sort_desc_f64(key, order, tmp, n);
+  free(tmp);
+}
+
+/* ------------------------------------------------------------------------ */
+/* nms — torchvision/csrc/ops/cpu/nms_kernel.cpp:17-95 (mode 0)              */
+/*       torchvision/csrc/ops/cuda/nms_kernel.cu:42-54 devIoU (mode 1)       */
+/*                                                                          */
+/* mode 0 ("cpu"):  areas rounded separately, den = (iarea + area_j) - inter,*/
+/*                  compare (double)ovr > iou_threshold(double).            */
+/* mode 1 ("cuda"): what nvcc makes of devIoU<float> in the reference build  */
+/*                  (SASS of the installed sm_100 cubin):   */
+/*                  Sa = fmul(a2-a0, a3-a1); t = fma(b2-b0, b3-b1, Sa);      */
+/*                  den = t - inter; compare ovr > (float)iou_threshold.    */
+/* Returns the number kept; keep[] holds original indices in descending-    */
+/* score order (stable).                                                    */
+/* ------------------------------------------------------------------------ */
+ORC_API int64_t orc_nms_f64(const double* boxes, const double* scores, int64_t n,
+                            double iou_threshold, int mode, int64_t* keep) {
+  if (n <= 0) return 0;
+  int64_t* order = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+  uint8_t* suppressed = (uint8_t*)calloc((size_t)n, 1);
+  double* areas = (double*)malloc((size_t)n * sizeof(double));
+  orc_argsort_desc_stable_f64(scores, n, order);
+  for (int64_t k = 0; k < n; ++k)
+    areas[k] = (boxes[4 * k + 2] - boxes[4 * k + 0]) * (boxes[4 * k + 3] - boxes[4 * k + 1]);
+  const double thr_f = (double)(float)iou_threshold;   /* narrowed to float, widened back (nms_kernel.cu:45) */
+  int64_t num_to_keep = 0;
+  for (int64_t _i = 0; _i < n; ++_i) {
+    int64_t i = order[_i];
+    if (suppressed[i]) continue;
+    keep[num_to_keep++] = i;
+    double ix1 = boxes[4 * i], iy1 = boxes[4 * i + 1], ix2 = boxes[4 * i + 2], iy2 = boxes[4 * i + 3];
+    double iarea = areas[i];
+    for (int64_t _j = _i + 1; _j < n; ++_j) {
+      int64_t j = order[_j];
+      if (suppressed[j]) continue;
+      double jx1 = boxes[4 * j], jy1 = boxes[4 * j + 1], jx2 = boxes[4 * j + 2], jy2 = boxes[4 * j + 3];
+      double xx1 = ix1 > jx1 ? ix1 : jx1, yy1 = iy1 > jy1 ? iy1 : jy1;
+      double xx2 = jx2 < ix2 ? jx2 : ix2, yy2 = jy2 < iy2 ? jy2 : iy2;
+      double w = (xx2 - xx1) > 0. ? (xx2 - xx1) : 0., h = (yy2 - yy1) > 0. ? (yy2 - yy1) : 0.;
+      double inter = w * h;
+      if (mode == 0) {
+        double ovr = inter / (iarea + areas[j] - inter);
+        if (ovr > iou_threshold) suppressed[j] = 1;
+      } else {
+        double t = fma(jx2 - jx1, jy2 - jy1, iarea);
+        double ovr = inter / (t - inter);
+        if (ovr > thr_f) suppressed[j] = 1;
+      }
+    }
+  }
+  free(order); free(suppressed); free(areas);
+  return num_to_keep;
+}
+
+/* ------------------------------------------------------------------------ */
+/* batched_nms — torchvision/ops/boxes.py:57-126                             */
+/* strategy 1 = _batched_nms_vanilla (boxes.py:112-126): per class id in     */
+/*   ascending order, nms on that class's boxes; result = kept indices       */
+/*   sorted by score descending.  The reference's final sort is unstable;    */
+/*   ties are resolved here by ascending index (what a stable sort gives).   */
+/* strategy 2 = _batched_nms_coordinate_trick (boxes.py:92-109):             */
+/*   offsets = float(idx) * (max(boxes) + 1); nms(boxes + offsets).          */
+/* strategy 0 = the reference's own switch (boxes.py:86): numel > limit ->   */
+/*   vanilla else trick, limit = 4000 (cpu) or 100000 (cuda) via `device`.   */
+/* ------------------------------------------------------------------------ */
+static int cmp_i64_b(const void* a, const void* b) {
+  int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+  return (x > y) - (x < y);
+}
+
+ORC_API int64_t orc_batched_nms_f64(const double* boxes, const double* scores, const int64_t* idxs,
+                                    int64_t n, double iou_threshold, int mode, int strategy,
+                                    int device_is_cuda, int64_t* keep) {
+  if (n <= 0) return 0;
+  if (strategy == 0) {
+    int64_t limit = device_is_cuda ? 100000 : 4000;
+    strategy = (4 * n > limit) ? 1 : 2;
+  }
+  if (strategy == 2) {
+    double mx = boxes[0];
+    for (int64_t i = 1; i < 4 * n; ++i) if (boxes[i] > mx) mx = boxes[i];
+    double step = mx + 1.0;
+    double* shifted = (double*)malloc((size_t)n * 4 * sizeof(double));
+    for (int64_t i = 0; i < n; ++i) {
+      double off = (double)idxs[i] * step;
+      for (int c = 0; c < 4; ++c) shifted[4 * i + c] = boxes[4 * i + c] + off;
+    }
+    int64_t k = orc_nms_f64(shifted, scores, n, iou_threshold, mode, keep);
+    free(shifted);
+    return k;
+  }
+  /* vanilla */
+  int64_t* classes = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+  memcpy(classes, idxs, (size_t)n * sizeof(int64_t));
+  qsort(classes, (size_t)n, sizeof(int64_t), cmp_i64_b);
+  uint8_t* keep_mask = (uint8_t*)calloc((size_t)n, 1);
+  double* cb = (double*)malloc((size_t)n * 4 * sizeof(double));
+  double* cs = (double*)malloc((size_t)n * sizeof(double));
+  int64_t* cidx = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+  int64_t* ckeep = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+  for (int64_t u = 0; u < n; ++u) {
+    if (u > 0 && classes[u] == classes[u - 1]) continue;
+    int64_t cls = classes[u], m = 0;
+    for (int64_t i = 0; i < n; ++i)
+      if (idxs[i] == cls) {
+        memcpy(cb + 4 * m, boxes + 4 * i, 4 * sizeof(double));
+        cs[m] = scores[i];
+        cidx[m] = i;
+        ++m;
+      }
+    int64_t k = orc_nms_f64(cb, cs, m, iou_threshold, mode, ckeep);
+    for (int64_t t = 0; t < k; ++t) keep_mask[cidx[ckeep[t]]] = 1;
+  }
+  int64_t nk = 0;
+  for (int64_t i = 0; i < n; ++i) if (keep_mask[i]) { cidx[nk] = i; cs[nk] = scores[i]; ++nk; }
+  orc_argsort_desc_stable_f64(cs, nk, ckeep);
+  for (int64_t t = 0; t < nk; ++t) keep[t] = cidx[ckeep[t]];
+  free(classes); free(keep_mask); free(cb); free(cs); free(cidx); free(ckeep);
+  return nk;
+}
+
+/* ------------------------------------------------------------------------ */
 /* roi_align — torchvision/csrc/ops/cpu/roi_align_kernel.cpp:18-115 and      */
 /*             cpu/roi_align_common.h:32-124 (pre_calc_for_bilinear_...)      */
 /* ------------------------------------------------------------------------ */

@@ -193,6 +193,32 @@ def test_nms_vs_oracle_sizes(vb, oracle, n, sem):
         _set(vb, "cuda")
 
 
+@pytest.mark.parametrize("sem", ["cpu", "cuda"])
+def test_nms_float64(vb, oracle, sem):
+    """fp64 boxes (test/test_ops.py:959-982 compares CPU and CUDA nms in fp64): segment kernel, mask path, batched."""
+    rng = np.random.default_rng(11)
+    mode = oracle.NMS_MODE_CPU if sem == "cpu" else oracle.NMS_MODE_CUDA
+    _set(vb, sem)
+    try:
+        for n in (500, 5000):
+            b = rng.random((n, 4)) * 100
+            b[:, 2:] = b[:, :2] + rng.random((n, 2)) * 30 + 0.5
+            s = rng.random(n)
+            keep = vb.ops.nms(t(b), t(s), 0.5)
+            assert keep.dtype == torch.int64 and np.array_equal(npy(keep), oracle.nms(b, s, 0.5, mode))
+        n = 40_000
+        b = rng.random((n, 4)) * 300
+        b[:, 2:] = b[:, :2] + rng.random((n, 2)) * 60 + 1
+        s = rng.permutation(n).astype(np.float64) / n
+        i = rng.integers(0, 20, n)
+        keep = vb.ops.batched_nms(t(b), t(s), t(i), 0.5)
+        assert np.array_equal(npy(keep), oracle.batched_nms(b, s, i, 0.5, mode=mode, device_is_cuda=True))
+    finally:
+        _set(vb, "cuda")
+    tv = pytest.importorskip("torchvision")
+    assert torch.equal(tv.ops.nms(t(b[:3000]), t(s[:3000]), 0.5), vb.ops.nms(t(b[:3000]), t(s[:3000]), 0.5))
+
+
 def test_nms_threshold_narrowing_semantics(vb):
     a = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 2]], dtype=torch.float32, device=DEV)   # iou == 0.2f exactly
     sc = torch.tensor([1.0, 0.5], device=DEV)

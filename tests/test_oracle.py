@@ -100,6 +100,21 @@ def test_nms_live(oracle, seed, thr):
     assert np.array_equal(tv.ops.nms(b, s, thr).numpy(), oracle.nms(b.numpy(), s.numpy(), thr))
 
 
+def test_nms_float64_live(oracle):
+    """The reference dispatches nms on float and double (cpu/nms_kernel.cpp:122-128); its own CUDA tests run
+    in fp64 (test/test_ops.py:959-982)."""
+    import torch
+
+    g = torch.Generator().manual_seed(7)
+    b = torch.rand(900, 4, generator=g, dtype=torch.float64) * 100
+    b[:, 2:] += b[:, :2]
+    s = torch.rand(900, generator=g, dtype=torch.float64)
+    i = torch.randint(0, 6, (900,), generator=g)
+    for thr in (0.2, 0.5, 0.8):
+        assert np.array_equal(tv.ops.nms(b, s, thr).numpy(), oracle.nms(b.numpy(), s.numpy(), thr))
+    assert np.array_equal(tv.ops.batched_nms(b, s, i, 0.5).numpy(), oracle.batched_nms(b.numpy(), s.numpy(), i.numpy(), 0.5))
+
+
 def test_cfg3_batched_nms_live_reduced(oracle):
     """cfg3 at reduced size (20k boxes, 80 classes): reference vanilla path on CPU vs oracle."""
     import torch

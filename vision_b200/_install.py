@@ -44,7 +44,7 @@ def install() -> None:
 
     @functools.wraps(orig_batched_nms)
     def batched_nms(boxes, scores, idxs, iou_threshold):
-        if (isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype in (torch.float32, torch.float16)
+        if (isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype in (torch.float32, torch.float64, torch.float16)
                 and not torch.jit.is_scripting() and not torch.jit.is_tracing()):
             return torch.ops.vision_b200.batched_nms(boxes, scores, idxs, float(iou_threshold))
         return orig_batched_nms(boxes, scores, idxs, iou_threshold)

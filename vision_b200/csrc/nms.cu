@@ -75,6 +75,35 @@ inline IouParams make_iou_params(double thr, int semantics) {
   return p;
 }
 
+// fp64 boxes (the reference instantiates nms for double; its tests compare CPU and CUDA in fp64)
+struct alignas(16) double4a { double x, y, z, w; };
+template <typename S> struct BoxOf;
+template <> struct BoxOf<float> { using type = float4; };
+template <> struct BoxOf<double> { using type = double4a; };
+template <typename Box> struct ScalarOf;
+template <> struct ScalarOf<float4> { using type = float; };
+template <> struct ScalarOf<double4a> { using type = double; };
+__device__ __forceinline__ float4 zero_box(float4*) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ double4a zero_box(double4a*) { return double4a{0., 0., 0., 0.}; }
+__device__ __forceinline__ float4 load_box(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double4a load_box(const double4a* p) { return *p; }
+
+// fp64: csrc/ops/cuda/nms_kernel.cu:42-54 instantiated for double compiles to the same shape as the float
+// kernel (SASS of the sm_100 cubin: Sa = DMUL, t = DFMA(bw, bh, Sa), den = t - inter, IEEE division, compare
+// against the threshold narrowed to float and widened back); the CPU kernel rounds both areas and compares
+// against the double threshold.
+__device__ __forceinline__ bool iou_gt(const double4a a, const double area_a, const double4a b, const IouParams p) {
+  const double left = fmax(a.x, b.x), right = fmin(a.z, b.z);
+  const double top = fmax(a.y, b.y), bottom = fmin(a.w, b.w);
+  const double w = fmax(sub_rn(right, left), 0.0), h = fmax(sub_rn(bottom, top), 0.0);
+  const double inter = mul_rn(w, h);
+  double den;
+  if (p.semantics == VB200_NMS_CUDA) den = sub_rn(__fma_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y), area_a), inter);
+  else den = sub_rn(add_rn(area_a, mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y))), inter);
+  const double q = div_rn(inter, den);
+  return p.semantics == VB200_NMS_CUDA ? (q > (double)p.thr_f) : (q > p.thr_d);
+}
+
 // a = higher-scoring (suppressor) box, b = candidate.  area_a precomputed = mul_rn(a.z-a.x, a.w-a.y).
 __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const IouParams p) {
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
@@ -103,10 +132,11 @@ __global__ void iota_kernel(int* __restrict__ out, int n) {
 }
 
 // boxes_sorted[p] = boxes[order[p]] (one 128-bit load per box)
-__global__ void gather_boxes_kernel(const float4* __restrict__ boxes, const int* __restrict__ order,
-                                    float4* __restrict__ out, int n) {
+template <typename Box>
+__global__ void gather_boxes_kernel(const Box* __restrict__ boxes, const int* __restrict__ order,
+                                    Box* __restrict__ out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __ldg(boxes + order[i]);
+  if (i < n) out[i] = load_box(boxes + order[i]);
 }
 
 // class key of the box at score-rank r; flags ids outside [0, 2^16) (the narrow-key fast path is then invalid)
@@ -126,24 +156,27 @@ __global__ void poison_count_kernel(const int* __restrict__ out_of_range, int64_
 }
 
 // class-major gather through two permutations + segment-start flags
-__global__ void gather_boxes_cm_kernel(const float4* __restrict__ boxes, const int* __restrict__ order,
+template <typename Box>
+__global__ void gather_boxes_cm_kernel(const Box* __restrict__ boxes, const int* __restrict__ order,
                                        const int* __restrict__ rank_cm, const int64_t* __restrict__ cls_sorted,
-                                       float4* __restrict__ out, uint8_t* __restrict__ seg_flag, int n) {
+                                       Box* __restrict__ out, uint8_t* __restrict__ seg_flag, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    out[i] = __ldg(boxes + order[rank_cm[i]]);
+    out[i] = load_box(boxes + order[rank_cm[i]]);
     seg_flag[i] = (i == 0 || cls_sorted[i] != cls_sorted[i - 1]) ? 1 : 0;
   }
 }
 
 // coordinate trick (boxes.py:103-107): boxes + float(idx) * (max + 1), each op rounded once
-__global__ void shift_boxes_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ idxs,
-                                   const float* __restrict__ max_coord, float4* __restrict__ out, int n) {
+template <typename Box>
+__global__ void shift_boxes_kernel(const Box* __restrict__ boxes, const int64_t* __restrict__ idxs,
+                                   const typename ScalarOf<Box>::type* __restrict__ max_coord, Box* __restrict__ out, int n) {
+  using S = typename ScalarOf<Box>::type;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const float step = add_rn(*max_coord, 1.0f);
-    const float off = mul_rn((float)idxs[i], step);
-    float4 b = boxes[i];
+    const S step = add_rn(*max_coord, (S)1);
+    const S off = mul_rn((S)idxs[i], step);
+    Box b = boxes[i];
     b.x = add_rn(b.x, off); b.y = add_rn(b.y, off); b.z = add_rn(b.z, off); b.w = add_rn(b.w, off);
     out[i] = b;
   }
@@ -151,17 +184,19 @@ __global__ void shift_boxes_kernel(const float4* __restrict__ boxes, const int64
 
 // One CTA per segment; see file header.  `suppressed` (zero on entry) is indexed by
 // position in the sorted order; on exit suppressed[p] == 0  <=>  box p is kept.
+template <typename Box>
 __global__ void __launch_bounds__(kSegThreads, 1)
-nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg_start,
+nms_segment_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_start,
                    const int* __restrict__ num_seg_ptr, int n_total, IouParams prm,
                    uint8_t* __restrict__ suppressed) {
-  __shared__ float4 sb[64];
-  __shared__ float sarea[64];
+  using S = typename ScalarOf<Box>::type;
+  __shared__ Box sb[64];
+  __shared__ S sarea[64];
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_removed, s_kept;
   __shared__ unsigned int s_rm[2];
-  __shared__ float4 ksb[64];        // the boxes kept in the current block, compacted
-  __shared__ float karea[64];
+  __shared__ Box ksb[64];           // the boxes kept in the current block, compacted
+  __shared__ S karea[64];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nseg = num_seg_ptr ? *num_seg_ptr : 1;
@@ -174,7 +209,7 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
       // stage the block's boxes; collect which of them are already suppressed
       bool sup = true;
       if (tid < 64) {
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        Box b = zero_box((Box*)nullptr);
         if (tid < nb) { b = boxes[s + b0 + tid]; sup = suppressed[s + b0 + tid] != 0; }
         sb[tid] = b;
         sarea[tid] = mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y));
@@ -186,8 +221,8 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int row = warp * 2 + rr;
-        const float4 a = sb[row];
-        const float aa = sarea[row];
+        const Box a = sb[row];
+        const S aa = sarea[row];
         const bool p0 = (lane > row) && (lane < nb) && (row < nb) && iou_gt(a, aa, sb[lane], prm);
         const bool p1 = (lane + 32 > row) && (lane + 32 < nb) && (row < nb) && iou_gt(a, aa, sb[lane + 32], prm);
         const unsigned int lo = __ballot_sync(0xffffffffu, p0);
@@ -225,7 +260,7 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
         const int half = tid & 1;
         for (int j = b0 + 64 + (tid >> 1); j < n; j += kSegThreads / 2) {
           if (suppressed[s + j]) continue;
-          const float4 bj = boxes[s + j];
+          const Box bj = boxes[s + j];
           bool dead = false;
           for (int t = half; t < nkept && !dead; t += 8) {
             bool d[4];
@@ -246,8 +281,9 @@ nms_segment_kernel(const float4* __restrict__ boxes, const int* __restrict__ seg
 
 // ---- mask path (single large segment) -------------------------------------
 // tile (rb, cb), cb >= rb, 64 threads = 64 rows; col boxes in smem; mask[row * col_blocks + cb]
+template <typename Box>
 __global__ void __launch_bounds__(64)
-nms_mask_kernel(const float4* __restrict__ boxes, int n, int col_blocks, IouParams prm,
+nms_mask_kernel(const Box* __restrict__ boxes, int n, int col_blocks, IouParams prm,
                 unsigned long long* __restrict__ mask) {
   // linear upper-triangular tile index -> (rb, cb)
   const long long t = blockIdx.x;
@@ -262,15 +298,16 @@ nms_mask_kernel(const float4* __restrict__ boxes, int n, int col_blocks, IouPara
   const long long first = rb * col_blocks - rb * (rb - 1) / 2;
   const int cb = (int)(rb + (t - first));
 
-  __shared__ float4 cbx[64];
+  using S = typename ScalarOf<Box>::type;
+  __shared__ Box cbx[64];
   const int col0 = cb * 64, row0 = (int)rb * 64;
   const int ncol = min(64, n - col0), nrow = min(64, n - row0);
   if ((int)threadIdx.x < ncol) cbx[threadIdx.x] = boxes[col0 + threadIdx.x];
   __syncthreads();
   if ((int)threadIdx.x < nrow) {
     const int row = row0 + threadIdx.x;
-    const float4 a = boxes[row];
-    const float aa = mul_rn(sub_rn(a.z, a.x), sub_rn(a.w, a.y));
+    const Box a = boxes[row];
+    const S aa = mul_rn(sub_rn(a.z, a.x), sub_rn(a.w, a.y));
     unsigned long long bits = 0;
     const int start = (cb == (int)rb) ? (int)threadIdx.x + 1 : 0;
     for (int i = start; i < ncol; ++i)
@@ -356,13 +393,18 @@ size_t cub_temp_bytes(int64_t n) {
   mx = b > mx ? b : mx;
   cub::DeviceReduce::Max(nullptr, b, (const float*)nullptr, (float*)nullptr, ni * 4);
   mx = b > mx ? b : mx;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (const double*)nullptr, (double*)nullptr, (const int*)nullptr, (int*)nullptr, ni);
+  mx = b > mx ? b : mx;
+  cub::DeviceReduce::Max(nullptr, b, (const double*)nullptr, (double*)nullptr, ni * 4);
+  mx = b > mx ? b : mx;
   cached_n = n;
   cached_bytes = mx + 4096;
   return cached_bytes;
 }
 
+// Workspaces are carved for the widest scalar (double): one size query serves both dtypes.
 struct NmsWs {
-  int* iota; int* order; float* scores_sorted; float4* boxes_sorted; uint8_t* suppressed;
+  int* iota; int* order; void* scores_sorted; void* boxes_sorted; uint8_t* suppressed;
   unsigned long long* mask; void* cub_temp; size_t cub_bytes; size_t total;
 };
 
@@ -371,8 +413,8 @@ NmsWs carve_nms(void* base, int64_t n) {
   NmsWs w;
   w.iota = c.take<int>(n);
   w.order = c.take<int>(n);
-  w.scores_sorted = c.take<float>(n);
-  w.boxes_sorted = c.take<float4>(n);
+  w.scores_sorted = c.take<double>(n);
+  w.boxes_sorted = c.take<double4a>(n);
   w.suppressed = c.take<uint8_t>(n);
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = c.take<char>(w.cub_bytes);
@@ -383,16 +425,17 @@ NmsWs carve_nms(void* base, int64_t n) {
 }
 
 // Sorted-order suppression for ONE segment of n boxes (boxes_sorted), result in suppressed[].
-int run_single_segment(const float4* boxes_sorted, int64_t n, IouParams prm, uint8_t* suppressed,
+template <typename Box>
+int run_single_segment(const Box* boxes_sorted, int64_t n, IouParams prm, uint8_t* suppressed,
                        unsigned long long* mask, cudaStream_t st) {
   if (n <= kSegmentMaxSingle || mask == nullptr) {
     VB200_CUDA_TRY(cudaMemsetAsync(suppressed, 0, (size_t)n, st));
-    nms_segment_kernel<<<1, kSegThreads, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, prm, suppressed);
+    nms_segment_kernel<Box><<<1, kSegThreads, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, prm, suppressed);
     return check_launch("nms_segment_kernel");
   }
   const int cb = (int)ceil_div64(n, 64);
   const long long tiles = (long long)cb * (cb + 1) / 2;
-  nms_mask_kernel<<<(unsigned)tiles, 64, 0, st>>>(boxes_sorted, (int)n, cb, prm, mask);
+  nms_mask_kernel<Box><<<(unsigned)tiles, 64, 0, st>>>(boxes_sorted, (int)n, cb, prm, mask);
   int rc = check_launch("nms_mask_kernel");
   if (rc) return rc;
   const size_t smem = (size_t)cb * sizeof(unsigned long long);
@@ -402,8 +445,10 @@ int run_single_segment(const float4* boxes_sorted, int64_t n, IouParams prm, uin
   return check_launch("nms_scan_kernel");
 }
 
-int nms_core(const float4* boxes, const float* scores, int64_t n, IouParams prm, void* workspace,
+template <typename S>
+int nms_core(const typename BoxOf<S>::type* boxes, const S* scores, int64_t n, IouParams prm, void* workspace,
              size_t workspace_bytes, int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st) {
+  using Box = typename BoxOf<S>::type;
   NmsWs w = carve_nms(workspace, n);
   if (workspace_bytes < w.total) { set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
   const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
@@ -411,12 +456,13 @@ int nms_core(const float4* boxes, const float* scores, int64_t n, IouParams prm,
   int rc = check_launch("iota_kernel");
   if (rc) return rc;
   size_t tb = w.cub_bytes;
-  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, scores, w.scores_sorted, w.iota, w.order, ni, 0, 32, st));
+  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, scores, (S*)w.scores_sorted, w.iota, w.order, ni, 0,
+                                                           (int)sizeof(S) * 8, st));
   g_launch_count.fetch_add(3, std::memory_order_relaxed);
-  gather_boxes_kernel<<<grd, blk, 0, st>>>(boxes, w.order, w.boxes_sorted, ni);
+  gather_boxes_kernel<Box><<<grd, blk, 0, st>>>(boxes, w.order, (Box*)w.boxes_sorted, ni);
   rc = check_launch("gather_boxes_kernel");
   if (rc) return rc;
-  rc = run_single_segment(w.boxes_sorted, n, prm, w.suppressed, w.mask, st);
+  rc = run_single_segment<Box>((const Box*)w.boxes_sorted, n, prm, w.suppressed, w.mask, st);
   if (rc) return rc;
   cub::TransformInputIterator<int64_t, ToI64, const int*> in_it(w.order, ToI64());
   cub::TransformInputIterator<bool, NotZero, const uint8_t*> flag_it(w.suppressed, NotZero());
@@ -439,7 +485,7 @@ extern "C" size_t vb200_nms_workspace_bytes(int64_t n) {
 extern "C" int vb200_nms(const void* boxes, const void* scores, int dtype, int64_t n, double iou_threshold,
                          int semantics, void* workspace, size_t workspace_bytes, int64_t* keep_out,
                          int64_t* num_keep_out, vb200_stream stream) {
-  VB200_REQUIRE(dtype == VB200_F32, "nms: only float32 boxes are supported by this build (got dtype %d)", dtype);
+  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64, "nms: boxes must be float32 or float64 (got dtype %d)", dtype);
   VB200_REQUIRE(n >= 0 && n < (1ll << 31), "nms: bad box count");
   VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "nms: bad semantics selector");
   VB200_REQUIRE(num_keep_out != nullptr, "nms: null num_keep_out");
@@ -448,16 +494,19 @@ extern "C" int vb200_nms(const void* boxes, const void* scores, int dtype, int64
   VB200_REQUIRE(boxes && scores && keep_out && workspace, "nms: null pointer");
   VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "nms: boxes must be 16-byte aligned");
   const IouParams prm = make_iou_params(iou_threshold, semantics);
-  return nms_core((const float4*)boxes, (const float*)scores, n, prm, workspace, workspace_bytes, keep_out,
-                  num_keep_out, st);
+  if (dtype == VB200_F64)
+    return nms_core<double>((const double4a*)boxes, (const double*)scores, n, prm, workspace, workspace_bytes, keep_out,
+                            num_keep_out, st);
+  return nms_core<float>((const float4*)boxes, (const float*)scores, n, prm, workspace, workspace_bytes, keep_out,
+                         num_keep_out, st);
 }
 
 namespace vb200 {
 namespace {
 struct BnmsWs {
-  int* iota; int* order; float* scores_sorted; int64_t* cls_keys; int64_t* cls_sorted; int* rank_cm;
-  float4* boxes_cm; uint8_t* seg_flag; int* seg_start; int* num_seg; uint8_t* suppressed;
-  uint8_t* keep_by_rank; float* max_coord; float4* shifted; void* cub_temp; size_t cub_bytes;
+  int* iota; int* order; void* scores_sorted; int64_t* cls_keys; int64_t* cls_sorted; int* rank_cm;
+  void* boxes_cm; uint8_t* seg_flag; int* seg_start; int* num_seg; uint8_t* suppressed;
+  uint8_t* keep_by_rank; void* max_coord; void* shifted; void* cub_temp; size_t cub_bytes;
   size_t nms_off; size_t total;
 };
 BnmsWs carve_bnms(void* base, int64_t n) {
@@ -465,18 +514,18 @@ BnmsWs carve_bnms(void* base, int64_t n) {
   BnmsWs w;
   w.iota = c.take<int>(n);
   w.order = c.take<int>(n);
-  w.scores_sorted = c.take<float>(n);
+  w.scores_sorted = c.take<double>(n);
   w.cls_keys = c.take<int64_t>(n);
   w.cls_sorted = c.take<int64_t>(n);
   w.rank_cm = c.take<int>(n);
-  w.boxes_cm = c.take<float4>(n);
+  w.boxes_cm = c.take<double4a>(n);
   w.seg_flag = c.take<uint8_t>(n);
   w.seg_start = c.take<int>(n + 1);
   w.num_seg = c.take<int>(64);
   w.suppressed = c.take<uint8_t>(n);
   w.keep_by_rank = c.take<uint8_t>(n);
-  w.max_coord = c.take<float>(64);
-  w.shifted = c.take<float4>(n);
+  w.max_coord = c.take<double>(64);
+  w.shifted = c.take<double4a>(n);
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = c.take<char>(w.cub_bytes);
   w.nms_off = c.off;                       // trick strategy reuses the plain-nms pipeline
@@ -493,26 +542,13 @@ __global__ void scatter_keep_kernel(const uint8_t* __restrict__ suppressed, cons
 }  // namespace
 }  // namespace vb200
 
-extern "C" size_t vb200_batched_nms_workspace_bytes(int64_t n) {
-  if (n <= 0) return 0;
-  return carve_bnms(nullptr, n).total;
-}
-
-extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
-                                 int64_t n, double iou_threshold, int semantics, int strategy,
-                                 void* workspace, size_t workspace_bytes, int64_t* keep_out,
-                                 int64_t* num_keep_out, vb200_stream stream) {
-  VB200_REQUIRE(dtype == VB200_F32, "batched_nms: only float32 boxes are supported by this build (got dtype %d)", dtype);
-  VB200_REQUIRE(n >= 0 && n < (1ll << 31), "batched_nms: bad box count");
-  VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "batched_nms: bad semantics selector");
-  const bool wide_keys = (strategy & VB200_BNMS_WIDE_KEYS) != 0;
-  strategy &= ~VB200_BNMS_WIDE_KEYS;
-  VB200_REQUIRE(strategy >= VB200_BNMS_AUTO && strategy <= VB200_BNMS_TRICK, "batched_nms: bad strategy");
-  VB200_REQUIRE(num_keep_out != nullptr, "batched_nms: null num_keep_out");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
-  VB200_REQUIRE(boxes && scores && idxs && keep_out && workspace, "batched_nms: null pointer");
-  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "batched_nms: boxes must be 16-byte aligned");
+namespace vb200 {
+namespace {
+template <typename S>
+int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_t n, double iou_threshold, int semantics,
+              int strategy, bool wide_keys, void* workspace, size_t workspace_bytes, int64_t* keep_out,
+              int64_t* num_keep_out, cudaStream_t st) {
+  using Box = typename BoxOf<S>::type;
   BnmsWs w = carve_bnms(workspace, n);
   if (workspace_bytes < w.total) { set_error("batched_nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
   const IouParams prm = make_iou_params(iou_threshold, semantics);
@@ -521,13 +557,13 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
 
   if (strategy == VB200_BNMS_TRICK) {
     size_t tb = w.cub_bytes;
-    VB200_CUDA_TRY(cub::DeviceReduce::Max(w.cub_temp, tb, (const float*)boxes, w.max_coord, ni * 4, st));
+    VB200_CUDA_TRY(cub::DeviceReduce::Max(w.cub_temp, tb, (const S*)boxes, (S*)w.max_coord, ni * 4, st));
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
-    shift_boxes_kernel<<<grd, blk, 0, st>>>((const float4*)boxes, idxs, w.max_coord, w.shifted, ni);
+    shift_boxes_kernel<Box><<<grd, blk, 0, st>>>((const Box*)boxes, idxs, (const S*)w.max_coord, (Box*)w.shifted, ni);
     int rc = check_launch("shift_boxes_kernel");
     if (rc) return rc;
-    return nms_core(w.shifted, (const float*)scores, n, prm, (char*)workspace + w.nms_off,
-                    workspace_bytes - w.nms_off, keep_out, num_keep_out, st);
+    return nms_core<S>((const Box*)w.shifted, (const S*)scores, n, prm, (char*)workspace + w.nms_off,
+                       workspace_bytes - w.nms_off, keep_out, num_keep_out, st);
   }
 
   // ---- vanilla semantics, fused ------------------------------------------
@@ -535,7 +571,7 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   int rc = check_launch("iota_kernel");
   if (rc) return rc;
   size_t tb = w.cub_bytes;
-  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, (const float*)scores, w.scores_sorted, w.iota, w.order, ni, 0, 32, st));
+  VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(w.cub_temp, tb, (const S*)scores, (S*)w.scores_sorted, w.iota, w.order, ni, 0, (int)sizeof(S) * 8, st));
   g_launch_count.fetch_add(3, std::memory_order_relaxed);
   // num_seg[1] doubles as the "class id outside [0, 2^16)" flag of the narrow-key fast path
   VB200_CUDA_TRY(cudaMemsetAsync(w.num_seg, 0, 2 * sizeof(int), st));
@@ -548,7 +584,7 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   VB200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, w.cls_keys, w.cls_sorted, w.iota, w.rank_cm, ni, 0,
                                                  wide_keys ? 64 : 16, st));
   g_launch_count.fetch_add(wide_keys ? 9 : 3, std::memory_order_relaxed);
-  gather_boxes_cm_kernel<<<grd, blk, 0, st>>>((const float4*)boxes, w.order, w.rank_cm, w.cls_sorted, w.boxes_cm, w.seg_flag, ni);
+  gather_boxes_cm_kernel<Box><<<grd, blk, 0, st>>>((const Box*)boxes, w.order, w.rank_cm, w.cls_sorted, (Box*)w.boxes_cm, w.seg_flag, ni);
   rc = check_launch("gather_boxes_cm_kernel");
   if (rc) return rc;
   tb = w.cub_bytes;
@@ -556,7 +592,7 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   VB200_CUDA_TRY(cudaMemsetAsync(w.suppressed, 0, (size_t)n, st));
   const int grid = sm_count() * 1;
-  nms_segment_kernel<<<grid, kSegThreads, 0, st>>>(w.boxes_cm, w.seg_start, w.num_seg, ni, prm, w.suppressed);
+  nms_segment_kernel<Box><<<grid, kSegThreads, 0, st>>>((const Box*)w.boxes_cm, w.seg_start, w.num_seg, ni, prm, w.suppressed);
   rc = check_launch("nms_segment_kernel");
   if (rc) return rc;
   scatter_keep_kernel<<<grd, blk, 0, st>>>(w.suppressed, w.rank_cm, w.keep_by_rank, ni);
@@ -572,4 +608,33 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
     if (rc) return rc;
   }
   return 0;
+}
+}  // namespace
+}  // namespace vb200
+
+extern "C" size_t vb200_batched_nms_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return carve_bnms(nullptr, n).total;
+}
+
+extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
+                                 int64_t n, double iou_threshold, int semantics, int strategy,
+                                 void* workspace, size_t workspace_bytes, int64_t* keep_out,
+                                 int64_t* num_keep_out, vb200_stream stream) {
+  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64, "batched_nms: boxes must be float32 or float64 (got dtype %d)", dtype);
+  VB200_REQUIRE(n >= 0 && n < (1ll << 31), "batched_nms: bad box count");
+  VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "batched_nms: bad semantics selector");
+  const bool wide_keys = (strategy & VB200_BNMS_WIDE_KEYS) != 0;
+  strategy &= ~VB200_BNMS_WIDE_KEYS;
+  VB200_REQUIRE(strategy >= VB200_BNMS_AUTO && strategy <= VB200_BNMS_TRICK, "batched_nms: bad strategy");
+  VB200_REQUIRE(num_keep_out != nullptr, "batched_nms: null num_keep_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
+  VB200_REQUIRE(boxes && scores && idxs && keep_out && workspace, "batched_nms: null pointer");
+  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "batched_nms: boxes must be 16-byte aligned");
+  if (dtype == VB200_F64)
+    return bnms_core<double>(boxes, scores, idxs, n, iou_threshold, semantics, strategy, wide_keys, workspace, workspace_bytes,
+                             keep_out, num_keep_out, st);
+  return bnms_core<float>(boxes, scores, idxs, n, iou_threshold, semantics, strategy, wide_keys, workspace, workspace_bytes,
+                          keep_out, num_keep_out, st);
 }

@@ -124,25 +124,25 @@ void check_nms_inputs(const at::Tensor& dets, const at::Tensor& scores) {
               "dimension 0, got ", dets.size(0), " and ", scores.size(0));
 }
 
-at::Tensor as_f32_boxes(const at::Tensor& t, const char* op) {
-  // The reference instantiates float / double / Half.  Half is widened (its reference kernel
-  // already multiplies in float); double is refused rather than silently narrowed.
-  TORCH_CHECK(t.scalar_type() != at::kDouble, op,
-              ": float64 boxes are not supported by the vision_b200 CUDA kernels (float32 / float16 only)");
-  return t.to(at::kFloat).contiguous();
+// The reference instantiates float / double / Half.  float and double run natively (both arithmetics
+// are reproduced bit for bit); Half is widened to float (its reference kernel already multiplies in float).
+at::Tensor nms_operand(const at::Tensor& t) {
+  return (t.scalar_type() == at::kDouble ? t : t.to(at::kFloat)).contiguous();
 }
 
 at::Tensor nms(const at::Tensor& dets, const at::Tensor& scores, double iou_threshold) {
   check_nms_inputs(dets, scores);
+  TORCH_CHECK(dets.scalar_type() == scores.scalar_type(), "dets should have the same type as scores");
   at::cuda::CUDAGuard guard(dets.device());
   if (dets.numel() == 0) return at::empty({0}, dets.options().dtype(at::kLong));
-  at::Tensor boxes = as_f32_boxes(dets, "nms"), sc = as_f32_boxes(scores, "nms");
+  at::Tensor boxes = nms_operand(dets), sc = nms_operand(scores);
+  const int dt = boxes.scalar_type() == at::kDouble ? VB200_F64 : VB200_F32;
   const int64_t n = boxes.size(0);
   const size_t wsb = vb200_nms_workspace_bytes(n);
   at::Tensor ws = workspace(wsb, boxes);
   at::Tensor keep = at::empty({n}, boxes.options().dtype(at::kLong));
   at::Tensor count = at::empty({1}, boxes.options().dtype(at::kLong));
-  check_rc(vb200_nms(boxes.data_ptr(), sc.data_ptr(), VB200_F32, n, iou_threshold, g_nms_semantics.load(), ws.data_ptr(),
+  check_rc(vb200_nms(boxes.data_ptr(), sc.data_ptr(), dt, n, iou_threshold, g_nms_semantics.load(), ws.data_ptr(),
                      wsb, keep.data_ptr<int64_t>(), count.data_ptr<int64_t>(), cur_stream()),
            "nms");
   const int64_t k = count.item<int64_t>();   // the reference's masked_select sync (nms_kernel.cu:257)
@@ -155,7 +155,9 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
   TORCH_CHECK(idxs.dim() == 1 && idxs.size(0) == dets.size(0), "idxs should be a 1d tensor with one entry per box");
   at::cuda::CUDAGuard guard(dets.device());
   if (dets.numel() == 0) return at::empty({0}, dets.options().dtype(at::kLong));
-  at::Tensor boxes = as_f32_boxes(dets, "batched_nms"), sc = as_f32_boxes(scores, "batched_nms");
+  at::Tensor boxes = nms_operand(dets), sc = nms_operand(scores);
+  TORCH_CHECK(boxes.scalar_type() == sc.scalar_type(), "boxes should have the same type as scores");
+  const int dt = boxes.scalar_type() == at::kDouble ? VB200_F64 : VB200_F32;
   at::Tensor cls = idxs.to(at::kLong).contiguous();
   const int64_t n = boxes.size(0);
   const size_t wsb = vb200_batched_nms_workspace_bytes(n);
@@ -166,7 +168,7 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
   for (int attempt = 0; attempt < 2 && k < 0; ++attempt) {
     // first attempt speculates 16-bit class ids; -1 asks for the wide-key repeat (arbitrary int64 ids)
     const int strategy = VB200_BNMS_AUTO | (attempt ? VB200_BNMS_WIDE_KEYS : 0);
-    check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), VB200_F32, n, iou_threshold,
+    check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), dt, n, iou_threshold,
                                g_nms_semantics.load(), strategy, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
                                count.data_ptr<int64_t>(), cur_stream()),
              "batched_nms");
