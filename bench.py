@@ -34,10 +34,10 @@ if ROOT not in sys.path:
 
 ALG_BYTES = 55_705_600 + 20_000 + 50_176_000      # map + rois + output
 K_ROIS = 1000
-# dram__bytes_read.sum + dram__bytes_write.sum of roi_align_plane_kernel<2>, one launch of this workload,
-# from profiles/r1_roi_align_plane_v2.ncu-rep (68,618,752 + 10,597,120 B; most of the 50 MB output is still
+# dram__bytes_read.sum + dram__bytes_write.sum of roi_align_line_kernel<7, 2>, one launch of this workload,
+# from profiles/r1_roi_align_line_v3.ncu-rep (67,274,240 + 9,228,288 B; most of the 50 MB output is still
 # dirty in the 126 MB L2 when the capture ends)
-NCU_TRAFFIC_BYTES = 68_618_752 + 10_597_120
+NCU_TRAFFIC_BYTES = 67_274_240 + 9_228_288
 WORKLOAD = "roi_align fp32 1x256x200x272, 1000 RoIs, 7x7, scale 0.25, sampling_ratio 2, aligned=False (BASELINE configs[1])"
 
 
@@ -362,8 +362,8 @@ def main():
                        "api": "torchvision.ops.roi_align after vision_b200.install()"},
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
-                "traffic_source": "profiles/r1_roi_align_plane_v2.ncu-rep (ncu --set full, one launch)",
-                "kernel": "roi_align_plane_kernel<2> (+ ~2 us roi_align_geometry_kernel inside the same event pair)",
+                "traffic_source": "profiles/r1_roi_align_line_v3.ncu-rep (ncu --set full, one launch)",
+                "kernel": "roi_align_line_kernel<7, 2> (+ ~4 us roi_align_line_geometry_kernel inside the same event pair)",
                 "algorithmic_bytes": ALG_BYTES, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": world * K_ROIS / (e2e_ms / 1e3), "unit": "RoIs/s", "ms_per_step": e2e_ms,

@@ -107,6 +107,40 @@ def test_roi_align_plane_path_batched_and_sampling_ratios(vb, oracle):
         np.testing.assert_allclose(npy(got), want, **F32_TOL)
 
 
+def test_roi_align_line_path(vb, oracle):
+    """7x7 / sampling_ratio 2 takes the line-wise kernel: batched maps, odd widths, RoIs hanging outside the
+    map (zero rows / zero columns), degenerate and border-hugging RoIs, both lane orientations."""
+    from vision_b200 import workloads
+
+    for seed, (b, c, h, w), k in ((1, (3, 7, 40, 53), 300), (2, (1, 24, 64, 31), 257), (3, (2, 5, 33, 200), 500)):
+        x, rois, kw = workloads.cfg2_roi_align(seed=seed, k=k, batch=b, channels=c, height=h, width=w)
+        rois = rois.clone()
+        rois[::7, 1:3] -= 90.0                      # start outside the map
+        rois[1::11, 3:] += 400.0                    # end far outside
+        rois[2::13, 3:] = rois[2::13, 1:3]          # zero-size
+        rois[3::17, 1:] = torch.tensor([w * 4 - 6.0, h * 4 - 6.0, w * 4 + 0.0, h * 4 + 0.0])   # bottom-right corner
+        rois[4::19, 3] = rois[4::19, 1] + 700.0     # very wide, short
+        for aligned in (False, True):
+            want = oracle.roi_align(x.numpy(), rois.numpy(), 7, 0.25, 2, aligned)
+            with force_env("VB200_ROI_ALIGN_PATH", "line"):
+                got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2, aligned)
+            np.testing.assert_allclose(npy(got), want, **F32_TOL)
+            with force_env("VB200_ROI_ALIGN_PATH", "plane"):
+                if w % 4 == 0:
+                    got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2, aligned)
+                    np.testing.assert_allclose(npy(got), want, **F32_TOL)
+
+
+def test_roi_align_cfg2_thread_per_bin_plane_path(vb, oracle):
+    from vision_b200 import workloads
+
+    x, rois, kw = workloads.cfg2_roi_align(channels=16)
+    want = oracle.roi_align(x.numpy(), rois.numpy(), 7, 0.25, 2, False)
+    with force_env("VB200_ROI_ALIGN_PATH", "plane"):
+        got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2, False)
+    np.testing.assert_allclose(npy(got), want, **F32_TOL)
+
+
 def test_roi_align_edge_cases(vb, oracle):
     x = torch.randn(1, 3, 8, 8, device=DEV)
     assert vb.ops.roi_align(x, torch.zeros(0, 5, device=DEV), 7).shape == (0, 3, 7, 7)

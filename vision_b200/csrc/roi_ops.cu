@@ -299,6 +299,219 @@ roi_align_plane_kernel(const float* __restrict__ input, const PackedEnt* __restr
 }
 
 // ---------------------------------------------------------------------------
+// Plane-resident path, line-wise lanes (P x P bins, SR x SR samples, P*SR*2 <= 32).
+// ---------------------------------------------------------------------------
+// The thread-per-bin kernel above is bound by shared-memory bank conflicts: its 32 lanes read
+// ~5 bin rows x 7 bin columns, i.e. random banks (3.2 wavefronts per LDS).  Here a warp owns one
+// (RoI, plane) pair and its lanes are the P*SR*2 taps of ONE line of the sampling grid: lane
+// (j, c) = tap c of sample j along the "lane axis".  The other ("loop") axis is walked by all
+// lanes together, so one LDS reads 28 words of a single image row (lane axis = x) or a single
+// image column (lane axis = y, conflict-free over any 32 consecutive rows because the pitch is
+// odd).  The geometry kernel picks, per RoI, the axis with fewer conflicts (simulation on cfg2:
+// 1.39 wavefronts per LDS vs 3.1).  Weights factor the same way: the lane-axis weight is a lane
+// constant, the loop-axis pair (1-l, l) is warp-uniform.  The P*SR*2 lanes of a bin column are
+// folded with a 2-step exchange that leaves each lane with two finished bins, stored directly.
+struct LineTab {            // per RoI, 96 words
+  uint2 lane[32];           // (BYTE offset | lane_is_y, weight) of this lane's tap; lanes >= P*SR*2: (lane 0's, 0)
+  uint2 loop[14];           // (BYTE offset of the low tap, l) per loop-axis sample
+  uint32_t lane_is_y;       // 0: lanes walk x, loop walks y (neighbour at +pitch); 1: the transpose
+  int32_t batch;
+  uint32_t pad[2];
+};
+static_assert(sizeof(LineTab) == 384, "LineTab layout");
+
+__host__ __device__ inline int line_pitch(int W) { return (W + 2) | 1; }   // odd, >= W + 2 zero columns
+
+// Packed (lo, l) of one axis sample with the same two tricks as PackedEnt.
+__device__ __forceinline__ void packed_axis(const AxisEnt<float>& a, int size, int& lo, float& l) {
+  if (a.lo < 0) { lo = size; l = 0.f; }
+  else if (a.hi == a.lo) { lo = size - 2; l = 1.f; }
+  else { lo = a.lo; l = a.l; }
+}
+
+// Max number of DISTINCT addresses of the active lanes that share a bank.
+__device__ __forceinline__ int bank_multiplicity(uint32_t addr, bool active, int lane) {
+  const unsigned same = __match_any_sync(0xffffffffu, active ? addr : 0xffffffffu - lane);
+  const bool leader = active && (__ffs(same) - 1 == lane);
+  const unsigned bank = __match_any_sync(0xffffffffu, leader ? (addr & 31u) : 64u + lane);
+  int m = leader ? __popc(bank) : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m;
+}
+
+template <int P, int SR>
+__global__ void __launch_bounds__(256)
+roi_align_line_geometry_kernel(const float* __restrict__ rois, LineTab* __restrict__ tab, int K, int H, int W,
+                               float scale, int aligned, int pitch, int force_axis) {
+  constexpr int NS = P * SR, NL = NS * 2;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= K) return;
+  const RoiGeom<float> g = roi_geometry<float, float>(rois + (int64_t)n * 5, scale, P, P, SR, aligned != 0, false);
+  const bool act = lane < NL;
+  const int j = act ? lane >> 1 : 0, c = lane & 1;
+  int xlo, ylo; float xl, yl;
+  packed_axis(axis_entry<float>(sample_coord<float>(g.start_w, g.bin_w, j / SR, j % SR, SR), W), W, xlo, xl);
+  packed_axis(axis_entry<float>(sample_coord<float>(g.start_h, g.bin_h, j / SR, j % SR, SR), H), H, ylo, yl);
+  const uint32_t ax = (uint32_t)(xlo + c), ay = (uint32_t)((ylo + c) * pitch);
+  const int mx = bank_multiplicity(ax, act, lane), my = bank_multiplicity(ay, act, lane);
+  const bool lane_is_y = force_axis ? force_axis == 2 : my < mx;
+  LineTab* t = tab + n;
+  const float l = lane_is_y ? yl : xl;
+  // lanes beyond the taps repeat lane 0's address with weight 0: a broadcast, never an extra bank conflict
+  const uint32_t my_off = (lane_is_y ? ay : ax) * 4u + (lane_is_y ? 1u : 0u);   // bit 0: lane axis
+  const uint32_t off0 = __shfl_sync(0xffffffffu, my_off, 0);
+  t->lane[lane] = act ? make_uint2(my_off, __float_as_uint(c ? l : 1.f - l)) : make_uint2(off0, 0u);
+  if (lane < NS) {   // loop-axis sample `lane`
+    int lo; float ll;
+    if (lane_is_y) packed_axis(axis_entry<float>(sample_coord<float>(g.start_w, g.bin_w, lane / SR, lane % SR, SR), W), W, lo, ll);
+    else packed_axis(axis_entry<float>(sample_coord<float>(g.start_h, g.bin_h, lane / SR, lane % SR, SR), H), H, lo, ll);
+    t->loop[lane] = make_uint2((uint32_t)(lane_is_y ? lo : lo * pitch) * 4u, __float_as_uint(ll));
+  }
+  if (lane == 0) { t->lane_is_y = lane_is_y; t->batch = g.batch; }
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+constexpr int kLineThreads = 1024;
+constexpr int kLineStageBytes = (kLineThreads / 32) * 2 * 128;   // per warp: two 128-byte slots (loop entries + header)
+
+__host__ __device__ inline size_t line_plane_bytes(int H, int pitch) { return (((size_t)(H + 2) * pitch * 4) + 15) & ~(size_t)15; }
+
+template <int P, int SR>
+__global__ void __launch_bounds__(kLineThreads, 1)
+roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict__ tab, float* __restrict__ output,
+                      int B, int C, int H, int W, int K, int pitch) {
+  constexpr int NS = P * SR, NL = NS * 2, NB = P * P;
+  static_assert(NL <= 32 && SR == 2 && P <= 8 && NS == 14, "lane mapping: 4 lanes per bin column, two finished bins per lane");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const uint32_t plane_s = smem_u32(plane);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  const uint32_t stage_s = plane_s + (uint32_t)line_plane_bytes(H, pitch) + (uint32_t)warp * 256u;
+  const int64_t total = (int64_t)B * C * K;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per;
+  const int64_t w1 = min(total, w0 + per);
+
+  // zero columns [W, pitch) of every row and the two zero rows, once
+  for (int r = warp; r < H; r += NW)
+    for (int col = W + lane; col < pitch; col += 32) plane[r * pitch + col] = 0.f;
+  for (int i = H * pitch + tid; i < (H + 2) * pitch; i += blockDim.x) plane[i] = 0.f;
+
+  const int q = lane & 3, grp = lane >> 2;
+  const bool hi = (q & 2) != 0, lo = (q & 1) != 0;
+  const float inv_count = 1.0f / (float)(SR * SR);
+  // output offsets of this lane's two finished bins (loop-axis bins 2q, 2q+1 of lane group grp)
+  const int off_x = 2 * q * P + grp, off_y = 2 * q + grp * P;       // lane axis x: bin = k * P + grp; y: the transpose
+  const bool st0 = grp < P && 2 * q < P, st1 = grp < P && 2 * q + 1 < P;
+  const int64_t ostep = (int64_t)NW * C * NB;
+
+  int64_t w = w0;
+  while (w < w1) {
+    const int pl = (int)(w / K);              // plane index = b * C + c
+    const int r0 = (int)(w - (int64_t)pl * K);
+    const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
+    const int b = pl / C;
+    __syncthreads();                           // everyone is done with the previous plane
+    {
+      const float* src = input + (int64_t)pl * H * W;
+      for (int r = warp; r < H; r += NW) {
+        const float* s = src + (int64_t)r * W;
+        const uint32_t d = plane_s + (uint32_t)(r * pitch) * 4u;
+        for (int col = lane; col < W; col += 32) cp_async4(d + col * 4u, s + col);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // The geometry of the next RoI travels one iteration ahead: the lane entry in registers, the
+    // 14 loop entries + header (128 B) by cp.async into this warp's staging slot.
+    int n = r0 + warp;
+    uint2 le = make_uint2(0u, 0u);
+    uint32_t slot = 0;
+    if (n < r1) {
+      le = __ldg(&tab[n].lane[lane]);
+      if (lane < 8) cp_async16(stage_s + lane * 16u, reinterpret_cast<const uint4*>(tab + n) + 16 + lane);
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");   // the plane has landed
+    __syncthreads();
+
+    float* __restrict__ outp = output + ((int64_t)n * C + (pl - b * C)) * NB;
+    for (; n < r1; n += NW, outp += ostep) {
+      const int nn = n + NW;
+      uint2 le_next = make_uint2(0u, 0u);
+      __syncwarp();
+      if (nn < r1) {
+        le_next = __ldg(&tab[nn].lane[lane]);
+        if (lane < 8) cp_async16(stage_s + (slot ^ 128u) + lane * 16u, reinterpret_cast<const uint4*>(tab + nn) + 16 + lane);
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const uint32_t st = stage_s + slot;
+      const bool lane_is_y = (le.x & 1u) != 0;             // bit 0 of every lane offset carries the lane axis
+      bool mine = true;
+      if (B > 1) mine = (int)lds_u32(st + 116u) == b;      // header word 1: the RoI's batch index
+      if (mine) {
+        const uint32_t base0 = plane_s + (le.x & ~3u);
+        const uint32_t base1 = base0 + (lane_is_y ? 4u : (uint32_t)pitch * 4u);
+        const float wl = __uint_as_float(le.y);
+        float acc[8];
+        acc[7] = 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const uint4 ee = lds_u128(st + p * 16u);     // the two samples of loop-axis bin p
+          const float a0 = lds_f32(base0 + ee.x), a1 = lds_f32(base1 + ee.x);
+          const float b0 = lds_f32(base0 + ee.z), b1 = lds_f32(base1 + ee.z);
+          const float ta = fmaf(__uint_as_float(ee.y), a1 - a0, a0);
+          const float tb = fmaf(__uint_as_float(ee.w), b1 - b0, b0);
+          acc[p] = (ta + tb) * wl;
+        }
+        // fold the 4 lanes of a bin column: after two exchanges lane q holds loop-axis bins 2q, 2q+1
+        float r4[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float send = hi ? acc[m] : acc[4 + m], keep = hi ? acc[4 + m] : acc[m];
+          r4[m] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        float s2[2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float send = lo ? r4[m] : r4[2 + m], keep = lo ? r4[2 + m] : r4[m];
+          s2[m] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        float* __restrict__ o = outp + (lane_is_y ? off_y : off_x);
+        if (st0) o[0] = s2[0] * inv_count;
+        if (st1) o[lane_is_y ? 1 : P] = s2[1] * inv_count;
+      }
+      slot ^= 128u;
+      le = le_next;
+    }
+    w += (r1 - r0);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // roi_pool: one thread per output element, bin window shared arithmetic
 // (roi_pool_kernel.cu:15-78) — integer/compare work, bit-exact incl. argmax.
 // ---------------------------------------------------------------------------
@@ -402,24 +615,37 @@ using namespace vb200;
 
 namespace {
 // Path selection shared by the workspace query and the launcher.
-bool roi_align_use_plane(int dtype, const void* input, int batch, int channels, int height, int width,
-                         int num_rois, int sampling_ratio) {
-  if (dtype != VB200_F32) return false;
-  if (height < 2 || width < 2) return false;
+//   0 generic, 1 plane-resident thread-per-bin (any pooled size, sampling_ratio 1..4),
+//   2 plane-resident line-wise lanes (7x7 bins, sampling_ratio 2: the detection-head shape).
+int roi_align_path(int dtype, const void* input, int batch, int channels, int height, int width, int num_rois,
+                   int pooled_h, int pooled_w, int sampling_ratio) {
+  if (dtype != VB200_F32) return 0;
+  if (height < 2 || width < 2) return 0;
   const size_t plane_bytes = ((size_t)(height + 2) * plane_pitch(width) + 2) * 4;
   const bool fits = plane_bytes + 1024 <= (size_t)max_smem_optin();
   const bool sr_ok = sampling_ratio >= 1 && sampling_ratio <= 4;
   const bool align_ok = width % 4 == 0 && (input == nullptr || ((uintptr_t)input % 16) == 0);
+  const bool bins_ok = pooled_h * pooled_w <= kPlaneMaxThreads;
+  const bool plane_ok = fits && sr_ok && align_ok && bins_ok;
+  const size_t line_bytes = line_plane_bytes(height, line_pitch(width)) + kLineStageBytes;
+  const bool line_ok = pooled_h == 7 && pooled_w == 7 && sampling_ratio == 2 &&
+                       line_bytes + 1024 <= (size_t)max_smem_optin();
   const int64_t pairs = (int64_t)batch * channels * num_rois;
-  bool use_plane = fits && sr_ok && align_ok && pairs >= 4096;
-  const char* force = getenv("VB200_ROI_ALIGN_PATH");   // "generic" | "plane" (testing / profiling)
-  if (force && force[0] == 'g') use_plane = false;
-  if (force && force[0] == 'p') use_plane = fits && sr_ok && align_ok;
-  return use_plane;
+  int path = pairs >= 4096 ? (line_ok ? 2 : plane_ok ? 1 : 0) : 0;
+  const char* force = getenv("VB200_ROI_ALIGN_PATH");   // "generic" | "plane" | "line" (testing / profiling)
+  if (force && force[0] == 'g') path = 0;
+  if (force && force[0] == 'p') path = plane_ok ? 1 : 0;
+  if (force && force[0] == 'l') path = line_ok ? 2 : 0;
+  return path;
 }
 size_t roi_align_geo_bytes(int num_rois, int pooled_h, int pooled_w, int sampling_ratio) {
   const size_t geo = (size_t)num_rois * (pooled_h + pooled_w) * sampling_ratio * sizeof(PackedEnt);
   return (geo + 255) & ~(size_t)255;
+}
+size_t roi_align_ws_bytes(int path, int num_rois, int pooled_h, int pooled_w, int sampling_ratio) {
+  if (path == 1) return roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio) + (size_t)num_rois * 4;
+  if (path == 2) return (size_t)num_rois * sizeof(LineTab);
+  return 0;
 }
 }  // namespace
 
@@ -427,8 +653,13 @@ extern "C" size_t vb200_roi_align_workspace_bytes(int dtype, int batch, int chan
                                                   int num_rois, int pooled_h, int pooled_w,
                                                   int sampling_ratio) {
   if (num_rois <= 0 || channels <= 0) return 0;
-  if (!roi_align_use_plane(dtype, nullptr, batch, channels, height, width, num_rois, sampling_ratio)) return 0;
-  return roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio) + (size_t)num_rois * 4;
+  // the larger of the two plane paths, so the answer does not depend on the environment override
+  size_t a = 0;
+  for (int path = 1; path <= 2; ++path) {
+    const size_t b = roi_align_ws_bytes(path, num_rois, pooled_h, pooled_w, sampling_ratio);
+    a = b > a ? b : a;
+  }
+  return roi_align_path(dtype, nullptr, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio) ? a : 0;
 }
 
 extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void* output, int dtype,
@@ -445,9 +676,28 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == VB200_F32) {
     const size_t geo_pad = roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio);
-    const bool use_plane = roi_align_use_plane(dtype, input, batch, channels, height, width, num_rois, sampling_ratio) &&
-                           workspace != nullptr && workspace_bytes >= geo_pad + (size_t)num_rois * 4 &&
-                           ((uintptr_t)workspace % 16) == 0 && pooled_h * pooled_w <= kPlaneMaxThreads;
+    int path = roi_align_path(dtype, input, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio);
+    if (path && (workspace == nullptr || ((uintptr_t)workspace % 16) != 0 ||
+                 workspace_bytes < roi_align_ws_bytes(path, num_rois, pooled_h, pooled_w, sampling_ratio)))
+      path = 0;
+    if (path == 2) {
+      const int pitch = line_pitch(width);
+      const size_t smem = line_plane_bytes(height, pitch) + kLineStageBytes;
+      LineTab* tab = (LineTab*)workspace;
+      const char* fa = getenv("VB200_ROI_LINE_AXIS");   // diagnosis: "x" | "y" pins the lane axis
+      const int force_axis = fa ? (fa[0] == 'y' ? 2 : fa[0] == 'x' ? 1 : 0) : 0;
+      roi_align_line_geometry_kernel<7, 2><<<ceil_div(num_rois * 32, 256), 256, 0, st>>>(
+          (const float*)rois, tab, num_rois, height, width, (float)spatial_scale, aligned, pitch, force_axis);
+      int rc = check_launch("roi_align_line_geometry_kernel");
+      if (rc) return rc;
+      const int64_t pairs = (int64_t)batch * channels * num_rois;
+      const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+      VB200_CUDA_TRY(cudaFuncSetAttribute(roi_align_line_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_line_kernel<7, 2><<<grid, kLineThreads, smem, st>>>((const float*)input, tab, (float*)output, batch,
+                                                                    channels, height, width, num_rois, pitch);
+      return check_launch("roi_align_line_kernel");
+    }
+    const bool use_plane = path == 1;
     if (use_plane) {
       const int pitch = plane_pitch(width);
       const size_t plane_bytes = ((size_t)(height + 2) * pitch + 2) * 4;
