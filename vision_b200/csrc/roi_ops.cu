@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(256)
 roi_align_line_geometry_kernel(const float* __restrict__ rois, LineTab* __restrict__ tab, int K, int H, int W,
                                float scale, int aligned, int pitch, int force_axis) {
   constexpr int NS = P * SR, NL = NS * 2;
+  asm volatile("griddepcontrol.launch_dependents;");   // the gather kernel may start staging its first plane
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (n >= K) return;
   const RoiGeom<float> g = roi_geometry<float, float>(rois + (int64_t)n * 5, scale, P, P, SR, aligned != 0, false);
@@ -447,6 +448,7 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
     }
     // The geometry of the next RoI travels one iteration ahead: the lane entry in registers, the
     // 14 loop entries + header (128 B) by cp.async into this warp's staging slot.
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the table is complete from here on (no-op after the first time)
     int n = r0 + warp;
     uint2 le = make_uint2(0u, 0u);
     uint32_t slot = 0;
@@ -693,8 +695,16 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       const int64_t pairs = (int64_t)batch * channels * num_rois;
       const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
       VB200_CUDA_TRY(cudaFuncSetAttribute(roi_align_line_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_line_kernel<7, 2><<<grid, kLineThreads, smem, st>>>((const float*)input, tab, (float*)output, batch,
-                                                                    channels, height, width, num_rois, pitch);
+      // programmatic dependent launch: the gather kernel zeroes its pads and stages its first plane while
+      // the geometry kernel is still running, and waits (griddepcontrol.wait) before it reads the table
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kLineThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      VB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, roi_align_line_kernel<7, 2>, (const float*)input, (const LineTab*)tab,
+                                        (float*)output, batch, channels, height, width, num_rois, pitch));
       return check_launch("roi_align_line_kernel");
     }
     const bool use_plane = path == 1;
