@@ -255,6 +255,38 @@ def test_nms_float64(vb, oracle, sem):
     assert torch.equal(tv.ops.nms(t(b[:3000]), t(s[:3000]), 0.5), vb.ops.nms(t(b[:3000]), t(s[:3000]), 0.5))
 
 
+@pytest.mark.parametrize("path", ["chain", "mask"])
+def test_nms_both_suppression_paths(vb, oracle, path):
+    """Plain nms: the single-CTA sequential kernel and the all-SM IoU mask + scan give the oracle's indices at
+    sizes either side of the switch-over, in both arithmetics and for fp64."""
+    rng = np.random.default_rng(23)
+    for n in (1, 63, 64, 65, 300, 2500, 5000):
+        b = rng.random((n, 4), dtype=np.float32) * 100
+        b[:, 2:] = b[:, :2] + rng.random((n, 2), dtype=np.float32) * 40 + 0.5
+        s = rng.random(n, dtype=np.float32)
+        for sem, mode in (("cuda", oracle.NMS_MODE_CUDA), ("cpu", oracle.NMS_MODE_CPU)):
+            _set(vb, sem)
+            try:
+                with force_env("VB200_NMS_PATH", path):
+                    keep = vb.ops.nms(t(b), t(s), 0.3)
+                    keep64 = vb.ops.nms(t(b.astype(np.float64)), t(s.astype(np.float64)), 0.3) if n in (65, 2500) else None
+            finally:
+                _set(vb, "cuda")
+            assert np.array_equal(npy(keep), oracle.nms(b, s, 0.3, mode)), (n, sem, path)
+            if keep64 is not None:
+                assert np.array_equal(npy(keep64), oracle.nms(b.astype(np.float64), s.astype(np.float64), 0.3, mode))
+    # degenerate boxes (zero area, inverted) push the mask kernel onto its exact-only branch
+    n = 700
+    b = rng.random((n, 4), dtype=np.float32) * 50
+    b[:, 2:] = b[:, :2] + rng.random((n, 2), dtype=np.float32) * 30
+    b[::5, 2] = b[::5, 0]                      # zero width
+    b[3::11, [0, 2]] = b[3::11, [2, 0]]        # inverted
+    s = rng.random(n, dtype=np.float32)
+    with force_env("VB200_NMS_PATH", path):
+        keep = vb.ops.nms(t(b), t(s), 0.4)
+    assert np.array_equal(npy(keep), oracle.nms(b, s, 0.4, oracle.NMS_MODE_CUDA))
+
+
 def test_nms_threshold_narrowing_semantics(vb):
     a = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 2]], dtype=torch.float32, device=DEV)   # iou == 0.2f exactly
     sc = torch.tensor([1.0, 0.5], device=DEV)
@@ -331,6 +363,41 @@ def test_batched_nms_strategies_classes_and_edges(vb, oracle):
         assert np.array_equal(npy(keep), want), (n, ncls, ids)
     e = vb.ops.batched_nms(torch.zeros(0, 4, device=DEV), torch.zeros(0, device=DEV), torch.zeros(0, dtype=torch.int64, device=DEV), 0.5)
     assert e.shape == (0,) and e.dtype == torch.int64
+
+
+def test_batched_nms_mask_scan_and_chain_paths_agree(vb, oracle):
+    """Classes of <= 2048 boxes go through the all-SM IoU mask + bit-word scan, longer ones through the per-class
+    sequential chain, in the same call; VB200_BNMS_PATH=chain pins the sequential kernel."""
+    rng = np.random.default_rng(17)
+    n = 40_000
+    b = rng.random((n, 4), dtype=np.float32) * 300
+    b[:, 2:] = b[:, :2] + rng.random((n, 2), dtype=np.float32) * 80 + 1
+    s = (rng.permutation(n).astype(np.float32)) / n
+    i = rng.integers(1, 40, n).astype(np.int64)
+    i[:6000] = 0                       # one class of 6000+ boxes (sequential path), 39 of ~870 (mask path)
+    i[6000:6003] = 77                  # a 3-box class
+    i[6003] = 78                       # a single-box class
+    for sem, mode in (("cuda", oracle.NMS_MODE_CUDA), ("cpu", oracle.NMS_MODE_CPU)):
+        want = oracle.batched_nms(b, s, i, 0.4, mode=mode, device_is_cuda=True)
+        _set(vb, sem)
+        try:
+            keep = vb.ops.batched_nms(t(b), t(s), t(i), 0.4)
+            with force_env("VB200_BNMS_PATH", "chain"):
+                keep_chain = vb.ops.batched_nms(t(b), t(s), t(i), 0.4)
+        finally:
+            _set(vb, "cuda")
+        assert np.array_equal(npy(keep), want) and np.array_equal(npy(keep_chain), want)
+    # segment boundaries on and around 64-position block edges, class sizes 63/64/65/128/2048/2049
+    sizes = [63, 64, 65, 128, 1, 2048, 2049, 191] + [700] * 35      # n > 25000: vanilla semantics
+    i = np.repeat(np.arange(len(sizes)), sizes).astype(np.int64)
+    n = len(i)
+    b = rng.random((n, 4), dtype=np.float32) * 120
+    b[:, 2:] = b[:, :2] + rng.random((n, 2), dtype=np.float32) * 50 + 1
+    s = (rng.permutation(n).astype(np.float32)) / n
+    perm = rng.permutation(n)
+    b, s, i = b[perm], s[perm], i[perm]
+    keep = vb.ops.batched_nms(t(b), t(s), t(i), 0.5)
+    assert np.array_equal(npy(keep), oracle.batched_nms(b, s, i, 0.5, mode=oracle.NMS_MODE_CUDA, device_is_cuda=True))
 
 
 # =============================== deform_conv2d ==================================

@@ -25,7 +25,7 @@ elif op == "batched_nms":
     b, s, i = [t.to(dev) for t in workloads.cfg3_batched_nms(clustered=len(sys.argv) > 3)]
     fn = lambda: vb.ops.batched_nms(b, s, i, 0.5)
 elif op == "nms":
-    b, s, i = [t.to(dev) for t in workloads.cfg3_batched_nms(n=20000)]
+    b, s, i = [t.to(dev) for t in workloads.cfg3_batched_nms(n=int(os.environ.get('NMS_N', '20000')))]
     fn = lambda: vb.ops.nms(b, s, 0.5)
 elif op in ("resize", "resize_noaa"):
     x = workloads.cfg5_resize(device=dev, batch=32)

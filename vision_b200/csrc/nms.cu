@@ -34,7 +34,6 @@ namespace vb200 {
 namespace {
 
 constexpr int kSegThreads = 1024;
-constexpr int64_t kSegmentMaxSingle = 3072;   // plain nms: above this use the mask path
 
 struct IouParams {
   float thr_f;
@@ -44,6 +43,9 @@ struct IouParams {
   double mid;
   int s_even;
   int use_div;
+  // fp32 filter in front of the exact test (bnms_mask_kernel): t = fma(-mid_f, den, inter) has the sign of
+  // inter - mid*den whenever |t| > eps_f * den (see make_iou_params); anything else is re-tested exactly.
+  float mid_f, eps_f;
 };
 
 // Both reference predicates have the form  q >= S  with q = RN_f32(inter/den) and S a float:
@@ -72,6 +74,11 @@ inline IouParams make_iou_params(double thr, int semantics) {
   uint32_t bits;
   memcpy(&bits, &S, 4);
   p.s_even = (bits & 1u) == 0u;
+  // v = inter - mid*den = (inter - mid_f*den) - (mid - mid_f)*den and t = RN(inter - mid_f*den):
+  // |v - t| <= 2^-24 |t| + 2^-24 |mid| den, so |t| > 2^-21 |mid_f| den (four times the second term) fixes the sign
+  // of v and rules out v == 0.  Tiny or non-finite operands never pass the filter (den > 1e-30 is required).
+  p.mid_f = (float)p.mid;
+  p.eps_f = p.use_div ? INFINITY : nextafterf(ldexpf(fabsf(p.mid_f), -21), INFINITY);
   return p;
 }
 
@@ -182,13 +189,303 @@ __global__ void shift_boxes_kernel(const Box* __restrict__ boxes, const int64_t*
   }
 }
 
+// ---- segmented mask + scan (batched_nms, segments up to kBnmsMaxLen boxes) ----------------------
+// The greedy chain of a class is short (n_c sequential decisions); the ~n_c^2/2 IoU tests are not, and
+// with one CTA per class they keep only as many SMs busy as there are classes.  So the tests are done
+// first, by every SM: row p (position in the class-major sorted order) gets `wpr` 64-bit words (stored
+// word-major: word k of row p at mask[k * n + p]), word k covering positions [64 (p/64 + k), +64) - bit set <=> that later box of the same class has
+// IoU(p, .) > threshold.  The per-class chain then only walks bit words.
+constexpr int kBnmsWpr = 33;                         // words per row
+constexpr int kBnmsMaxLen = 64 * (kBnmsWpr - 1);     // a segment this long spans at most kBnmsWpr position blocks
+
+// Largest idx with seg_start[idx] <= p.
+__device__ __forceinline__ int find_segment(const int* __restrict__ seg_start, int nseg, int p) {
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(seg_start + mid) <= p) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Column-side terms of the fp32 filter, fixed per lane for a whole tile.
+template <typename Box> struct ColTerms;
+template <> struct ColTerms<float4> {
+  float4 b; float bw, bh, sb; bool bad;
+  __device__ __forceinline__ void set(const float4 v) {
+    b = v; bw = sub_rn(v.z, v.x); bh = sub_rn(v.w, v.y); sb = mul_rn(bw, bh);
+    bad = !(bw >= 0.f) || !(bh >= 0.f) || !(sb <= 1e37f);   // inverted / NaN / huge boxes: exact test only
+  }
+};
+template <> struct ColTerms<double4a> {
+  double4a b; bool bad;
+  __device__ __forceinline__ void set(const double4a v) { b = v; bad = true; }   // fp64 boxes: the exact test is the only test
+};
+
+// fp32 filter in front of the exact test.  For a proper row box (aw, ah >= 0, Sa > 1e-29) and a proper column
+// box, inter <= min(Sa, Sb) up to rounding, so den > Sa / 2 > 1e-30: the den guard of make_iou_params holds
+// without a per-test check.  Returns the decision; `unsure` when only the exact test may decide.
+template <int SEM>
+__device__ __forceinline__ bool iou_gt_filter(const float4 a, const float area_a, const ColTerms<float4>& c, const IouParams p,
+                                              bool& unsure) {
+  // Only one extent is clamped: with mid > 0 (required by the caller) a negative h makes inter <= 0 and the
+  // decision "not greater", which is what the exact test returns for an empty intersection.
+  const float w = fmaxf(sub_rn(fminf(a.z, c.b.z), fmaxf(a.x, c.b.x)), 0.f);
+  const float h = sub_rn(fminf(a.w, c.b.w), fmaxf(a.y, c.b.y));
+  const float inter = mul_rn(w, h);
+  const float den = SEM == VB200_NMS_CUDA ? sub_rn(__fmaf_rn(c.bw, c.bh, area_a), inter) : sub_rn(add_rn(area_a, c.sb), inter);
+  const float t = __fmaf_rn(-p.mid_f, den, inter);
+  unsure = !(fabsf(t) > mul_rn(p.eps_f, den));
+  return t > 0.f;
+}
+template <int SEM>
+__device__ __forceinline__ bool iou_gt_filter(const double4a, const double, const ColTerms<double4a>&, const IouParams, bool& unsure) {
+  unsure = true;
+  return false;
+}
+
+// CTA = one block of 64 rows (positions), 2 warps (small CTAs: a row block has 1..33 tiles, and a CTA lives as
+// long as its busiest warp); a warp owns whole 64x64 tiles (column block kb = i + warp, i + warp + 2, ...): its
+// lanes hold two column boxes each, the rows are broadcast from shared memory, and one vote per 32 IoU tests
+// delivers the bits.  min/max, compares and votes share the half-rate ALU pipe, which is what bounds this
+// kernel, so everything else (result capture, unsure flags, column validity) is kept off it or out of the loop.
+template <typename Box, int SEM, int kMaskWarps>
+__global__ void __launch_bounds__(kMaskWarps * 32)
+bnms_mask_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_start, const int* __restrict__ num_seg_ptr,
+                 int n, int wpr, int max_len, IouParams prm, unsigned long long* __restrict__ mask) {
+  using S = typename ScalarOf<Box>::type;
+  __shared__ Box rbx[64];
+  __shared__ S rarea[64];
+  __shared__ int rend[64];             // segment end of row r, or 0 when the row is not handled here
+  __shared__ unsigned long long s_word[kMaskWarps][64];   // a warp's tile: row r's 64 column bits
+  __shared__ int s_kmax, s_rowbad;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nseg = seg_start ? *num_seg_ptr : 1;      // no table: one segment [0, n)
+  if (tid == 0) { s_kmax = -1; s_rowbad = 0; }
+  __syncthreads();
+  if (tid < 64) {
+    const int p = 64 * i + tid;
+    int e = 0;
+    Box a = zero_box((Box*)nullptr);
+    if (p < n) {
+      int s = 0, ee = n;
+      if (seg_start) {
+        const int sg = find_segment(seg_start, nseg, p);
+        s = __ldg(seg_start + sg);
+        ee = (sg + 1 < nseg) ? __ldg(seg_start + sg + 1) : n;
+      }
+      if (ee - s <= max_len) { e = ee; a = boxes[p]; }     // longer segments take the sequential path
+    }
+    const S aw = sub_rn(a.z, a.x), ah = sub_rn(a.w, a.y), sa = mul_rn(aw, ah);
+    rbx[tid] = a;
+    rarea[tid] = sa;
+    rend[tid] = e;
+    if (e > 0) {
+      atomicMax(&s_kmax, (e - 1) >> 6);
+      if (!(aw >= (S)0) || !(ah >= (S)0) || !(sa > (S)1e-29) || !(sa <= (S)1e37)) s_rowbad = 1;   // the filter's den bound needs proper rows
+    }
+  }
+  __syncthreads();
+  const int kmax = s_kmax;
+  const bool exact_only = s_rowbad != 0 || prm.use_div != 0 || !(prm.mid_f > 0.f);
+  for (int kb = i + warp; kb <= kmax; kb += kMaskWarps) {
+    const int col0 = kb * 64;
+    ColTerms<Box> c0, c1;
+    c0.set((col0 + lane < n) ? boxes[col0 + lane] : zero_box((Box*)nullptr));
+    c1.set((col0 + 32 + lane < n) ? boxes[col0 + 32 + lane] : zero_box((Box*)nullptr));
+    bool unsure = exact_only | c0.bad | c1.bad;
+    if (!exact_only) {
+#pragma unroll 8
+      for (int r = 0; r < 64; ++r) {
+        const Box a = rbx[r];
+        const S aa = rarea[r];
+        bool u0, u1;
+        const bool p0 = iou_gt_filter<SEM>(a, aa, c0, prm, u0);
+        const bool p1 = iou_gt_filter<SEM>(a, aa, c1, prm, u1);
+        const unsigned int v0 = __ballot_sync(0xffffffffu, p0), v1 = __ballot_sync(0xffffffffu, p1);
+        unsure |= u0 | u1;
+        if (lane == 0) s_word[warp][r] = ((unsigned long long)v1 << 32) | v0;
+      }
+    }
+    if (__any_sync(0xffffffffu, unsure)) {       // warp-uniform and rare: (re)do the tile with the exact predicate
+      for (int r = 0; r < 64; ++r) {
+        const Box a = rbx[r];
+        const S aa = rarea[r];
+        const unsigned int v0 = __ballot_sync(0xffffffffu, iou_gt(a, aa, c0.b, prm));
+        const unsigned int v1 = __ballot_sync(0xffffffffu, iou_gt(a, aa, c1.b, prm));
+        if (lane == 0) s_word[warp][r] = ((unsigned long long)v1 << 32) | v0;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int r = lane + 32 * hh;
+      const int p = 64 * i + r, e = rend[r];
+      if (e > 0 && col0 < e) {
+        unsigned long long word = s_word[warp][r];
+        // keep columns in (p, e): later positions of the same class
+        const int first = p + 1 - col0, last = e - col0;         // valid bit range [first, last)
+        if (first > 0) word &= first >= 64 ? 0ull : ~0ull << first;
+        if (last < 64) word &= ~0ull >> (64 - last);
+        mask[(size_t)(kb - i) * n + p] = word;          // word-major: the 64 rows of a tile are 512 contiguous bytes
+      }
+    }
+    __syncwarp();              // s_word is rewritten by the next tile
+  }
+}
+
+// Chain of one segment [s, e) over the mask, kScanThreads = 256 threads.  256 positions per step: their
+// diagonal words (4 per row) are staged in shared memory one step ahead, warp 0 walks the 256 decisions, then
+// warp j folds the rows that were kept into removed-word j for the blocks after the step.
+__device__ __forceinline__ void segment_scan(const unsigned long long* __restrict__ mask, int wpr, int n, int s, int e,
+                                             uint8_t* __restrict__ suppressed, unsigned long long* removed /* 2 (wpr + 4) */,
+                                             unsigned long long (*dgbuf)[256][4] /* 2 */, unsigned long long* keptw /* 4 */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kfirst = s >> 6, klast = (e - 1) >> 6;
+  unsigned long long* keptbits = removed + (wpr + 4);     // one bit per position of the segment, set when kept
+  for (int t = tid; t < 2 * (wpr + 4); t += blockDim.x) removed[t] = 0ull;
+  // thread t owns words (row t, 0..3) of a step
+  auto fetch = [&](int kb0, unsigned long long (&v)[4]) {
+    const int pos = 64 * kb0 + tid;
+#pragma unroll
+    for (int wq = 0; wq < 4; ++wq) {
+      const int kb = kb0 + wq;
+      v[wq] = 0ull;
+      if (pos >= s && pos < e && kb <= klast && wq >= (tid >> 6)) v[wq] = mask[(size_t)(kb - (pos >> 6)) * n + pos];
+    }
+  };
+  // Long segments (plain nms on tens of thousands of boxes) PULL: at the start of a step every thread folds the
+  // four words of the step for some of the rows kept so far - independent, sector-sized loads, as many in
+  // flight as there are threads x unroll - instead of pushing each step's kept rows into every later word.
+  const bool pull = (klast - kfirst + 1) > 72;
+  unsigned long long nxt[4];
+  fetch(kfirst, nxt);
+  int buf = 0;
+  for (int kb0 = kfirst; kb0 <= klast; kb0 += 4, buf ^= 1) {
+    unsigned long long (*dg)[4] = dgbuf[buf];
+#pragma unroll
+    for (int wq = 0; wq < 4; ++wq) dg[tid][wq] = nxt[wq];
+    if (kb0 + 4 <= klast) fetch(kb0 + 4, nxt);         // in flight during the chain below
+    if (pull && kb0 > kfirst) {
+      unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+      const int r_end = 64 * kb0;
+      const int nw = min(4, klast - kb0 + 1);       // words of this step that exist
+      for (int r0 = s + tid; r0 < r_end; r0 += 8 * (int)blockDim.x) {
+        // all loads are unconditional (suppressed rows are masked afterwards, rows past the end re-read the
+        // last row), so the 8 flag loads and then the 32 word loads are in flight together
+        unsigned long long keepm[8], v[8][4];
+        int rr[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = r0 + u * (int)blockDim.x;
+          rr[u] = min(r, r_end - 1);
+          // kept bits of earlier steps live in shared memory (removed[] doubles as the bitmap once a block is decided)
+          keepm[u] = (r < r_end && ((keptbits[(rr[u] >> 6) - kfirst] >> (rr[u] & 63)) & 1ull)) ? ~0ull : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned long long* __restrict__ q = mask + (size_t)(kb0 - (rr[u] >> 6)) * n + rr[u];   // lanes = consecutive rows
+#pragma unroll
+          for (int wq = 0; wq < 4; ++wq) v[u][wq] = wq < nw ? q[(size_t)wq * n] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int wq = 0; wq < 4; ++wq) acc[wq] |= v[u][wq] & keepm[u];
+      }
+#pragma unroll
+      for (int wq = 0; wq < 4; ++wq) {
+        const unsigned int lo32 = __reduce_or_sync(0xffffffffu, (unsigned int)acc[wq]);
+        const unsigned int hi32 = __reduce_or_sync(0xffffffffu, (unsigned int)(acc[wq] >> 32));
+        if (lane == 0) atomicOr(&removed[kb0 - kfirst + wq], ((unsigned long long)hi32 << 32) | lo32);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // Every lane runs the same chain on the block's diagonal words, which are pulled into registers first so
+      // that no load sits between two decisions; then the lanes fold the kept rows' words of the later blocks.
+      unsigned long long rem[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rem[g] = removed[kb0 - kfirst + g];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int base = 64 * (kb0 + g);
+        unsigned long long kept = 0ull;
+        if (base < e) {
+          unsigned long long inseg = ~0ull;       // positions of this block inside [s, e)
+          if (s > base) inseg &= ~0ull << (s - base);
+          if (e - base < 64) inseg &= ~0ull >> (64 - (e - base));
+          unsigned long long rg = rem[g] | ~inseg;
+#pragma unroll
+          for (int h0 = 0; h0 < 64; h0 += 32) {
+            unsigned long long d[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) d[b] = dg[g * 64 + h0 + b][g];
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+              if (!((rg >> (h0 + b)) & 1ull)) { kept |= 1ull << (h0 + b); rg |= d[b]; }
+          }
+#pragma unroll
+          for (int w2 = g + 1; w2 < 4; ++w2) {
+            unsigned long long acc = 0ull;
+            if ((kept >> lane) & 1ull) acc |= dg[g * 64 + lane][w2];
+            if ((kept >> (lane + 32)) & 1ull) acc |= dg[g * 64 + 32 + lane][w2];
+            const unsigned int lo32 = __reduce_or_sync(0xffffffffu, (unsigned int)acc);
+            const unsigned int hi32 = __reduce_or_sync(0xffffffffu, (unsigned int)(acc >> 32));
+            rem[w2] |= ((unsigned long long)hi32 << 32) | lo32;
+          }
+        }
+        if (lane == 0) { keptw[g] = kept; if (kb0 + g <= klast) keptbits[kb0 - kfirst + g] = kept; }
+      }
+    }
+    __syncthreads();
+    {
+      const int pos = 64 * kb0 + tid;
+      if (pos >= s && pos < e) suppressed[pos] = ((keptw[tid >> 6] >> (tid & 63)) & 1ull) ? 0 : 1;
+    }
+    if (!pull) {   // push: warp j folds this step's kept rows into removed-word j (pull mode: later steps fetch what they need)
+      for (int j = kb0 + 4 + warp; j <= klast; j += (int)(blockDim.x >> 5)) {
+        unsigned long long acc = 0ull;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const unsigned long long kw = keptw[g];
+          const int blk = kb0 + g;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int b = lane + 32 * hh;
+            if ((kw >> b) & 1ull) acc |= mask[(size_t)(j - blk) * n + (64 * blk + b)];
+          }
+        }
+        const unsigned int lo32 = __reduce_or_sync(0xffffffffu, (unsigned int)acc);
+        const unsigned int hi32 = __reduce_or_sync(0xffffffffu, (unsigned int)(acc >> 32));
+        if (lane == 0) removed[j - kfirst] |= ((unsigned long long)hi32 << 32) | lo32;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int kScanThreads = 256;
+__global__ void __launch_bounds__(kScanThreads, 1)
+bnms_scan_kernel(const unsigned long long* __restrict__ mask, int wpr, int max_len, const int* __restrict__ seg_start,
+                 const int* __restrict__ num_seg_ptr, int n_total, uint8_t* __restrict__ suppressed) {
+  extern __shared__ unsigned long long sc_removed[];          // 2 (wpr + 4) words: removed bits, kept bits
+  __shared__ unsigned long long sc_dg[2][256][4], sc_keptw[4];
+  const int nseg = seg_start ? *num_seg_ptr : 1;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const int s = seg_start ? seg_start[seg] : 0;
+    const int e = (seg_start && seg + 1 < nseg) ? seg_start[seg + 1] : n_total;
+    if (e - s > 0 && e - s <= max_len) segment_scan(mask, wpr, n_total, s, e, suppressed, sc_removed, sc_dg, sc_keptw);
+  }
+}
+
 // One CTA per segment; see file header.  `suppressed` (zero on entry) is indexed by
 // position in the sorted order; on exit suppressed[p] == 0  <=>  box p is kept.
 template <typename Box>
 __global__ void __launch_bounds__(kSegThreads, 1)
 nms_segment_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_start,
                    const int* __restrict__ num_seg_ptr, int n_total, IouParams prm,
-                   uint8_t* __restrict__ suppressed) {
+                   uint8_t* __restrict__ suppressed, int min_len) {
   using S = typename ScalarOf<Box>::type;
   __shared__ Box sb[64];
   __shared__ S sarea[64];
@@ -204,6 +501,7 @@ nms_segment_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_st
     const int s = seg_start ? seg_start[seg] : 0;
     const int e = seg_start ? ((seg + 1 < nseg) ? seg_start[seg + 1] : n_total) : n_total;
     const int n = e - s;
+    if (n <= min_len) continue;                     // short segments: bnms_mask_kernel + bnms_scan_kernel
     for (int b0 = 0; b0 < n; b0 += 64) {
       const int nb = min(64, n - b0);
       // stage the block's boxes; collect which of them are already suppressed
@@ -279,84 +577,6 @@ nms_segment_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_st
   }
 }
 
-// ---- mask path (single large segment) -------------------------------------
-// tile (rb, cb), cb >= rb, 64 threads = 64 rows; col boxes in smem; mask[row * col_blocks + cb]
-template <typename Box>
-__global__ void __launch_bounds__(64)
-nms_mask_kernel(const Box* __restrict__ boxes, int n, int col_blocks, IouParams prm,
-                unsigned long long* __restrict__ mask) {
-  // linear upper-triangular tile index -> (rb, cb)
-  const long long t = blockIdx.x;
-  // rows are enumerated so that row rb has (col_blocks - rb) tiles
-  // solve rb: t < sum_{r<=rb} (col_blocks - r)
-  const double cbd = (double)col_blocks;
-  long long rb = (long long)floor(((2.0 * cbd + 1.0) - sqrt((2.0 * cbd + 1.0) * (2.0 * cbd + 1.0) - 8.0 * (double)t)) * 0.5);
-  if (rb < 0) rb = 0;
-  // fix up rounding
-  while (rb > 0 && t < rb * col_blocks - rb * (rb - 1) / 2) --rb;
-  while (t >= (rb + 1) * col_blocks - (rb + 1) * rb / 2) ++rb;
-  const long long first = rb * col_blocks - rb * (rb - 1) / 2;
-  const int cb = (int)(rb + (t - first));
-
-  using S = typename ScalarOf<Box>::type;
-  __shared__ Box cbx[64];
-  const int col0 = cb * 64, row0 = (int)rb * 64;
-  const int ncol = min(64, n - col0), nrow = min(64, n - row0);
-  if ((int)threadIdx.x < ncol) cbx[threadIdx.x] = boxes[col0 + threadIdx.x];
-  __syncthreads();
-  if ((int)threadIdx.x < nrow) {
-    const int row = row0 + threadIdx.x;
-    const Box a = boxes[row];
-    const S aa = mul_rn(sub_rn(a.z, a.x), sub_rn(a.w, a.y));
-    unsigned long long bits = 0;
-    const int start = (cb == (int)rb) ? (int)threadIdx.x + 1 : 0;
-    for (int i = start; i < ncol; ++i)
-      if (iou_gt(a, aa, cbx[i], prm)) bits |= 1ull << i;
-    mask[(long long)row * col_blocks + cb] = bits;
-  }
-}
-
-__global__ void __launch_bounds__(1024, 1)
-nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int col_blocks,
-                uint8_t* __restrict__ suppressed) {
-  extern __shared__ unsigned long long removed[];   // col_blocks words
-  __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long s_kept;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < col_blocks; i += blockDim.x) removed[i] = 0;
-  __syncthreads();
-  for (int nb = 0; nb < col_blocks; ++nb) {
-    const int row0 = nb * 64;
-    const int cnt = min(64, n - row0);
-    if (tid < 64) diag[tid] = (tid < cnt) ? mask[(long long)(row0 + tid) * col_blocks + nb] : 0ull;
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long rem = removed[nb], kept = 0;
-#pragma unroll 8
-      for (int i = 0; i < 64; ++i) {
-        const unsigned long long d = diag[i];
-        if (i < cnt && !((rem >> i) & 1ull)) { kept |= 1ull << i; rem |= d; }
-      }
-      s_kept = kept;
-    }
-    __syncthreads();
-    const unsigned long long kept = s_kept;
-    if (tid < cnt) suppressed[row0 + tid] = ((kept >> tid) & 1ull) ? 0 : 1;
-    // OR the mask rows of the kept boxes into removed[nb+1 ..]
-    for (int j = nb + 1 + tid; j < col_blocks; j += blockDim.x) {
-      unsigned long long acc = removed[j];
-      unsigned long long k = kept;
-      while (k) {
-        const int i = __ffsll((long long)k) - 1;
-        k &= k - 1;
-        acc |= mask[(long long)(row0 + i) * col_blocks + j];
-      }
-      removed[j] = acc;
-    }
-    __syncthreads();
-  }
-}
-
 struct NotZero {
   __host__ __device__ __forceinline__ bool operator()(const uint8_t v) const { return v == 0; }
 };
@@ -419,7 +639,7 @@ NmsWs carve_nms(void* base, int64_t n) {
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = c.take<char>(w.cub_bytes);
   const int64_t cb = ceil_div64(n, 64);
-  w.mask = (n > kSegmentMaxSingle) ? c.take<unsigned long long>((size_t)n * cb) : nullptr;
+  w.mask = c.take<unsigned long long>((size_t)n * cb);
   w.total = c.off;
   return w;
 }
@@ -428,21 +648,28 @@ NmsWs carve_nms(void* base, int64_t n) {
 template <typename Box>
 int run_single_segment(const Box* boxes_sorted, int64_t n, IouParams prm, uint8_t* suppressed,
                        unsigned long long* mask, cudaStream_t st) {
-  if (n <= kSegmentMaxSingle || mask == nullptr) {
+  const char* force = getenv("VB200_NMS_PATH");      // "chain" | "mask" (testing / profiling)
+  bool use_mask = true;            // measured faster at every size (0.09 vs 0.20 ms at n = 1000; 0.15 vs 0.87 ms at n = 3000)
+  if (force && force[0] == 'c') use_mask = false;
+  if (force && force[0] == 'm') use_mask = true;
+  if (!use_mask || mask == nullptr) {
     VB200_CUDA_TRY(cudaMemsetAsync(suppressed, 0, (size_t)n, st));
-    nms_segment_kernel<Box><<<1, kSegThreads, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, prm, suppressed);
+    nms_segment_kernel<Box><<<1, kSegThreads, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, prm, suppressed, 0);
     return check_launch("nms_segment_kernel");
   }
+  // IoU bit matrix on every SM (row pitch = the number of 64-position blocks), then one CTA walks the chain
   const int cb = (int)ceil_div64(n, 64);
-  const long long tiles = (long long)cb * (cb + 1) / 2;
-  nms_mask_kernel<Box><<<(unsigned)tiles, 64, 0, st>>>(boxes_sorted, (int)n, cb, prm, mask);
-  int rc = check_launch("nms_mask_kernel");
+  if (prm.semantics == VB200_NMS_CUDA)
+    bnms_mask_kernel<Box, VB200_NMS_CUDA, 8><<<cb, 256, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, cb, (int)n, prm, mask);
+  else
+    bnms_mask_kernel<Box, VB200_NMS_CPU, 8><<<cb, 256, 0, st>>>(boxes_sorted, nullptr, nullptr, (int)n, cb, (int)n, prm, mask);
+  int rc = check_launch("bnms_mask_kernel");
   if (rc) return rc;
-  const size_t smem = (size_t)cb * sizeof(unsigned long long);
-  if (smem > 48 * 1024)
-    VB200_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_scan_kernel<<<1, 1024, smem, st>>>(mask, (int)n, cb, suppressed);
-  return check_launch("nms_scan_kernel");
+  const size_t smem = 2 * (size_t)(cb + 4) * sizeof(unsigned long long);
+  if (smem > 24 * 1024)
+    VB200_CUDA_TRY(cudaFuncSetAttribute(bnms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bnms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, cb, (int)n, nullptr, nullptr, (int)n, suppressed);
+  return check_launch("bnms_scan_kernel");
 }
 
 template <typename S>
@@ -507,7 +734,7 @@ struct BnmsWs {
   int* iota; int* order; void* scores_sorted; int64_t* cls_keys; int64_t* cls_sorted; int* rank_cm;
   void* boxes_cm; uint8_t* seg_flag; int* seg_start; int* num_seg; uint8_t* suppressed;
   uint8_t* keep_by_rank; void* max_coord; void* shifted; void* cub_temp; size_t cub_bytes;
-  size_t nms_off; size_t total;
+  unsigned long long* mask; size_t nms_off; size_t total;
 };
 BnmsWs carve_bnms(void* base, int64_t n) {
   Carver c(base);
@@ -528,6 +755,7 @@ BnmsWs carve_bnms(void* base, int64_t n) {
   w.shifted = c.take<double4a>(n);
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = c.take<char>(w.cub_bytes);
+  w.mask = c.take<unsigned long long>((size_t)n * kBnmsWpr);
   w.nms_off = c.off;                       // trick strategy reuses the plain-nms pipeline
   c.off += carve_nms(nullptr, n).total;
   w.total = c.off;
@@ -591,8 +819,31 @@ int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_
   VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, w.iota, w.seg_flag, w.seg_start, w.num_seg, ni, st));
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   VB200_CUDA_TRY(cudaMemsetAsync(w.suppressed, 0, (size_t)n, st));
+  const char* mp = getenv("VB200_BNMS_PATH");       // "chain": per-class sequential kernel only (testing / profiling)
+  const bool use_mask = !(mp && mp[0] == 'c');
+  if (use_mask) {
+    const char* mw = getenv("VB200_BNMS_WARPS");     // tuning: warps per mask CTA (2 | 4 | 8)
+    const int warps = mw ? atoi(mw) : 8;
+#define VB200_LAUNCH_MASK(SEMV, WV)                                                                        \
+  bnms_mask_kernel<Box, SEMV, WV><<<ceil_div(ni, 64), WV * 32, 0, st>>>((const Box*)w.boxes_cm, w.seg_start, \
+                                                                        w.num_seg, ni, kBnmsWpr, kBnmsMaxLen, prm, w.mask)
+    if (semantics == VB200_NMS_CUDA) {
+      if (warps == 2) VB200_LAUNCH_MASK(VB200_NMS_CUDA, 2); else if (warps == 8) VB200_LAUNCH_MASK(VB200_NMS_CUDA, 8); else VB200_LAUNCH_MASK(VB200_NMS_CUDA, 4);
+    } else {
+      if (warps == 2) VB200_LAUNCH_MASK(VB200_NMS_CPU, 2); else if (warps == 8) VB200_LAUNCH_MASK(VB200_NMS_CPU, 8); else VB200_LAUNCH_MASK(VB200_NMS_CPU, 4);
+    }
+#undef VB200_LAUNCH_MASK
+    rc = check_launch("bnms_mask_kernel");
+    if (rc) return rc;
+  }
   const int grid = sm_count() * 1;
-  nms_segment_kernel<Box><<<grid, kSegThreads, 0, st>>>((const Box*)w.boxes_cm, w.seg_start, w.num_seg, ni, prm, w.suppressed);
+  if (use_mask) {
+    bnms_scan_kernel<<<grid, kScanThreads, 2 * (kBnmsWpr + 4) * 8, st>>>(w.mask, kBnmsWpr, kBnmsMaxLen, w.seg_start, w.num_seg, ni, w.suppressed);
+    rc = check_launch("bnms_scan_kernel");
+    if (rc) return rc;
+  }
+  nms_segment_kernel<Box><<<grid, kSegThreads, 0, st>>>((const Box*)w.boxes_cm, w.seg_start, w.num_seg, ni, prm, w.suppressed,
+                                                          use_mask ? kBnmsMaxLen : 0);
   rc = check_launch("nms_segment_kernel");
   if (rc) return rc;
   scatter_keep_kernel<<<grd, blk, 0, st>>>(w.suppressed, w.rank_cm, w.keep_by_rank, ni);
