@@ -8,17 +8,14 @@
 //   * order = stable radix sort of scores (descending);  batched: a second
 //     stable sort by class id turns the score order into class-major segments
 //     whose inner order is still score-descending;
-//   * "segment" kernel: one CTA per class segment walks the segment in blocks of
-//     64 boxes: (1) the 64x64 diagonal IoU bit-matrix by warp ballot, (2) one
-//     thread resolves the greedy chain inside the block on bit-words,
-//     (3) all threads test the still-alive later boxes against the <=64 boxes
-//     kept in this block (boxes kept in shared memory, broadcast reads).  Only
-//     kept boxes ever act as suppressors, suppressed boxes are skipped — this
-//     is the reference's greedy order exactly, with no N x N/64 mask in HBM.
-//     All classes run concurrently (grid = segments), replacing ~80 Python
-//     iterations x ~10 launches + syncs;
-//   * "mask" path for a single huge segment (plain nms, n > kSegmentMaxSingle):
-//     upper-triangular 64x64 tiles over all SMs -> bit mask, then a one-CTA scan;
+//   * mask + scan (default): bnms_mask_kernel computes the IoU bit matrix of every class on all SMs
+//     (64x64 tiles per warp, one vote per 32 tests, fp32 filter in front of the exact predicate),
+//     bnms_scan_kernel walks each class's greedy chain on bit words (one CTA per class).  Plain nms
+//     is the same pair with a single segment;
+//   * "segment" kernel (classes longer than 2048 boxes): one CTA per class segment walks the segment
+//     in blocks of 64 boxes: (1) the 64x64 diagonal IoU bit-matrix by warp ballot, (2) one thread
+//     resolves the greedy chain inside the block on bit-words, (3) all threads test the still-alive
+//     later boxes against the <=64 boxes kept in this block.  No mask memory, any segment length;
 //   * kept indices are emitted in global score order by flag compaction.
 // IoU arithmetic is written with explicit round-to-nearest intrinsics so that
 // the selected semantics (compiled-CUDA-reference or CPU-reference) is
