@@ -27,9 +27,13 @@ elif op == "batched_nms":
 elif op == "nms":
     b, s, i = [t.to(dev) for t in workloads.cfg3_batched_nms(n=int(os.environ.get('NMS_N', '20000')))]
     fn = lambda: vb.ops.nms(b, s, 0.5)
-elif op in ("resize", "resize_noaa"):
+elif op in ("resize", "resize_noaa", "resize_u8", "resize_f32"):
     x = workloads.cfg5_resize(device=dev, batch=32)
-    fn = lambda: vb.transforms.resize(x, [224, 224], antialias=(op == "resize"))
+    if op == "resize_u8":
+        x = (x.float() * 255).round().to(torch.uint8)
+    if op == "resize_f32":
+        x = x[:16].float()
+    fn = lambda: vb.transforms.resize(x, [224, 224], antialias=(op != "resize_noaa"))
 elif op in ("deform", "deform_f32"):
     dt = torch.bfloat16 if op == "deform" else torch.float32
     xi, off, w, bi, m = [t.to(dev) for t in workloads.cfg4_deform_conv2d(batch=int(os.environ.get('DCN_BATCH', '8')), dtype=dt)]

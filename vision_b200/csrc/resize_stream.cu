@@ -1,4 +1,5 @@
-// resize_stream.cu — bilinear-antialias DOWNSCALE fast path (the cfg5 regime: 2160x3840 -> 224x224).
+// resize_stream.cu — bilinear-antialias DOWNSCALE fast path (the cfg5 regime: 2160x3840 -> 224x224; fp16, bf16,
+// uint8 and fp32 storage).
 //
 // Reference route (torchvision/transforms/v2/functional/_geometry.py:340-360): cast to fp32 (full
 // size pass), aten::_upsample_bilinear2d_aa (one thread per output pixel looping over ~20x36 taps,
@@ -47,7 +48,7 @@ __device__ __forceinline__ int interval_lo(float scale, int i, int in_size) {
 }
 
 // ATen span + sequential total for output index o (UpSample.cuh:303-331), bilinear filter
-__device__ __forceinline__ void aa_span(float scale, int o, int in_size, int* xmin_o, float* xmc_o, float* total_o) {
+__device__ __forceinline__ void aa_span(float scale, int o, int in_size, int* xmin_o, int* xend_o, float* xmc_o, float* total_o) {
   const float support = scale, invscale = 1.0f / scale;           // scale >= 1 on this path
   const float c = centre(scale, o);
   const int xmin = max((int)(c - support + 0.5f), 0);
@@ -59,41 +60,77 @@ __device__ __forceinline__ void aa_span(float scale, int o, int in_size, int* xm
     a = a < 0.f ? -a : a;
     total += a < 1.f ? 1.f - a : 0.f;
   }
-  *xmin_o = xmin; *xmc_o = xmc; *total_o = total;
+  *xmin_o = xmin; *xend_o = xmin + xsize; *xmc_o = xmc; *total_o = total;
 }
 
-__device__ __forceinline__ float aa_weight(float scale, int x, int xmin, float xmc, float total) {
+// weight of input x for an output with span [xmin, xend): ATen drops what its integer span excludes even when
+// the filter argument is (just) inside the support
+__device__ __forceinline__ float aa_weight(float scale, int x, int xmin, int xend, float xmc, float total) {
   float a = ((float)(x - xmin) + xmc + 0.5f) * (1.0f / scale);
   a = a < 0.f ? -a : a;
   const float w = a < 1.f ? 1.f - a : 0.f;
-  return (x >= xmin && total != 0.f) ? __fdiv_rn(w, total) : (x >= xmin ? w : 0.f);
+  const bool in_span = x >= xmin && x < xend;
+  return (in_span && total != 0.f) ? __fdiv_rn(w, total) : (in_span ? w : 0.f);
 }
 
-template <typename T> struct Pair;
-template <> struct Pair<__half> {
-  static __device__ __forceinline__ float2 cvt(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+// Storage types: PPW pixels per 32-bit shared-memory word; pair(rowp, q) = pixels 2q, 2q+1 of the thread's slot
+// run as fp32 (q is a compile-time constant after unrolling, so the word loads are shared between pairs).
+template <typename T> struct Px;
+template <> struct Px<__half> {
+  static constexpr int PPW = 2;
+  static __device__ __forceinline__ float2 pair(const uint32_t* rowp, int q) {
+    const uint32_t u = rowp[q];
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  }
 };
-template <> struct Pair<__nv_bfloat16> {
-  static __device__ __forceinline__ float2 cvt(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+template <> struct Px<__nv_bfloat16> {
+  static constexpr int PPW = 2;
+  static __device__ __forceinline__ float2 pair(const uint32_t* rowp, int q) {
+    const uint32_t u = rowp[q];
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
 };
+template <> struct Px<float> {
+  static constexpr int PPW = 1;
+  static __device__ __forceinline__ float2 pair(const uint32_t* rowp, int q) {
+    const uint2 u = *reinterpret_cast<const uint2*>(rowp + 2 * q);      // the slot starts on an even pixel
+    return make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
+  }
+};
+template <> struct Px<uint8_t> {
+  static constexpr int PPW = 4;
+  // byte b -> float without the conversion unit: 0x4B000000 | b is 2^23 + b exactly
+  static __device__ __forceinline__ float2 pair(const uint32_t* rowp, int q) {
+    const uint32_t u = rowp[q >> 1];
+    const uint32_t lo = __byte_perm(u, 0x4B000000u, (q & 1) ? 0x7442 : 0x7440);
+    const uint32_t hi = __byte_perm(u, 0x4B000000u, (q & 1) ? 0x7443 : 0x7441);
+    return make_float2(__uint_as_float(lo) - 8388608.0f, __uint_as_float(hi) - 8388608.0f);
+  }
+};
+template <typename T> __device__ __forceinline__ T store_px(float v) { return from_acc<T, float>(v); }
+// _geometry.py:352-359 for integer images: round half to even, then the cast (bilinear weights are convex: no clamp needed,
+// the saturating conversion is a guard only)
+template <> __device__ __forceinline__ uint8_t store_px<uint8_t>(float v) { return (uint8_t)__float2uint_rn(fminf(fmaxf(v, 0.f), 255.f)); }
 
-// T: 16-bit storage type.  LW: 32-bit words (pixel pairs) each thread reads per row.
+// T: storage type (fp16, bf16, fp32, uint8).  NP: pixel PAIRS each thread reads per row.
 // NW: consumer warps the kernel is compiled for (block = (n_cwarps + 1) * 32 <= (NW + 1) * 32).
-template <typename T, int LW, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 && LW <= 10) ? 3 : 1)
+template <typename T, int NP, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 && NP <= 12) ? 3 : 1)
 resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamParams p, int n_cwarps) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: [stages][row_pitch] | full[S] empty[S] | totx[OW] xminx[OW] xmcx[OW] | toty.. | rowA[band] rowB[band] rowK[band]
+  // layout: [stages][row_pitch] | full[S] empty[S] | totx[OW] xmcx[OW] xminx[OW] xendx[OW] | toty.. | rowA[band] rowB[band] rowK[band]
   unsigned char* stages = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)p.n_stages * p.row_pitch);
   uint64_t* empty = full + p.n_stages;
   float* totx = reinterpret_cast<float*>(empty + p.n_stages);
   float* xmcx = totx + p.out_w;
   int* xminx = reinterpret_cast<int*>(xmcx + p.out_w);
-  float* toty = reinterpret_cast<float*>(xminx + p.out_w);
+  int* xendx = xminx + p.out_w;
+  float* toty = reinterpret_cast<float*>(xendx + p.out_w);
   float* ymcy = toty + p.out_h;
   int* yminy = reinterpret_cast<int*>(ymcy + p.out_h);
-  float* rowA = reinterpret_cast<float*>(yminy + p.out_h);
+  int* yendy = yminy + p.out_h;
+  float* rowA = reinterpret_cast<float*>(yendy + p.out_h);
   float* rowB = rowA + p.band_cap;
   int* rowK = reinterpret_cast<int*>(rowB + p.band_cap);
 
@@ -115,8 +152,8 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   for (int s = 0; s < p.n_stages; ++s)
     for (int b = row_bytes + tid * 4; b < p.row_pitch; b += nthreads * 4)
       *reinterpret_cast<uint32_t*>(stages + (size_t)s * p.row_pitch + b) = 0u;
-  for (int o = tid; o < p.out_w; o += nthreads) aa_span(p.scale_w, o, p.in_w, &xminx[o], &xmcx[o], &totx[o]);
-  for (int o = tid; o < p.out_h; o += nthreads) aa_span(p.scale_h, o, p.in_h, &yminy[o], &ymcy[o], &toty[o]);
+  for (int o = tid; o < p.out_w; o += nthreads) aa_span(p.scale_w, o, p.in_w, &xminx[o], &xendx[o], &xmcx[o], &totx[o]);
+  for (int o = tid; o < p.out_h; o += nthreads) aa_span(p.scale_h, o, p.in_h, &yminy[o], &yendy[o], &ymcy[o], &toty[o]);
   __syncthreads();
   for (int rl = tid; rl < nrows; rl += nthreads) {
     const int r = r0 + rl;
@@ -126,8 +163,8 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
     while (k > 0 && !at_or_past(p.scale_h, k - 1, r)) --k;
     while (k < p.out_h && at_or_past(p.scale_h, k, r)) ++k;
     rowK[rl] = k;
-    rowA[rl] = (k < p.out_h) ? aa_weight(p.scale_h, r, yminy[k], ymcy[k], toty[k]) : 0.f;
-    rowB[rl] = (k >= 1) ? aa_weight(p.scale_h, r, yminy[k - 1], ymcy[k - 1], toty[k - 1]) : 0.f;
+    rowA[rl] = (k < p.out_h) ? aa_weight(p.scale_h, r, yminy[k], yendy[k], ymcy[k], toty[k]) : 0.f;
+    rowB[rl] = (k >= 1) ? aa_weight(p.scale_h, r, yminy[k - 1], yendy[k - 1], ymcy[k - 1], toty[k - 1]) : 0.f;
   }
   fence_proxy_async();
   __syncthreads();
@@ -155,24 +192,26 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   const bool have = i <= p.out_w;
   const int lo = have ? interval_lo(p.scale_w, i, p.in_w) : p.in_w;
   const int hi = have ? ((i >= p.out_w) ? p.in_w : interval_lo(p.scale_w, i + 1, p.in_w)) : p.in_w;
-  const int e = lo & ~1;                          // word-aligned first pixel slot
+  constexpr int PPW = Px<T>::PPW;
+  constexpr int ALIGN = PPW > 2 ? PPW : 2;        // the slot starts on a 32-bit word AND on a pixel pair
+  const int e = lo & ~(ALIGN - 1);
   // weights kept as packed fp32 pairs: the inner loop is FFMA2 (fma.rn.f32x2, sm_100) — one issue slot
-  // for the two pixels of a 32-bit word
-  unsigned long long wA2[LW], wB2[LW];
+  // for two pixels
+  unsigned long long wA2[NP], wB2[NP];
 #pragma unroll
-  for (int t = 0; t < LW; ++t) {
+  for (int t = 0; t < NP; ++t) {
     float wa[2], wb[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int x = e + 2 * t + h;
       const bool in_iv = have && x >= lo && x < hi;
-      wa[h] = (in_iv && i < p.out_w) ? aa_weight(p.scale_w, x, xminx[i], xmcx[i], totx[i]) : 0.f;
-      wb[h] = (in_iv && i >= 1) ? aa_weight(p.scale_w, x, xminx[i - 1], xmcx[i - 1], totx[i - 1]) : 0.f;
+      wa[h] = (in_iv && i < p.out_w) ? aa_weight(p.scale_w, x, xminx[i], xendx[i], xmcx[i], totx[i]) : 0.f;
+      wb[h] = (in_iv && i >= 1) ? aa_weight(p.scale_w, x, xminx[i - 1], xendx[i - 1], xmcx[i - 1], totx[i - 1]) : 0.f;
     }
     wA2[t] = pack2(wa[0], wa[1]);
     wB2[t] = pack2(wb[0], wb[1]);
   }
-  const int word0 = min(e >> 1, (int)(row_bytes >> 2));     // beyond the row: the zeroed pad
+  const int word0 = min((int)((e * (int)sizeof(T)) >> 2), (int)(row_bytes >> 2));     // beyond the row: the zeroed pad
   const bool writer = have && lane < 31 && i < p.out_w;     // lane 31 only supplies B to lane 30
   T* __restrict__ dst = out + plane * (int64_t)p.out_h * p.out_w + i;
 
@@ -186,8 +225,8 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
     const uint32_t* __restrict__ rowp = reinterpret_cast<const uint32_t*>(stage_ptr);
     unsigned long long accA = 0ull, accB = 0ull;             // (a0, a1), (b0, b1) as fp32 pairs
 #pragma unroll
-    for (int t = 0; t < LW; ++t) {
-      const float2 v = Pair<T>::cvt(rowp[t]);
+    for (int t = 0; t < NP; ++t) {
+      const float2 v = Px<T>::pair(rowp, t);
       const unsigned long long v2 = pack2(v.x, v.y);
       accA = fma2(wA2[t], v2, accA);
       accB = fma2(wB2[t], v2, accB);
@@ -200,7 +239,7 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
     const float h = A + __shfl_down_sync(0xffffffffu, B, 1);
     const int k = rowK[rl];
     if (k != k_cur) {                              // CTA-uniform: output row k_cur - 1 is complete
-      if (writer && k_cur - 1 >= oy0) dst[(int64_t)(k_cur - 1) * p.out_w] = from_acc<T, float>(acc_lo);
+      if (writer && k_cur - 1 >= oy0) dst[(int64_t)(k_cur - 1) * p.out_w] = store_px<T>(acc_lo);
       acc_lo = acc_hi; acc_hi = 0.f; k_cur = k;
     }
     acc_hi = fmaf(rowA[rl], h, acc_hi);
@@ -208,12 +247,13 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   }
   // rows of the band are exhausted: acc_lo holds output row k_cur - 1; a band that ended exactly on an
   // interval boundary (k_cur == oy1 - 1 cannot happen: the band includes interval oy1) -> k_cur == oy1
-  if (writer && k_cur - 1 >= oy0 && k_cur - 1 < oy1) dst[(int64_t)(k_cur - 1) * p.out_w] = from_acc<T, float>(acc_lo);
-  if (writer && k_cur < oy1 && k_cur >= oy0) dst[(int64_t)k_cur * p.out_w] = from_acc<T, float>(acc_hi);
+  if (writer && k_cur - 1 >= oy0 && k_cur - 1 < oy1) dst[(int64_t)(k_cur - 1) * p.out_w] = store_px<T>(acc_lo);
+  if (writer && k_cur < oy1 && k_cur >= oy0) dst[(int64_t)k_cur * p.out_w] = store_px<T>(acc_hi);
 }
 
-template <typename T, int LW, int NW>
+template <typename T, int NP, int NW>
 int launch_stream(const void* in, void* out, int64_t planes, const StreamParams& p0, cudaStream_t st) {
+  constexpr int LW = (NP * 2 * (int)sizeof(T) + 3) / 4;       // 32-bit words a thread reads per row
   StreamParams p = p0;
   const int n_cwarps = ceil_div(p.out_w + 1, 31);
   const uint32_t row_bytes = (uint32_t)p.in_w * sizeof(T);
@@ -233,8 +273,8 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
     band_rows = (int)((p.rows_out_per_cta + 2) * p.scale_h) + 4;
   }
   p.band_cap = (band_rows + 31) & ~31;
-  const size_t fixed = (size_t)(p.out_w + p.out_h) * 12 + (size_t)p.band_cap * 12 + 256;
-  const int ctas_per_sm = (NW <= 8 && LW <= 10) ? 3 : 2;
+  const size_t fixed = (size_t)(p.out_w + p.out_h) * 16 + (size_t)p.band_cap * 12 + 256;
+  const int ctas_per_sm = (NW <= 8 && NP <= 12) ? 3 : 2;
   const size_t budget = ((size_t)max_smem_optin() - 3072) / ctas_per_sm - 1024;   // smem per CTA (1 KB reserved each)
   if (budget < fixed + 3 * (size_t)p.row_pitch) return 0;
   int stages = (int)((budget - fixed) / p.row_pitch);
@@ -242,12 +282,12 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
   if (stages < 3) return 0;
   p.n_stages = stages;
   const size_t smem = (size_t)stages * p.row_pitch + (size_t)stages * 16 + fixed;
-  VB200_CUDA_TRY(cudaFuncSetAttribute(resize_aa_stream_kernel<T, LW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VB200_CUDA_TRY(cudaFuncSetAttribute(resize_aa_stream_kernel<T, NP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t done = 0;
   while (done < planes) {
     const int64_t chunk = planes - done < 65535 ? planes - done : 65535;
     dim3 grid((unsigned)splits, (unsigned)chunk);
-    resize_aa_stream_kernel<T, LW, NW><<<grid, (n_cwarps + 1) * 32, smem, st>>>(
+    resize_aa_stream_kernel<T, NP, NW><<<grid, (n_cwarps + 1) * 32, smem, st>>>(
         (const T*)in + done * (int64_t)p.in_h * p.in_w, (T*)out + done * (int64_t)p.out_h * p.out_w, p, n_cwarps);
     int rc = check_launch("resize_aa_stream_kernel");
     if (rc) return rc;
@@ -258,13 +298,15 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
 
 template <typename T>
 int dispatch_lw(const void* in, void* out, int64_t planes, const StreamParams& p, cudaStream_t st) {
-  // a thread owns at most floor(scale)+1 pixels, +1 slot for word alignment
-  const int need = ((int)floorf(p.scale_w) + 1 + 1 + 1) / 2;
+  // a thread owns at most floor(scale)+1 pixels, + the slot alignment slack
+  constexpr int ALIGN = Px<T>::PPW > 2 ? Px<T>::PPW : 2;
+  const int need = ((int)floorf(p.scale_w) + 1 + (ALIGN - 1) + 1) / 2;     // pixel pairs
   const bool small = ceil_div(p.out_w + 1, 31) <= 8;
   if (small) {
     if (need <= 4) return launch_stream<T, 4, 8>(in, out, planes, p, st);
     if (need <= 6) return launch_stream<T, 6, 8>(in, out, planes, p, st);
     if (need <= 10) return launch_stream<T, 10, 8>(in, out, planes, p, st);
+    if (need <= 12) return launch_stream<T, 12, 8>(in, out, planes, p, st);
     if (need <= 16) return launch_stream<T, 16, 8>(in, out, planes, p, st);
     return 0;
   }
@@ -282,16 +324,19 @@ int resize_aa_stream_try(const void* in, void* out, int dtype, int64_t planes, i
   const char* force = getenv("VB200_RESIZE_PATH");            // "generic" disables the fast path
   if (force && force[0] == 'g') return 0;
   if (mode != VB200_RESIZE_BILINEAR) return 0;
-  if (dtype != VB200_F16 && dtype != VB200_BF16) return 0;
+  if (dtype != VB200_F16 && dtype != VB200_BF16 && dtype != VB200_U8 && dtype != VB200_F32) return 0;
+  const size_t esize = dtype == VB200_F32 ? 4 : dtype == VB200_U8 ? 1 : 2;
   if (in_w <= out_w || in_h < out_h) return 0;                 // horizontal downscale, vertical scale >= 1
   if (out_w + 1 > 31 * kMaxConsumerWarps) return 0;
-  if (((size_t)in_w * 2) % 16 != 0 || ((uintptr_t)in % 16) != 0) return 0;
+  if (((size_t)in_w * esize) % 16 != 0 || ((uintptr_t)in % 16) != 0) return 0;
   StreamParams p{};
   p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
   p.scale_w = (float)in_w / (float)out_w;
   p.scale_h = (float)in_h / (float)out_h;
   if (p.scale_w < 2.0f) return 0;
   if (dtype == VB200_F16) return dispatch_lw<__half>(in, out, planes, p, st);
+  if (dtype == VB200_U8) return dispatch_lw<uint8_t>(in, out, planes, p, st);
+  if (dtype == VB200_F32) return dispatch_lw<float>(in, out, planes, p, st);
   return dispatch_lw<__nv_bfloat16>(in, out, planes, p, st);
 }
 
