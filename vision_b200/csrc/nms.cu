@@ -625,7 +625,9 @@ struct NmsWs {
   unsigned long long* mask; void* cub_temp; size_t cub_bytes; size_t total;
 };
 
-NmsWs carve_nms(void* base, int64_t n) {
+// with_mask = false leaves out the n x n/64-bit IoU matrix (1.25 GB at n = 100 000): run_single_segment then takes
+// the sequential chain kernel.
+NmsWs carve_nms(void* base, int64_t n, bool with_mask = true) {
   Carver c(base);
   NmsWs w;
   w.iota = c.take<int>(n);
@@ -636,7 +638,7 @@ NmsWs carve_nms(void* base, int64_t n) {
   w.cub_bytes = cub_temp_bytes(n);
   w.cub_temp = c.take<char>(w.cub_bytes);
   const int64_t cb = ceil_div64(n, 64);
-  w.mask = c.take<unsigned long long>((size_t)n * cb);
+  w.mask = with_mask ? c.take<unsigned long long>((size_t)n * cb) : nullptr;
   w.total = c.off;
   return w;
 }
@@ -671,9 +673,9 @@ int run_single_segment(const Box* boxes_sorted, int64_t n, IouParams prm, uint8_
 
 template <typename S>
 int nms_core(const typename BoxOf<S>::type* boxes, const S* scores, int64_t n, IouParams prm, void* workspace,
-             size_t workspace_bytes, int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st) {
+             size_t workspace_bytes, int64_t* keep_out, int64_t* num_keep_out, cudaStream_t st, bool with_mask = true) {
   using Box = typename BoxOf<S>::type;
-  NmsWs w = carve_nms(workspace, n);
+  NmsWs w = carve_nms(workspace, n, with_mask);
   if (workspace_bytes < w.total) { set_error("nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
   const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
   iota_kernel<<<grd, blk, 0, st>>>(w.iota, ni);
@@ -733,6 +735,9 @@ struct BnmsWs {
   uint8_t* keep_by_rank; void* max_coord; void* shifted; void* cub_temp; size_t cub_bytes;
   unsigned long long* mask; size_t nms_off; size_t total;
 };
+// The reference picks the coordinate trick only for numel <= 100 000 (boxes.py:86); a caller that forces it on a larger
+// problem gets the sequential kernel instead of a gigabyte-sized bit matrix in every batched_nms workspace.
+inline bool bnms_trick_with_mask(int64_t n) { return 4 * n <= 100000; }
 BnmsWs carve_bnms(void* base, int64_t n) {
   Carver c(base);
   BnmsWs w;
@@ -754,7 +759,7 @@ BnmsWs carve_bnms(void* base, int64_t n) {
   w.cub_temp = c.take<char>(w.cub_bytes);
   w.mask = c.take<unsigned long long>((size_t)n * kBnmsWpr);
   w.nms_off = c.off;                       // trick strategy reuses the plain-nms pipeline
-  c.off += carve_nms(nullptr, n).total;
+  c.off += carve_nms(nullptr, n, bnms_trick_with_mask(n)).total;
   w.total = c.off;
   return w;
 }
@@ -788,7 +793,7 @@ int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_
     int rc = check_launch("shift_boxes_kernel");
     if (rc) return rc;
     return nms_core<S>((const Box*)w.shifted, (const S*)scores, n, prm, (char*)workspace + w.nms_off,
-                       workspace_bytes - w.nms_off, keep_out, num_keep_out, st);
+                       workspace_bytes - w.nms_off, keep_out, num_keep_out, st, bnms_trick_with_mask(n));
   }
 
   // ---- vanilla semantics, fused ------------------------------------------
