@@ -95,27 +95,39 @@ class ClockSampler:
 
 
 def cpu_reference_fn():
-    """The reference's own CPU implementation of the path, if the wheel is importable; else the oracle port."""
+    """The reference's own CPU implementation of the path, if the wheel is importable; else the oracle port.
+    Returns (fn, kind, description, threads).  The reference kernel is a single-threaded loop over RoIs
+    (csrc/ops/cpu/roi_align_kernel.cpp:33-35), so "all the host threads it can use" is one thread per call; to
+    give it the whole machine the RoIs are split into one chunk per core and the UNMODIFIED op is called on the
+    chunks from a thread pool (the op releases the GIL; outputs are concatenated in RoI order)."""
     import torch
+    from concurrent.futures import ThreadPoolExecutor
     from vision_b200 import workloads
 
     x, rois, kw = workloads.cfg2_roi_align()
+    threads = max(1, min(os.cpu_count() or 1, 64, rois.shape[0]))
+    chunks = [c for c in torch.chunk(rois, threads, dim=0) if c.shape[0]]
+    pool = ThreadPoolExecutor(max_workers=len(chunks))
     try:
         import torchvision
 
         def fn():
-            return torchvision.ops.roi_align(x, rois, **kw)
+            return torch.cat(list(pool.map(lambda r: torchvision.ops.roi_align(x, r, **kw), chunks)), dim=0)
 
-        return fn, "reference", f"torchvision {torchvision.__version__} CPU kernel (csrc/ops/cpu/roi_align_kernel.cpp, single-threaded loop)"
+        return fn, "reference", (f"torchvision {torchvision.__version__} CPU kernel (csrc/ops/cpu/roi_align_kernel.cpp, a "
+                                 f"single-threaded loop) called on {len(chunks)} RoI chunks from {len(chunks)} threads"), len(chunks)
     except Exception:
+        import numpy as np
         import oracle
 
-        xn, rn = x.numpy(), rois.numpy()
+        xn = x.numpy()
+        rn = [c.numpy() for c in chunks]
 
         def fn():
-            return oracle.roi_align(xn, rn, kw["output_size"], kw["spatial_scale"], kw["sampling_ratio"], kw["aligned"])
+            return np.concatenate(list(pool.map(lambda r: oracle.roi_align(xn, r, kw["output_size"], kw["spatial_scale"],
+                                                                         kw["sampling_ratio"], kw["aligned"]), rn)), axis=0)
 
-        return fn, "port", "oracle/vision_oracle.c restatement (single-threaded C)"
+        return fn, "port", f"oracle/vision_oracle.c restatement (single-threaded C) on {len(chunks)} RoI chunks / threads", len(chunks)
 
 
 def time_cpu(fn, calls: int) -> float:
@@ -131,8 +143,8 @@ def run_reference(args, rank: int):
         return
     import torch
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    fn, kind, desc = cpu_reference_fn()
+    torch.set_num_threads(1)          # the pool supplies the parallelism; no intra-op threads under it
+    fn, kind, desc, threads = cpu_reference_fn()
     for _ in range(min(args.warmup, 2)):
         fn()
     t0 = time.perf_counter()
@@ -146,7 +158,7 @@ def run_reference(args, rank: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "n/a (CPU)", "parallelism": "host cores"},
-        "cpu_baseline": {"value": val, "unit": "RoIs/s", "cores": 1, "host_cores": os.cpu_count(), "kind": kind,
+        "cpu_baseline": {"value": val, "unit": "RoIs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": kind,
                          "sample": f"{args.steps} full-size calls of the workload; {desc}"},
         "e2e": {"value": val, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -348,10 +360,10 @@ def main():
         # CPU baseline: bounded sample on this box's host cores (rank 0, N=1 only)
         cpu = None
         if world == 1:
-            torch.set_num_threads(os.cpu_count() or 1)
-            fn, kind, desc = cpu_reference_fn()
+            torch.set_num_threads(1)      # the pool supplies the parallelism
+            fn, kind, desc, threads = cpu_reference_fn()
             sec = time_cpu(fn, args.cpu_calls)
-            cpu = {"value": K_ROIS / sec, "unit": "RoIs/s", "cores": 1, "host_cores": os.cpu_count(), "kind": kind,
+            cpu = {"value": K_ROIS / sec, "unit": "RoIs/s", "cores": threads, "host_cores": os.cpu_count(), "kind": kind,
                    "sample": f"{args.cpu_calls} full-size calls ({sec * 1e3:.0f} ms each); {desc}"}
         line = {
             "metric": "roi_align RoIs/s", "value": world * K_ROIS / (ms_per_step / 1e3), "unit": "RoIs/s", "n_gpus": world,
