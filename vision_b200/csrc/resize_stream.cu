@@ -178,6 +178,7 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
       uint32_t ph = 0;
       for (int rl = 0; rl < nrows; ++rl) {
         mbar_wait(&empty[s], ph ^ 1u);
+        fence_proxy_async();      // consumers' generic-proxy reads of this stage (released by their arrive) before the async-proxy rewrite
         mbar_expect_tx(&full[s], row_bytes);
         bulk_g2s(stages + (size_t)s * p.row_pitch, src + (int64_t)rl * p.in_w, row_bytes, &full[s]);
         if (++s == p.n_stages) { s = 0; ph ^= 1u; }
