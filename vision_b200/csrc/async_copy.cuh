@@ -25,6 +25,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait with a suspend-time hint (ns): the thread may sleep in hardware instead of re-issuing the poll, which
+// keeps issue slots free for the warps that have work (consumers of a ring that is refilled from HBM).
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITH_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONEH_%=;\n\t"
+      "bra WAITH_%=;\n\t"
+      "DONEH_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
 // global -> shared, bytes % 16 == 0, both addresses 16 B aligned; completes on `bar` (complete_tx).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -221,8 +221,9 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   int s = 0;
   uint32_t ph = 0;
   const unsigned char* stage_ptr = stages + (size_t)word0 * 4;
+  const int n_stages = p.n_stages, row_pitch = p.row_pitch;      // registers, not a constant-bank load per row
   for (int rl = 0; rl < nrows; ++rl) {
-    mbar_wait(&full[s], ph);
+    mbar_wait_hint(&full[s], ph, 2000u);
     const uint32_t* __restrict__ rowp = reinterpret_cast<const uint32_t*>(stage_ptr);
     unsigned long long accA = 0ull, accB = 0ull;             // (a0, a1), (b0, b1) as fp32 pairs
 #pragma unroll
@@ -235,7 +236,7 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
     const float a0 = lo32(accA), a1 = hi32(accA), b0 = lo32(accB), b1 = hi32(accB);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
-    if (++s == p.n_stages) { s = 0; ph ^= 1u; stage_ptr = stages + (size_t)word0 * 4; } else stage_ptr += p.row_pitch;
+    if (++s == n_stages) { s = 0; ph ^= 1u; stage_ptr = stages + (size_t)word0 * 4; } else stage_ptr += row_pitch;
     const float A = a0 + a1, B = b0 + b1;
     const float h = A + __shfl_down_sync(0xffffffffu, B, 1);
     const int k = rowK[rl];
