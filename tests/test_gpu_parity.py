@@ -694,3 +694,57 @@ def test_c_abi_direct_ctypes_call(vb, oracle):
     assert np.array_equal(npy(out), wo) and np.array_equal(npy(arg), wa)
     rc = lib.vb200_roi_pool_forward(None, None, None, None, 0, 1, 8, 200, 272, 64, 0, 7, ctypes.c_double(0.25), None)
     assert rc == -1 and b"pooled size" in lib.vb200_last_error()
+
+
+def test_detection_callers_are_drop_in(vb):
+    """The real callers of the path: RegionProposalNetwork.filter_proposals (batched_nms over FPN
+    levels, rpn.py:242-298), MultiScaleRoIAlign (roi_align per level, poolers.py:147-228) and
+    RoIHeads.postprocess_detections (batched_nms over classes, roi_heads.py:680-737), run with the reference kernels
+    and again after vision_b200.install(): NMS-driven outputs must be IDENTICAL (bit-exact kept indices), pooled
+    features within the roi_align tolerance."""
+    tv = pytest.importorskip("torchvision")
+    from collections import OrderedDict
+    from torchvision.models.detection.anchor_utils import AnchorGenerator
+    from torchvision.models.detection.image_list import ImageList
+    from torchvision.models.detection.roi_heads import RoIHeads
+    from torchvision.models.detection.rpn import RegionProposalNetwork, RPNHead
+
+    torch.manual_seed(0)
+    sizes = [(100, 136), (50, 68), (25, 34), (13, 17)]
+    feats = OrderedDict((str(i), torch.randn(2, 64, h, w, device=DEV)) for i, (h, w) in enumerate(sizes))
+    images = ImageList(torch.zeros(2, 3, 400, 544, device=DEV), [(400, 544), (380, 520)])
+    anchors = AnchorGenerator(((32,), (64,), (128,), (256,)), ((0.5, 1.0, 2.0),) * 4)
+    rpn = RegionProposalNetwork(anchors, RPNHead(64, 3), 0.7, 0.3, 256, 0.5, dict(training=2000, testing=1000),
+                                dict(training=2000, testing=300), 0.7).to(DEV).eval()
+    pool = tv.ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    heads = RoIHeads(pool, None, None, 0.5, 0.5, 512, 0.25, None, 0.01, 0.5, 100)
+    logits = torch.randn(600, 21, device=DEV) * 3
+    reg = torch.randn(600, 21 * 4, device=DEV) * 0.5
+
+    def run():
+        with torch.no_grad():
+            props, _ = rpn(images, feats)
+            pooled = pool(feats, props, images.image_sizes)
+            dets = heads.postprocess_detections(logits, reg, [p[:300] for p in props], images.image_sizes)
+        return props, pooled, dets
+
+    assert not vb.installed()
+    ref_props, ref_pooled, ref_dets = run()
+    vb.install()
+    try:
+        before = vb.launch_count()
+        props, pooled, dets = run()
+        assert vb.launch_count() > before            # our kernels ran, not the wheel's
+    finally:
+        vb.uninstall()
+    for a, b in zip(props, ref_props):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert pooled.shape == ref_pooled.shape
+    # the reference CUDA roi_align is itself up to 7e-5 away from its CPU kernel (see _check_roi_align_vs_both_references)
+    cpu_pooled = pool(OrderedDict((k, v.cpu()) for k, v in feats.items()), [p.cpu() for p in ref_props], images.image_sizes)
+    torch.testing.assert_close(pooled.cpu(), cpu_pooled, rtol=1e-5, atol=1e-5)
+    assert (pooled - ref_pooled).abs().max().item() <= (ref_pooled.cpu() - cpu_pooled).abs().max().item() + 2e-5
+    for ours, ref in zip(dets, ref_dets):            # (boxes, scores, labels), each a per-image list
+        assert len(ours) == len(ref) == 2
+        for a, b in zip(ours, ref):
+            assert a.shape == b.shape and torch.equal(a, b)
