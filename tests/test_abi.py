@@ -43,6 +43,21 @@ def test_workspace_queries_need_no_gpu():
     assert lib.vb200_batched_nms_workspace_bytes(ctypes.c_int64(100000)) > 100000 * 60
 
 
+def test_batched_nms_workspace_stays_small():
+    """A 100k-box batched_nms takes the fused per-class path; its workspace must not carry the n x n/64-bit matrix of
+    the plain-nms pipeline (1.25 GB at this size), only the 33-words-per-row class mask (26 MB) and the sort buffers."""
+    from vision_b200 import _lib
+    import ctypes
+
+    lib = _lib.core()
+    lib.vb200_batched_nms_workspace_bytes.restype = ctypes.c_size_t
+    lib.vb200_nms_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.vb200_batched_nms_workspace_bytes(ctypes.c_int64(100_000)) < 64 << 20
+    # inside the reference's coordinate-trick range the plain-nms matrix is part of it (and small)
+    assert lib.vb200_batched_nms_workspace_bytes(ctypes.c_int64(25_000)) < 128 << 20
+    assert lib.vb200_nms_workspace_bytes(ctypes.c_int64(1000)) < 1 << 20
+
+
 def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     from vision_b200 import _lib
 
