@@ -13,10 +13,13 @@
 //     reference's exact (uncontracted, round-to-nearest) coordinate arithmetic;
 //   * generic kernel: CTA = (RoI, channel chunk), geometry table in shared
 //     memory, threads stride over (channel, bin) so output stores are coalesced;
-//   * plane-resident kernel (fp32, fixed sampling_ratio, plane <= ~220 KB):
-//     persistent CTAs hold one whole H*W channel plane in shared memory (bulk
-//     async copy + mbarrier), every gather is an LDS, each input byte leaves
-//     HBM once and each output byte is written once.
+//   * plane-resident kernels (fp32, fixed sampling_ratio, plane <= ~220 KB):
+//     persistent CTAs hold one whole H*W channel plane in shared memory, every
+//     gather is an LDS, each input byte leaves HBM once and each output byte is
+//     written once.  Two lane mappings: thread-per-bin (any pooled size,
+//     sampling_ratio 1..4; bank-conflict bound) and line-wise (7x7 bins,
+//     sampling_ratio 2: a warp owns one RoI, its lanes are the taps of one line
+//     of the sampling grid, so an LDS reads one image row or column).
 #include "async_copy.cuh"
 #include "common.cuh"
 
