@@ -20,6 +20,11 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_extra():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_cpu_extra.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     import oracle as O   # test infrastructure only
 

@@ -748,3 +748,35 @@ def test_detection_callers_are_drop_in(vb):
         assert len(ours) == len(ref) == 2
         for a, b in zip(ours, ref):
             assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_extra_goldens_from_the_reference(vb, golden_extra):
+    """tests/golden/reference_cpu_extra.npz: outputs of the reference itself for the shapes that reach the line-wise
+    roi_align kernel, the float64 NMS path and the uint8 / fp32 streaming resize."""
+    g = golden_extra
+    x, r = t(g["line_x"]), t(g["line_rois"])
+    for al in (0, 1):
+        for path in ("line", "plane", "generic"):
+            with force_env("VB200_ROI_ALIGN_PATH", path):
+                got = vb.ops.roi_align(x, r, 7, 0.25, 2, bool(al))
+            np.testing.assert_allclose(npy(got), g[f"line_out_a{al}"], **F32_TOL)
+    b, s, i = t(g["nms64_boxes"]), t(g["nms64_scores"]), t(g["nms64_idxs"])
+    assert b.dtype == torch.float64
+    _set(vb, "cpu")                                  # the fixtures come from the CPU kernel's arithmetic
+    try:
+        for k, thr in enumerate(g["nms64_thr"]):
+            assert np.array_equal(npy(vb.ops.nms(b, s, float(thr))), g[f"nms64_keep{k}"])
+        assert np.array_equal(npy(vb.ops.batched_nms(b, s, i, 0.5)), g["bnms64_keep_t"])    # numel 2800: coordinate trick
+    finally:
+        _set(vb, "cuda")
+    img = t(g["rs8_img"])
+    for size in ((9, 20), (31, 200)):
+        want, want_f = g[f"rs8_out_{size[0]}x{size[1]}"], g[f"rs8_float_{size[0]}x{size[1]}"]
+        ties = np.abs(want_f - np.floor(want_f) - 0.5) < 1e-3
+        for path in ("stream", "generic"):           # anything but "generic" leaves the streaming kernel on
+            with force_env("VB200_RESIZE_PATH", path):
+                got = npy(vb.transforms.resize_image(img, list(size), antialias=True))
+            assert got.dtype == np.uint8 and np.array_equal(got[~ties], want[~ties])
+            assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
+    got = vb.transforms.resize_image(t(g["rsf_img"]), [20, 60], antialias=True)
+    np.testing.assert_allclose(npy(got), g["rsf_out_20x60"], rtol=1e-5, atol=1e-5)

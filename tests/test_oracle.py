@@ -148,3 +148,27 @@ def test_resize_live_fp16_route(oracle):
     ref = F.interpolate(x.float(), size=[28, 28], mode="bilinear", align_corners=False, antialias=True).half()
     got = torch.from_numpy(oracle.resize(x.float().numpy(), (28, 28), 0, True)).half()
     assert (ref.float() - got.float()).abs().max().item() <= 1e-3
+
+
+def test_extra_goldens_line_roi_align_fp64_nms_integer_resize(oracle, golden_extra):
+    """tests/golden/reference_cpu_extra.npz (gen_golden_extra.py): the detection-head roi_align shape, float64 nms /
+    batched_nms, and resize of uint8 / fp32 images routed as _geometry.py:340-360 routes CUDA tensors."""
+    g = golden_extra
+    for al in (0, 1):
+        got = oracle.roi_align(g["line_x"], g["line_rois"], (7, 7), 0.25, 2, bool(al))
+        assert np.array_equal(got, g[f"line_out_a{al}"])
+    b, s, i = g["nms64_boxes"], g["nms64_scores"], g["nms64_idxs"]
+    assert b.dtype == np.float64
+    for k, thr in enumerate(g["nms64_thr"]):
+        assert np.array_equal(oracle.nms(b, s, float(thr)), g[f"nms64_keep{k}"])
+    assert np.array_equal(oracle.batched_nms(b, s, i, 0.5, strategy=1), g["bnms64_keep_v"])
+    assert np.array_equal(oracle.batched_nms(b, s, i, 0.5, strategy=2), g["bnms64_keep_t"])
+    for size in ((9, 20), (31, 200)):
+        f = oracle.resize(g["rs8_img"].astype(np.float32), size, oracle.RESIZE_BILINEAR, True)
+        want_f = g[f"rs8_float_{size[0]}x{size[1]}"]
+        np.testing.assert_allclose(f, want_f, rtol=0, atol=2e-4)        # 0..255 scale
+        out = np.rint(f).astype(np.uint8)                                 # round half to even, like Tensor.round_
+        ties = np.abs(want_f - np.floor(want_f) - 0.5) < 1e-3
+        assert np.array_equal(out[~ties], g[f"rs8_out_{size[0]}x{size[1]}"][~ties])
+    np.testing.assert_allclose(oracle.resize(g["rsf_img"], (20, 60), oracle.RESIZE_BILINEAR, True), g["rsf_out_20x60"],
+                               rtol=1e-6, atol=1e-6)
