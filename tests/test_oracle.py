@@ -172,3 +172,81 @@ def test_extra_goldens_line_roi_align_fp64_nms_integer_resize(oracle, golden_ext
         assert np.array_equal(out[~ties], g[f"rs8_out_{size[0]}x{size[1]}"][~ties])
     np.testing.assert_allclose(oracle.resize(g["rsf_img"], (20, 60), oracle.RESIZE_BILINEAR, True), g["rsf_out_20x60"],
                                rtol=1e-6, atol=1e-6)
+
+
+# ---- randomised live comparisons against the reference's CPU kernels (importable in the build container) ----
+@pytest.mark.parametrize("seed", range(6))
+def test_roi_ops_random_shapes_live(oracle, seed):
+    """roi_align / roi_pool / ps_roi_align on random shapes, scales, pooled sizes and sampling ratios, RoIs partly
+    outside the map: the oracle must reproduce the reference CPU kernels bit for bit (same arithmetic, same order)."""
+    import torch
+
+    g = torch.Generator().manual_seed(100 + seed)
+    n_img, c = int(torch.randint(1, 4, (1,), generator=g)), int(torch.randint(1, 7, (1,), generator=g))
+    h, w = int(torch.randint(5, 40, (1,), generator=g)), int(torch.randint(5, 40, (1,), generator=g))
+    ph, pw = int(torch.randint(1, 8, (1,), generator=g)), int(torch.randint(1, 8, (1,), generator=g))
+    scale = [1.0, 0.5, 0.25, 0.0625][seed % 4]
+    sr = [-1, 1, 2, 3][(seed // 2) % 4]
+    k = 17
+    x = torch.randn(n_img, c, h, w, generator=g)
+    r = torch.zeros(k, 5)
+    r[:, 0] = torch.randint(0, n_img, (k,), generator=g).float()
+    r[:, 1] = (torch.rand(k, generator=g) * 1.4 - 0.2) * w / scale
+    r[:, 2] = (torch.rand(k, generator=g) * 1.4 - 0.2) * h / scale
+    r[:, 3] = r[:, 1] + torch.rand(k, generator=g) * w / scale
+    r[:, 4] = r[:, 2] + torch.rand(k, generator=g) * h / scale
+    for aligned in (False, True):
+        want = tv.ops.roi_align(x, r, (ph, pw), scale, sr, aligned).numpy()
+        assert np.array_equal(oracle.roi_align(x.numpy(), r.numpy(), (ph, pw), scale, sr, aligned), want)
+    po, pa = torch.ops.torchvision.roi_pool(x, r, scale, ph, pw)
+    o, a = oracle.roi_pool(x.numpy(), r.numpy(), (ph, pw), scale)
+    assert np.array_equal(o, po.numpy()) and np.array_equal(a, pa.numpy())
+    xp = torch.randn(n_img, c * ph * pw, h, w, generator=g)
+    o_ref, m_ref = torch.ops.torchvision.ps_roi_align(xp, r, scale, ph, pw, sr)
+    o, m = oracle.ps_roi_align(xp.numpy(), r.numpy(), (ph, pw), scale, sr)
+    assert np.array_equal(m, m_ref.numpy())
+    np.testing.assert_array_equal(np.nan_to_num(o, nan=7.0, posinf=8.0, neginf=9.0),
+                                  np.nan_to_num(o_ref.numpy(), nan=7.0, posinf=8.0, neginf=9.0))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_deform_conv2d_random_geometry_live(oracle, seed):
+    import torch
+
+    g = torch.Generator().manual_seed(200 + seed)
+    groups, ogrps = [(1, 1), (2, 1), (1, 2), (2, 3)][seed]
+    cin, cout = 6 * groups // groups * groups, 2 * groups
+    cin = 6 if groups == 1 else 6
+    cin = cin - cin % (groups * ogrps) + (groups * ogrps if cin % (groups * ogrps) else 0)
+    kh, kw = [(3, 3), (1, 1), (3, 2), (2, 3)][seed]
+    sh, sw = [(1, 1), (2, 2), (2, 1), (1, 2)][seed]
+    ph, pw = [(1, 1), (0, 0), (1, 0), (2, 1)][seed]
+    dh, dw = [(1, 1), (1, 1), (2, 1), (1, 2)][seed]
+    b, ih, iw = 2, 9, 8
+    oh = (ih + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    ow = (iw + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    x = torch.randn(b, cin, ih, iw, generator=g)
+    off = torch.randn(b, ogrps * 2 * kh * kw, oh, ow, generator=g) * 1.5
+    msk = torch.rand(b, ogrps * kh * kw, oh, ow, generator=g)
+    wt = torch.randn(cout, cin // groups, kh, kw, generator=g)
+    bias = torch.randn(cout, generator=g)
+    for m in (msk, None):
+        want = tv.ops.deform_conv2d(x, off, wt, bias, (sh, sw), (ph, pw), (dh, dw), m).numpy()
+        got = oracle.deform_conv2d(x.numpy(), off.numpy(), wt.numpy(), bias.numpy(), (sh, sw), (ph, pw), (dh, dw),
+                                   None if m is None else m.numpy())
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)     # the reference sums through a BLAS GEMM
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_resize_random_sizes_live(oracle, seed):
+    import torch
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(300 + seed)
+    h, w = int(torch.randint(3, 90, (1,), generator=g)), int(torch.randint(3, 90, (1,), generator=g))
+    oh, ow = int(torch.randint(1, 120, (1,), generator=g)), int(torch.randint(1, 120, (1,), generator=g))
+    x = torch.rand(2, 2, h, w, generator=g)
+    for mode, code in (("bilinear", oracle.RESIZE_BILINEAR), ("bicubic", oracle.RESIZE_BICUBIC)):
+        for aa in (False, True):
+            want = F.interpolate(x, size=[oh, ow], mode=mode, align_corners=False, antialias=aa).numpy()
+            np.testing.assert_allclose(oracle.resize(x.numpy(), (oh, ow), code, aa), want, rtol=0, atol=5e-6)   # ATen vectorises the sums
