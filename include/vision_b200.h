@@ -114,7 +114,9 @@ VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, vo
  * Writes the kept ORIGINAL indices, in descending-score order (stable), to
  * keep_out[0..*num_keep_out) — both device memory, keep_out sized n.  The
  * caller reads *num_keep_out (the reference's masked_select sync).
- * dtype: F32 or F64, as the reference dispatches (F16 inputs are widened by the caller). */
+ * dtype: F32 or F64, as the reference dispatches (F16 inputs are widened by the caller).
+ * workspace: sort buffers + the n x ceil(n/64) 64-bit IoU matrix (about n*n/8 bytes: 1.2 MB at
+ * n = 3 000, 50 MB at 20 000, 1.25 GB at 100 000 - the reference allocates the same matrix). */
 VB200_API size_t vb200_nms_workspace_bytes(int64_t n);
 VB200_API int vb200_nms(const void* boxes, const void* scores, int dtype, int64_t n, double iou_threshold,
               int semantics, void* workspace, size_t workspace_bytes, int64_t* keep_out,
@@ -123,7 +125,10 @@ VB200_API int vb200_nms(const void* boxes, const void* scores, int dtype, int64_
 /* ---- batched_nms -------------------------------------------------------
  * Replaces the Python torchvision.ops.boxes.batched_nms (boxes.py:57-126):
  * one fused device pipeline instead of a per-class Python loop.  idxs [n] int64.
- * Output as vb200_nms (or *num_keep_out = -1, see VB200_BNMS_WIDE_KEYS).  strategy: VB200_BNMS_*. */
+ * Output as vb200_nms (or *num_keep_out = -1, see VB200_BNMS_WIDE_KEYS).  strategy: VB200_BNMS_*.
+ * workspace: sort buffers + 33 mask words per box (42 MB at n = 100 000); the plain-nms matrix is
+ * included only up to the reference's coordinate-trick range (4 n <= 100 000) - VB200_BNMS_TRICK
+ * forced on a larger problem runs the sequential per-segment kernel instead. */
 VB200_API size_t vb200_batched_nms_workspace_bytes(int64_t n);
 VB200_API int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
                       int64_t n, double iou_threshold, int semantics, int strategy,
