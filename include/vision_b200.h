@@ -71,6 +71,9 @@ VB200_API const char* vb200_last_error(void);
 /* Number of kernel launches issued by this library in this process (all
  * threads); bench.py reports the delta over the timed region. */
 VB200_API uint64_t vb200_launch_count(void);
+/* The VB200_* path overrides (testing / profiling only) are read from the environment once, the first
+ * time a launcher needs them; this re-reads them (tests switch paths inside one process). */
+VB200_API void vb200_reload_env(void);
 
 /* ---- roi_align ---------------------------------------------------------
  * Replaces roi_align_forward_kernel, csrc/ops/cuda/roi_align_kernel.cu:334-394
@@ -114,7 +117,8 @@ VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, vo
  * Writes the kept ORIGINAL indices, in descending-score order (stable), to
  * keep_out[0..*num_keep_out) — both device memory, keep_out sized n.  The
  * caller reads *num_keep_out (the reference's masked_select sync).
- * dtype: F32 or F64, as the reference dispatches (F16 inputs are widened by the caller).
+ * dtype: F32, F64 or F16 - the three instantiations of the reference kernel, each with the arithmetic of its compiled
+ * reference (F16: devIoU<Half> mixes half and float roundings, nms_kernel.cu:42-54; VB200_NMS_CUDA only).
  * workspace: sort buffers + the n x ceil(n/64) 64-bit IoU matrix (about n*n/8 bytes: 1.2 MB at
  * n = 3 000, 50 MB at 20 000, 1.25 GB at 100 000 - the reference allocates the same matrix). */
 VB200_API size_t vb200_nms_workspace_bytes(int64_t n);

@@ -48,6 +48,7 @@ def _p(a):
 
 NMS_MODE_CPU = 0   # arithmetic of csrc/ops/cpu/nms_kernel.cpp
 NMS_MODE_CUDA = 1  # arithmetic of the compiled csrc/ops/cuda/nms_kernel.cu (FMA-contracted Sa+Sb, float thr)
+NMS_MODE_CUDA_HALF = 2  # the compiled devIoU<Half>: pass fp16 values (any float container); pinned on the GPU box only
 
 
 def _is_f64(a) -> bool:

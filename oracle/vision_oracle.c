@@ -67,9 +67,20 @@ ORC_API void orc_argsort_desc_stable_f32(const float* key, int64_t n, int64_t* o
 /*                  (SASS of the installed sm_100 cubin):   */
 /*                  Sa = fmul(a2-a0, a3-a1); t = fma(b2-b0, b3-b1, Sa);      */
 /*                  den = t - inter; compare ovr > (float)iou_threshold.    */
+/* mode 2 ("cuda half"): what nvcc makes of devIoU<Half> (SASS of the same   */
+/*                  cubin): inputs are fp16 values (passed widened to       */
+/*                  float); left/right/top/bottom chosen on them; the two   */
+/*                  extents and the HEIGHT factor of every area are rounded */
+/*                  to half, the WIDTH factor stays fp32; products in fp32; */
+/*                  Sa+Sb contracted as in mode 1; float threshold.  The    */
+/*                  reference has no CPU Half kernel, so this mode is       */
+/*                  pinned on the GPU box only, against the wheel's CUDA    */
+/*                  kernel (tests/test_gpu_parity.py).                      */
 /* Returns the number kept; keep[] holds original indices in descending-    */
 /* score order (stable).                                                    */
 /* ------------------------------------------------------------------------ */
+static inline float half_rn_(float v) { return (float)(_Float16)v; }   /* F2FP.F16.F32 + HADD2.F32: round to nearest even, overflow -> inf */
+
 ORC_API int64_t orc_nms_f32(const float* boxes, const float* scores, int64_t n,
                             double iou_threshold, int mode, int64_t* keep) {
   if (n <= 0) return 0;
@@ -77,8 +88,10 @@ ORC_API int64_t orc_nms_f32(const float* boxes, const float* scores, int64_t n,
   uint8_t* suppressed = (uint8_t*)calloc((size_t)n, 1);
   float* areas = (float*)malloc((size_t)n * sizeof(float));
   orc_argsort_desc_stable_f32(scores, n, order);
-  for (int64_t k = 0; k < n; ++k)
-    areas[k] = (boxes[4 * k + 2] - boxes[4 * k + 0]) * (boxes[4 * k + 3] - boxes[4 * k + 1]);
+  for (int64_t k = 0; k < n; ++k) {
+    float hh = boxes[4 * k + 3] - boxes[4 * k + 1];
+    areas[k] = (boxes[4 * k + 2] - boxes[4 * k + 0]) * (mode == 2 ? half_rn_(hh) : hh);
+  }
   const float thr_f = (float)iou_threshold;
   int64_t num_to_keep = 0;
   for (int64_t _i = 0; _i < n; ++_i) {
@@ -93,11 +106,18 @@ ORC_API int64_t orc_nms_f32(const float* boxes, const float* scores, int64_t n,
       float jx1 = boxes[4 * j], jy1 = boxes[4 * j + 1], jx2 = boxes[4 * j + 2], jy2 = boxes[4 * j + 3];
       float xx1 = fmaxf_(ix1, jx1), yy1 = fmaxf_(iy1, jy1);
       float xx2 = fminf_(ix2, jx2), yy2 = fminf_(iy2, jy2);
-      float w = fmaxf_(0.f, xx2 - xx1), h = fmaxf_(0.f, yy2 - yy1);
+      float w = xx2 - xx1, h = yy2 - yy1;
+      if (mode == 2) { w = half_rn_(w); h = half_rn_(h); }
+      w = (w > 0.f) ? w : 0.f;   /* max(x, 0) with NaN -> 0, as FMNMX / std::max(0, x) give */
+      h = (h > 0.f) ? h : 0.f;
       float inter = w * h;
       if (mode == 0) {
         float ovr = inter / (iarea + areas[j] - inter);
         if ((double)ovr > iou_threshold) suppressed[j] = 1;
+      } else if (mode == 2) {
+        float t = fmaf(jx2 - jx1, half_rn_(jy2 - jy1), iarea);
+        float ovr = inter / (t - inter);
+        if (ovr > thr_f) suppressed[j] = 1;
       } else {
         float t = fmaf(jx2 - jx1, jy2 - jy1, iarea);
         float ovr = inter / (t - inter);
@@ -136,11 +156,17 @@ ORC_API int64_t orc_batched_nms_f32(const float* boxes, const float* scores, con
   if (strategy == 2) {
     float mx = boxes[0];
     for (int64_t i = 1; i < 4 * n; ++i) if (boxes[i] > mx) mx = boxes[i];
+    /* mode 2: every tensor op of boxes.py:103-107 runs on Half tensors: computed in float, rounded to half */
     float step = mx + 1.0f;
+    if (mode == 2) step = half_rn_(step);
     float* shifted = (float*)malloc((size_t)n * 4 * sizeof(float));
     for (int64_t i = 0; i < n; ++i) {
-      float off = (float)idxs[i] * step;
-      for (int c = 0; c < 4; ++c) shifted[4 * i + c] = boxes[4 * i + c] + off;
+      float off = (mode == 2 ? half_rn_((float)idxs[i]) : (float)idxs[i]) * step;
+      if (mode == 2) off = half_rn_(off);
+      for (int c = 0; c < 4; ++c) {
+        float v = boxes[4 * i + c] + off;
+        shifted[4 * i + c] = mode == 2 ? half_rn_(v) : v;
+      }
     }
     int64_t k = orc_nms_f32(shifted, scores, n, iou_threshold, mode, keep);
     free(shifted);

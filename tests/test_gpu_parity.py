@@ -34,14 +34,20 @@ class force_env:
         self.key, self.val = key, val
 
     def __enter__(self):
+        from vision_b200 import _lib
+
         self.old = os.environ.get(self.key)
         os.environ[self.key] = self.val
+        _lib.core().vb200_reload_env()          # the library reads its overrides once, not per call
 
     def __exit__(self, *a):
+        from vision_b200 import _lib
+
         if self.old is None:
             os.environ.pop(self.key, None)
         else:
             os.environ[self.key] = self.old
+        _lib.core().vb200_reload_env()
 
 
 def test_native_library_loaded(vb):

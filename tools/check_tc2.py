@@ -16,9 +16,11 @@ def run(cases):
     for (batch, cin, cout, hw, dt) in cases:
         xi, off, w, bi, m = [t.cuda() for t in workloads.cfg4_deform_conv2d(seed=batch + hw, batch=batch, c_in=cin, c_out=cout, hw=hw, dtype=dt)]
         os.environ["VB200_DCN_CTA2"] = "0"
+        vb._lib.core().vb200_reload_env()
         ref = vb.ops.deform_conv2d(xi, off, w, bi, 1, 1, 1, m)
         torch.cuda.synchronize()
         os.environ["VB200_DCN_CTA2"] = "1"
+        vb._lib.core().vb200_reload_env()
         t0 = time.time()
         got = vb.ops.deform_conv2d(xi, off, w, bi, 1, 1, 1, m)
         torch.cuda.synchronize()

@@ -1,0 +1,105 @@
+"""Round-2 diagnostics (GPU): (1) headroom of the 16-bit deform_conv2d tests at 1e-2, (2) timings of the reference's own
+sm_100 CUDA kernels (the wheel) next to ours on the five BASELINE configs.  Prints plain lines; not a test."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torchvision as tv  # noqa: E402
+import vision_b200 as vb  # noqa: E402
+from vision_b200 import workloads  # noqa: E402
+
+DEV = "cuda"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+
+
+def timed(fn, iters=10, warm=3, l2=True):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if l2:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / iters
+
+
+def ratio(got, want, tol):
+    err = (got.float() - want.float()).abs()
+    return float((err / (tol + tol * want.float().abs())).max()), float(err.max())
+
+
+def dcn_headroom():
+    import oracle
+    torch.manual_seed(0)
+    cin, cout, g, og, sh, sw, ph, pw, dh, dw, kh, kw, ih, iw = 6, 2, 2, 3, 2, 1, 1, 0, 2, 1, 3, 2, 5, 4
+    oh = (ih + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    ow = (iw + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    for dtype in (torch.float16, torch.bfloat16):
+        x = torch.rand(33, cin, ih, iw).to(dtype); off = torch.randn(33, og * 2 * kh * kw, oh, ow).to(dtype)
+        msk = torch.randn(33, og * kh * kw, oh, ow).to(dtype); w = torch.randn(cout, cin // g, kh, kw).to(dtype); bias = torch.randn(cout).to(dtype)
+        got = vb.ops.deform_conv2d(x.to(DEV), off.to(DEV), w.to(DEV), bias.to(DEV), (sh, sw), (ph, pw), (dh, dw), msk.to(DEV))
+        want = torch.from_numpy(oracle.deform_conv2d(x.float().numpy(), off.float().numpy(), w.float().numpy(), bias.float().numpy(),
+                                                    (sh, sw), (ph, pw), (dh, dw), msk.float().numpy()))
+        print("dcn test-geometry", dtype, "ratio@1e-2, maxabs:", ratio(got.cpu(), want, 1e-2), flush=True)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1e-2)):
+        x, off, w, b, _ = workloads.cfg4_deform_conv2d(batch=4, c_in=256, c_out=256, hw=64, dtype=dtype, offset_scale=0.0, use_mask=False)
+        x, off, w, b = x.to(DEV), off.to(DEV), w.to(DEV), b.to(DEV)
+        got = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, None)
+        want = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=1, padding=1)
+        print("dcn zero-offset vs fp64 conv", dtype, f"ratio@{tol}:", ratio(got, want, tol), flush=True)
+
+
+def gpu_reference():
+    assert not vb.installed()
+    # cfg2 roi_align
+    x, rois, kw = workloads.cfg2_roi_align()
+    xd, rd = x.to(DEV), rois.to(DEV)
+    print("cfg2 roi_align ms: ref", timed(lambda: tv.ops.roi_align(xd, rd, **kw), 20), "ours", timed(lambda: vb.ops.roi_align(xd, rd, **kw), 20), flush=True)
+    print("cfg2 roi_pool ms: ref", timed(lambda: tv.ops.roi_pool(xd, rd, 7, 0.25), 20), "ours", timed(lambda: vb.ops.roi_pool(xd, rd, 7, 0.25), 20), flush=True)
+    xp = x[:, :245].contiguous().to(DEV)
+    print("ps_roi_align(245ch,7x7,sr2) ms: ref", timed(lambda: tv.ops.ps_roi_align(xp, rd, 7, 0.25, 2), 20), "ours", timed(lambda: vb.ops.ps_roi_align(xp, rd, 7, 0.25, 2), 20), flush=True)
+    # backward of roi_align through the reference
+    xg = xd.clone().requires_grad_(True)
+    o = tv.ops.roi_align(xg, rd, **kw); go = torch.randn_like(o)
+    print("cfg2 roi_align backward (reference atomics) ms:", timed(lambda: torch.autograd.grad(o, xg, go, retain_graph=True), 10), flush=True)
+    del xg, o, go
+    # cfg3
+    b, s, i = [t.to(DEV) for t in workloads.cfg3_batched_nms()]
+    print("cfg3 batched_nms ms: ref", timed(lambda: tv.ops.batched_nms(b, s, i, 0.5), 5, 2), "ours", timed(lambda: vb.ops.batched_nms(b, s, i, 0.5), 20), flush=True)
+    for n in (1000, 20000, 100000):
+        print(f"nms n={n} ms: ref", timed(lambda: tv.ops.nms(b[:n], s[:n], 0.5), 5, 2), "ours", timed(lambda: vb.ops.nms(b[:n], s[:n], 0.5), 10), flush=True)
+    del b, s, i
+    # cfg4
+    xi, off, w, bi, m = workloads.cfg4_deform_conv2d(device=DEV)
+    t_ours = timed(lambda: vb.ops.deform_conv2d(xi, off, w, bi, 1, 1, 1, m), 10)
+    t16 = timed(lambda: tv.ops.deform_conv2d(xi.half(), off.half(), w.half(), bi.half(), 1, 1, 1, m.half()), 3, 1)
+    xf, of, wf, bf, mf = xi.float(), off.float(), w.float(), bi.float(), m.float()
+    t32 = timed(lambda: tv.ops.deform_conv2d(xf, of, wf, bf, 1, 1, 1, mf), 3, 1)
+    t_ours32 = timed(lambda: vb.ops.deform_conv2d(xf, of, wf, bf, 1, 1, 1, mf), 2, 1)
+    print("cfg4 deform_conv2d ms: ref fp16 (incl. casts)", t16, "ref fp32", t32, "ours bf16", t_ours, "ours fp32", t_ours32, flush=True)
+    del xi, off, w, bi, m, xf, of, wf, bf, mf
+    torch.cuda.empty_cache()
+    # cfg5
+    from torchvision.transforms.v2 import functional as TF
+    img = workloads.cfg5_resize(device=DEV, batch=32)
+    print("cfg5 resize batch 32 ms: ref", timed(lambda: TF.resize(img, [224, 224]), 3, 1), "ours", timed(lambda: vb.transforms.resize(img, [224, 224]), 10), flush=True)
+    print("cfg5 resize bicubic batch 32 ms: ref", timed(lambda: TF.resize(img, [224, 224], interpolation=TF.InterpolationMode.BICUBIC), 3, 1),
+          "ours", timed(lambda: vb.transforms.resize(img, [224, 224], interpolation=TF.InterpolationMode.BICUBIC), 5), flush=True)
+    print("cfg5 resize no-AA batch 32 ms: ref", timed(lambda: TF.resize(img, [224, 224], antialias=False), 3, 1),
+          "ours", timed(lambda: vb.transforms.resize(img, [224, 224], antialias=False), 5), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "dcn"):
+        dcn_headroom()
+    if which in ("all", "ref"):
+        gpu_reference()

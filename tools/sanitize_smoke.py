@@ -19,6 +19,7 @@ def env(k, v):
         os.environ.pop(k, None)
     else:
         os.environ[k] = v
+    vb._lib.core().vb200_reload_env()
 
 
 def roi():

@@ -38,6 +38,7 @@ def core() -> ctypes.CDLL:
             lib = ctypes.CDLL(CORE_LIB, mode=ctypes.RTLD_GLOBAL)
             lib.vb200_last_error.restype = ctypes.c_char_p
             lib.vb200_launch_count.restype = ctypes.c_uint64
+            lib.vb200_reload_env.restype = None
             for name in ("vb200_nms_workspace_bytes", "vb200_batched_nms_workspace_bytes",
                          "vb200_roi_align_workspace_bytes", "vb200_deform_conv2d_workspace_bytes"):
                 getattr(lib, name).restype = ctypes.c_size_t
@@ -62,7 +63,7 @@ def load_ops() -> None:
 
 # every symbol include/vision_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
-    "vb200_abi_version", "vb200_last_error", "vb200_launch_count",
+    "vb200_abi_version", "vb200_last_error", "vb200_launch_count", "vb200_reload_env",
     "vb200_roi_align_workspace_bytes", "vb200_roi_align_forward", "vb200_roi_pool_forward",
     "vb200_ps_roi_align_forward", "vb200_nms_workspace_bytes", "vb200_nms",
     "vb200_batched_nms_workspace_bytes", "vb200_batched_nms", "vb200_deform_conv2d_workspace_bytes",

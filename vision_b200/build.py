@@ -46,7 +46,12 @@ def _newer(target: str, deps: list[str]) -> bool:
 def build_core(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "vision_b200.h")]
+    # every header under csrc/ and include/ is a dependency of every object (struct layouts such as DcnParams and the
+    # mbarrier helpers are shared between translation units; a stale object would link silently)
+    import glob
+
+    headers = sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                     glob.glob(os.path.join(INCLUDE, "*.h")))
     nvcc = _nvcc()
     objs = []
 

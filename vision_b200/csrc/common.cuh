@@ -30,11 +30,11 @@ inline int check_launch(const char* what) {
   return 0;
 }
 
-#define VB200_CUDA_TRY(expr)                                                        \
+#define VB200_CUDA_TRY(...)                                                         \
   do {                                                                              \
-    cudaError_t _e = (expr);                                                        \
+    cudaError_t _e = (__VA_ARGS__);                                                 \
     if (_e != cudaSuccess) {                                                        \
-      vb200::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));             \
+      vb200::set_error("%s failed: %s", #__VA_ARGS__, cudaGetErrorString(_e));      \
       return (int)_e;                                                               \
     }                                                                               \
   } while (0)
@@ -50,6 +50,26 @@ inline int check_launch(const char* what) {
 // device attribute cache (per current device)
 int sm_count();
 int max_smem_optin();
+
+// VB200_* path overrides (testing / profiling): read from the environment ONCE when the library first needs them
+// (no getenv on the per-call path); vb200_reload_env() re-reads them.  nullptr when unset.
+enum EnvKey { ENV_ROI_ALIGN_PATH, ENV_ROI_LINE_AXIS, ENV_NMS_PATH, ENV_BNMS_PATH, ENV_BNMS_WARPS, ENV_RESIZE_PATH, ENV_DCN_PATH,
+              ENV_DCN_CTA2, ENV_DCN_STAGES, ENV_DCN_BN, ENV_ROI_BWD_PATH, ENV_COUNT };
+const char* env_override(EnvKey k);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch: remembers the
+// largest size already granted.
+template <auto kernel>
+inline cudaError_t ensure_dyn_smem(size_t bytes) {
+  static size_t granted[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (bytes <= granted[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) granted[dev] = bytes;
+  return e;
+}
 
 // ---- dtype traits -----------------------------------------------------------
 template <typename T> struct Acc { using type = float; };

@@ -167,7 +167,7 @@ int launch_simt(const void* input, const void* weight, const void* offset, const
     return VB200_EUNSUPPORTED;
   }
   if (smem > 48 * 1024)
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_simt_kernel<T>>(smem));
   const int cout_g = p.c_out / p.groups;
   dim3 grid((unsigned)ceil_div(p.out_h * p.out_w, BN), (unsigned)(p.groups * ceil_div(cout_g, BM)), (unsigned)p.batch);
   deform_conv2d_simt_kernel<T><<<grid, DCN_THREADS, smem, st>>>((const T*)input, (const T*)weight, (const T*)offset,
@@ -219,7 +219,7 @@ extern "C" int vb200_deform_conv2d_forward(const void* input, const void* weight
   VB200_REQUIRE(input && weight && offset && out && (!use_mask || mask), "deform_conv2d: null pointer");
   VB200_REQUIRE((int64_t)c_in * in_h * in_w < (1ll << 31) && batch <= 65535, "deform_conv2d: tensor too large");
   cudaStream_t st = (cudaStream_t)stream;
-  const char* force = getenv("VB200_DCN_PATH");   // "simt" forces the SIMT kernel
+  const char* force = env_override(ENV_DCN_PATH);   // "simt" forces the SIMT kernel
   if (!(force && force[0] == 's')) {
     const int rc = deform_conv2d_tc_try(input, weight, offset, mask, bias, out, dtype, p, workspace, workspace_bytes, st);
     if (rc != 0) return rc == 1 ? 0 : rc;

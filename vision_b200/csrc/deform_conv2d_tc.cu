@@ -666,7 +666,7 @@ size_t tc2_smem_bytes(int KK) {
   return (size_t)TC2_STAGES * (TC_BM + 256) * 128 + 256 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
 }
 bool tc2_enabled(const DcnParams& p) {
-  const char* env = getenv("VB200_DCN_CTA2");
+  const char* env = env_override(ENV_DCN_CTA2);
   if (!(env && env[0] == '1')) return false;
   return p.c_out % 512 == 0 && tc2_smem_bytes(p.kh * p.kw) <= (size_t)max_smem_optin();
 }
@@ -679,7 +679,7 @@ constexpr int tc_kb(int BN) { return BN > 256 ? 32 : 64; }
 // no gain, profiles/deform_conv2d_r1.md).
 int tc_stages(int BN) {
   if (BN <= 256) return 3;
-  const char* env = getenv("VB200_DCN_STAGES");
+  const char* env = env_override(ENV_DCN_STAGES);
   const int n = env ? atoi(env) : 4;        // 4: each gather group owns its own pair of K-32 stages
   return n == 2 || n == 3 ? n : 4;
 }
@@ -687,7 +687,7 @@ size_t tc_smem_bytes(int BN, int KK) {
   return (size_t)tc_stages(BN) * (TC_BM + BN) * 2 * tc_kb(BN) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
 }
 int tc_pick_bn(const DcnParams& p) {
-  const char* env = getenv("VB200_DCN_BN");           // profiling override: 128 / 256 / 512
+  const char* env = env_override(ENV_DCN_BN);           // profiling override: 128 / 256 / 512
   const int KK = p.kh * p.kw;
   const int cands[3] = {512, 256, 128};
   for (int c = 0; c < 3; ++c) {
@@ -707,7 +707,7 @@ bool tc_eligible(int dtype, const DcnParams& p) {
   if (p.c_out % 128 != 0) return false;
   if (tc_pick_bn(p) == 0) return false;
   if ((int64_t)p.in_h * p.in_w * p.c_in >= (1ll << 30)) return false;      // 32-bit byte offsets into one image
-  const char* env = getenv("VB200_DCN_PATH");
+  const char* env = env_override(ENV_DCN_PATH);
   if (env && env[0] == 's') return false;
   return true;
 }
@@ -742,7 +742,7 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
     const int total_tiles = p.batch * ceil_div(HWo, TC_BM);
     dim3 grid2((unsigned)((total_tiles + 1) & ~1), (unsigned)(p.c_out / 512));
     const size_t smem2 = tc2_smem_bytes(KK);
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc2_kernel<T>>(smem2));
     deform_conv2d_tc2_kernel<T><<<grid2, TC_THREADS, smem2, st>>>(nhwc, wpacked, (const T*)offset, (const T*)mask,
                                                                   (const T*)bias, (T*)out, p, total_tiles);
     rc = check_launch("deform_conv2d_tc2_kernel");
@@ -759,8 +759,7 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   const size_t smem = tc_smem_bytes(BN, KK);
 #define VB200_TC_LAUNCH(BN_, ST_)                                                                                         \
   {                                                                                                                       \
-    VB200_CUDA_TRY(cudaFuncSetAttribute(deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)>,                                 \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                         \
+    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)>>(smem));                         \
     deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)><<<grid, TC1_THREADS, smem, st>>>(                                    \
         nhwc, wpacked, (const T*)offset, (const T*)mask, (const T*)bias, (T*)out, p);                                     \
   }

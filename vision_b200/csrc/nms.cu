@@ -43,6 +43,11 @@ struct IouParams {
   // fp32 filter in front of the exact test (bnms_mask_kernel): t = fma(-mid_f, den, inter) has the sign of
   // inter - mid*den whenever |t| > eps_f * den (see make_iou_params); anything else is re-tested exactly.
   float mid_f, eps_f;
+  // boxes are exact widenings of fp16 values and the arithmetic is what nvcc made of devIoU<Half>
+  // (csrc/ops/cuda/nms_kernel.cu:42-54; SASS of the wheel's sm_100 cubin): min/max on the half values, the two
+  // extents and the HEIGHT of each area rounded to half (F2FP.F16.F32), the WIDTH of each area kept in fp32, all
+  // products in fp32, Sb's product contracted into Sa + Sb, IEEE fp32 division, float threshold.
+  int half_mode;
 };
 
 // Both reference predicates have the form  q >= S  with q = RN_f32(inter/den) and S a float:
@@ -76,6 +81,7 @@ inline IouParams make_iou_params(double thr, int semantics) {
   // of v and rules out v == 0.  Tiny or non-finite operands never pass the filter (den > 1e-30 is required).
   p.mid_f = (float)p.mid;
   p.eps_f = p.use_div ? INFINITY : nextafterf(ldexpf(fabsf(p.mid_f), -21), INFINITY);
+  p.half_mode = 0;
   return p;
 }
 
@@ -108,14 +114,27 @@ __device__ __forceinline__ bool iou_gt(const double4a a, const double area_a, co
   return p.semantics == VB200_NMS_CUDA ? (q > (double)p.thr_f) : (q > p.thr_d);
 }
 
-// a = higher-scoring (suppressor) box, b = candidate.  area_a precomputed = mul_rn(a.z-a.x, a.w-a.y).
+__device__ __forceinline__ float half_rn(float v) { return __half2float(__float2half_rn(v)); }
+
+// Area of the suppressor box as the selected reference arithmetic forms it (the "Sa" of devIoU / `areas` of the CPU kernel).
+__device__ __forceinline__ float box_area(const float4 a, const IouParams p) {
+  const float w = sub_rn(a.z, a.x), h = sub_rn(a.w, a.y);
+  return mul_rn(w, p.half_mode ? half_rn(h) : h);
+}
+__device__ __forceinline__ double box_area(const double4a a, const IouParams) { return mul_rn(sub_rn(a.z, a.x), sub_rn(a.w, a.y)); }
+
+// a = higher-scoring (suppressor) box, b = candidate.  area_a precomputed = box_area(a).
 __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const IouParams p) {
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
   const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
-  const float w = fmaxf(sub_rn(right, left), 0.f), h = fmaxf(sub_rn(bottom, top), 0.f);
+  float w = sub_rn(right, left), h = sub_rn(bottom, top);
+  if (p.half_mode) { w = half_rn(w); h = half_rn(h); }
+  w = fmaxf(w, 0.f); h = fmaxf(h, 0.f);
   const float inter = mul_rn(w, h);
   float den;
-  if (p.semantics == VB200_NMS_CUDA) {
+  if (p.half_mode) {
+    den = sub_rn(__fmaf_rn(sub_rn(b.z, b.x), half_rn(sub_rn(b.w, b.y)), area_a), inter);
+  } else if (p.semantics == VB200_NMS_CUDA) {
     // nms_kernel.cu:50-53 as compiled: Sb's product contracted into (Sa + Sb), float threshold
     den = sub_rn(__fmaf_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y), area_a), inter);
   } else {
@@ -172,17 +191,37 @@ __global__ void gather_boxes_cm_kernel(const Box* __restrict__ boxes, const int*
 }
 
 // coordinate trick (boxes.py:103-107): boxes + float(idx) * (max + 1), each op rounded once
+__device__ __forceinline__ float round_storage(float v, int half_mode) { return half_mode ? __half2float(__float2half_rn(v)) : v; }
+__device__ __forceinline__ double round_storage(double v, int) { return v; }
+
+// half_mode: the reference runs every step as a separate fp16 tensor op (boxes.py:103-107 on Half tensors):
+// idxs.to(half), max + 1, the product and the sum are each computed in float and rounded to half.
 template <typename Box>
 __global__ void shift_boxes_kernel(const Box* __restrict__ boxes, const int64_t* __restrict__ idxs,
-                                   const typename ScalarOf<Box>::type* __restrict__ max_coord, Box* __restrict__ out, int n) {
+                                   const typename ScalarOf<Box>::type* __restrict__ max_coord, Box* __restrict__ out, int n,
+                                   int half_mode) {
   using S = typename ScalarOf<Box>::type;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const S step = add_rn(*max_coord, (S)1);
-    const S off = mul_rn((S)idxs[i], step);
+    const S step = round_storage(add_rn(*max_coord, (S)1), half_mode);
+    const S off = round_storage(mul_rn(round_storage((S)idxs[i], half_mode), step), half_mode);
     Box b = boxes[i];
-    b.x = add_rn(b.x, off); b.y = add_rn(b.y, off); b.z = add_rn(b.z, off); b.w = add_rn(b.w, off);
+    b.x = round_storage(add_rn(b.x, off), half_mode); b.y = round_storage(add_rn(b.y, off), half_mode);
+    b.z = round_storage(add_rn(b.z, off), half_mode); b.w = round_storage(add_rn(b.w, off), half_mode);
     out[i] = b;
+  }
+}
+
+// fp16 boxes / scores -> their exact fp32 widenings (the half arithmetic is reproduced on these, see IouParams::half_mode)
+__global__ void widen_half_kernel(const uint2* __restrict__ boxes_h, const __half* __restrict__ scores_h,
+                                  float4* __restrict__ boxes_f, float* __restrict__ scores_f, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint2 v = __ldg(boxes_h + i);
+    const __half2 lo = *reinterpret_cast<const __half2*>(&v.x), hi = *reinterpret_cast<const __half2*>(&v.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    boxes_f[i] = make_float4(a.x, a.y, b.x, b.y);
+    scores_f[i] = __half2float(scores_h[i]);
   }
 }
 
@@ -273,7 +312,7 @@ bnms_mask_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_star
       }
       if (ee - s <= max_len) { e = ee; a = boxes[p]; }     // longer segments take the sequential path
     }
-    const S aw = sub_rn(a.z, a.x), ah = sub_rn(a.w, a.y), sa = mul_rn(aw, ah);
+    const S aw = sub_rn(a.z, a.x), ah = sub_rn(a.w, a.y), sa = box_area(a, prm);
     rbx[tid] = a;
     rarea[tid] = sa;
     rend[tid] = e;
@@ -284,7 +323,7 @@ bnms_mask_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_star
   }
   __syncthreads();
   const int kmax = s_kmax;
-  const bool exact_only = s_rowbad != 0 || prm.use_div != 0 || !(prm.mid_f > 0.f);
+  const bool exact_only = s_rowbad != 0 || prm.use_div != 0 || !(prm.mid_f > 0.f) || prm.half_mode != 0;
   for (int kb = i + warp; kb <= kmax; kb += kMaskWarps) {
     const int col0 = kb * 64;
     ColTerms<Box> c0, c1;
@@ -507,7 +546,7 @@ nms_segment_kernel(const Box* __restrict__ boxes, const int* __restrict__ seg_st
         Box b = zero_box((Box*)nullptr);
         if (tid < nb) { b = boxes[s + b0 + tid]; sup = suppressed[s + b0 + tid] != 0; }
         sb[tid] = b;
-        sarea[tid] = mul_rn(sub_rn(b.z, b.x), sub_rn(b.w, b.y));
+        sarea[tid] = box_area(b, prm);
         const unsigned int m = __ballot_sync(0xffffffffu, sup);
         if (lane == 0) s_rm[warp] = m;
       }
@@ -647,7 +686,7 @@ NmsWs carve_nms(void* base, int64_t n, bool with_mask = true) {
 template <typename Box>
 int run_single_segment(const Box* boxes_sorted, int64_t n, IouParams prm, uint8_t* suppressed,
                        unsigned long long* mask, cudaStream_t st) {
-  const char* force = getenv("VB200_NMS_PATH");      // "chain" | "mask" (testing / profiling)
+  const char* force = env_override(ENV_NMS_PATH);      // "chain" | "mask" (testing / profiling)
   bool use_mask = true;            // measured faster at every size (0.09 vs 0.20 ms at n = 1000; 0.15 vs 0.87 ms at n = 3000)
   if (force && force[0] == 'c') use_mask = false;
   if (force && force[0] == 'm') use_mask = true;
@@ -666,7 +705,7 @@ int run_single_segment(const Box* boxes_sorted, int64_t n, IouParams prm, uint8_
   if (rc) return rc;
   const size_t smem = 2 * (size_t)(cb + 4) * sizeof(unsigned long long);
   if (smem > 24 * 1024)
-    VB200_CUDA_TRY(cudaFuncSetAttribute(bnms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VB200_CUDA_TRY(ensure_dyn_smem<bnms_scan_kernel>(smem));
   bnms_scan_kernel<<<1, kScanThreads, smem, st>>>(mask, cb, (int)n, nullptr, nullptr, (int)n, suppressed);
   return check_launch("bnms_scan_kernel");
 }
@@ -703,23 +742,52 @@ int nms_core(const typename BoxOf<S>::type* boxes, const S* scores, int64_t n, I
 
 using namespace vb200;
 
+namespace {
+// fp16 inputs: the exact fp32 widenings of boxes and scores live in front of the regular workspace
+struct WideWs { float4* boxes; float* scores; size_t total; };
+WideWs carve_wide(void* base, int64_t n) {
+  Carver c(base);
+  WideWs w;
+  w.boxes = c.take<float4>(n);
+  w.scores = c.take<float>(n);
+  w.total = c.off;
+  return w;
+}
+int widen_half(const void* boxes, const void* scores, const WideWs& w, int64_t n, cudaStream_t st) {
+  widen_half_kernel<<<ceil_div((int)n, 256), 256, 0, st>>>((const uint2*)boxes, (const __half*)scores, w.boxes, w.scores, (int)n);
+  return check_launch("widen_half_kernel");
+}
+}  // namespace
+
 extern "C" size_t vb200_nms_workspace_bytes(int64_t n) {
   if (n <= 0) return 0;
-  return carve_nms(nullptr, n).total;
+  return carve_nms(nullptr, n).total + carve_wide(nullptr, n).total;
 }
 
 extern "C" int vb200_nms(const void* boxes, const void* scores, int dtype, int64_t n, double iou_threshold,
                          int semantics, void* workspace, size_t workspace_bytes, int64_t* keep_out,
                          int64_t* num_keep_out, vb200_stream stream) {
-  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64, "nms: boxes must be float32 or float64 (got dtype %d)", dtype);
+  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64 || dtype == VB200_F16,
+                "nms: boxes must be float32, float64 or float16 (got dtype %d)", dtype);
   VB200_REQUIRE(n >= 0 && n < (1ll << 31), "nms: bad box count");
   VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "nms: bad semantics selector");
   VB200_REQUIRE(num_keep_out != nullptr, "nms: null num_keep_out");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
   VB200_REQUIRE(boxes && scores && keep_out && workspace, "nms: null pointer");
-  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "nms: boxes must be 16-byte aligned");
-  const IouParams prm = make_iou_params(iou_threshold, semantics);
+  VB200_REQUIRE(((uintptr_t)boxes % (dtype == VB200_F16 ? 8 : 16)) == 0, "nms: boxes must be aligned to one box (4 scalars)");
+  IouParams prm = make_iou_params(iou_threshold, semantics);
+  if (dtype == VB200_F16) {
+    // the reference has a Half kernel on CUDA only (the CPU kernel raises), so there is one fp16 arithmetic
+    VB200_REQUIRE(semantics == VB200_NMS_CUDA, "nms: float16 boxes exist only with VB200_NMS_CUDA semantics");
+    const WideWs ww = carve_wide(workspace, n);
+    if (workspace_bytes < ww.total) { set_error("nms: workspace too small"); return VB200_EWORKSPACE; }
+    const int rc = widen_half(boxes, scores, ww, n, st);
+    if (rc) return rc;
+    prm.half_mode = 1;
+    return nms_core<float>(ww.boxes, ww.scores, n, prm, (char*)workspace + ww.total, workspace_bytes - ww.total, keep_out,
+                           num_keep_out, st);
+  }
   if (dtype == VB200_F64)
     return nms_core<double>((const double4a*)boxes, (const double*)scores, n, prm, workspace, workspace_bytes, keep_out,
                             num_keep_out, st);
@@ -777,11 +845,12 @@ namespace {
 template <typename S>
 int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_t n, double iou_threshold, int semantics,
               int strategy, bool wide_keys, void* workspace, size_t workspace_bytes, int64_t* keep_out,
-              int64_t* num_keep_out, cudaStream_t st) {
+              int64_t* num_keep_out, cudaStream_t st, int half_mode = 0) {
   using Box = typename BoxOf<S>::type;
   BnmsWs w = carve_bnms(workspace, n);
   if (workspace_bytes < w.total) { set_error("batched_nms: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
-  const IouParams prm = make_iou_params(iou_threshold, semantics);
+  IouParams prm = make_iou_params(iou_threshold, semantics);
+  prm.half_mode = half_mode;
   const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
   if (strategy == VB200_BNMS_AUTO) strategy = (4 * n > 100000) ? VB200_BNMS_VANILLA : VB200_BNMS_TRICK;   // boxes.py:86
 
@@ -789,7 +858,7 @@ int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_
     size_t tb = w.cub_bytes;
     VB200_CUDA_TRY(cub::DeviceReduce::Max(w.cub_temp, tb, (const S*)boxes, (S*)w.max_coord, ni * 4, st));
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
-    shift_boxes_kernel<Box><<<grd, blk, 0, st>>>((const Box*)boxes, idxs, (const S*)w.max_coord, (Box*)w.shifted, ni);
+    shift_boxes_kernel<Box><<<grd, blk, 0, st>>>((const Box*)boxes, idxs, (const S*)w.max_coord, (Box*)w.shifted, ni, half_mode);
     int rc = check_launch("shift_boxes_kernel");
     if (rc) return rc;
     return nms_core<S>((const Box*)w.shifted, (const S*)scores, n, prm, (char*)workspace + w.nms_off,
@@ -821,10 +890,10 @@ int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_
   VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, w.iota, w.seg_flag, w.seg_start, w.num_seg, ni, st));
   g_launch_count.fetch_add(2, std::memory_order_relaxed);
   VB200_CUDA_TRY(cudaMemsetAsync(w.suppressed, 0, (size_t)n, st));
-  const char* mp = getenv("VB200_BNMS_PATH");       // "chain": per-class sequential kernel only (testing / profiling)
+  const char* mp = env_override(ENV_BNMS_PATH);       // "chain": per-class sequential kernel only (testing / profiling)
   const bool use_mask = !(mp && mp[0] == 'c');
   if (use_mask) {
-    const char* mw = getenv("VB200_BNMS_WARPS");     // tuning: warps per mask CTA (2 | 4 | 8)
+    const char* mw = env_override(ENV_BNMS_WARPS);     // tuning: warps per mask CTA (2 | 4 | 8)
     const int warps = mw ? atoi(mw) : 8;
 #define VB200_LAUNCH_MASK(SEMV, WV)                                                                        \
   bnms_mask_kernel<Box, SEMV, WV><<<ceil_div(ni, 64), WV * 32, 0, st>>>((const Box*)w.boxes_cm, w.seg_start, \
@@ -867,14 +936,15 @@ int bnms_core(const void* boxes, const void* scores, const int64_t* idxs, int64_
 
 extern "C" size_t vb200_batched_nms_workspace_bytes(int64_t n) {
   if (n <= 0) return 0;
-  return carve_bnms(nullptr, n).total;
+  return carve_bnms(nullptr, n).total + carve_wide(nullptr, n).total;
 }
 
 extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const int64_t* idxs, int dtype,
                                  int64_t n, double iou_threshold, int semantics, int strategy,
                                  void* workspace, size_t workspace_bytes, int64_t* keep_out,
                                  int64_t* num_keep_out, vb200_stream stream) {
-  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64, "batched_nms: boxes must be float32 or float64 (got dtype %d)", dtype);
+  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64 || dtype == VB200_F16,
+                "batched_nms: boxes must be float32, float64 or float16 (got dtype %d)", dtype);
   VB200_REQUIRE(n >= 0 && n < (1ll << 31), "batched_nms: bad box count");
   VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "batched_nms: bad semantics selector");
   const bool wide_keys = (strategy & VB200_BNMS_WIDE_KEYS) != 0;
@@ -884,7 +954,16 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) { VB200_CUDA_TRY(cudaMemsetAsync(num_keep_out, 0, sizeof(int64_t), st)); return 0; }
   VB200_REQUIRE(boxes && scores && idxs && keep_out && workspace, "batched_nms: null pointer");
-  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0, "batched_nms: boxes must be 16-byte aligned");
+  VB200_REQUIRE(((uintptr_t)boxes % (dtype == VB200_F16 ? 8 : 16)) == 0, "batched_nms: boxes must be aligned to one box (4 scalars)");
+  if (dtype == VB200_F16) {
+    VB200_REQUIRE(semantics == VB200_NMS_CUDA, "batched_nms: float16 boxes exist only with VB200_NMS_CUDA semantics");
+    const WideWs ww = carve_wide(workspace, n);
+    if (workspace_bytes < ww.total) { set_error("batched_nms: workspace too small"); return VB200_EWORKSPACE; }
+    const int rc = widen_half(boxes, scores, ww, n, st);
+    if (rc) return rc;
+    return bnms_core<float>(ww.boxes, ww.scores, idxs, n, iou_threshold, semantics, strategy, wide_keys, (char*)workspace + ww.total,
+                            workspace_bytes - ww.total, keep_out, num_keep_out, st, 1);
+  }
   if (dtype == VB200_F64)
     return bnms_core<double>(boxes, scores, idxs, n, iou_threshold, semantics, strategy, wide_keys, workspace, workspace_bytes,
                              keep_out, num_keep_out, st);

@@ -172,7 +172,7 @@ int launch_resize(const void* in, void* out, int64_t planes, int in_h, int in_w,
       return VB200_EUNSUPPORTED;
     }
     if (smem > 48 * 1024)
-      VB200_CUDA_TRY(cudaFuncSetAttribute(resize_aa_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VB200_CUDA_TRY(ensure_dyn_smem<resize_aa_generic_kernel<T>>(smem));
     int64_t done = 0;
     while (done < planes) {   // gridDim.z limit
       const int64_t chunk = planes - done < 65535 ? planes - done : 65535;

@@ -284,7 +284,7 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
   if (stages < 3) return 0;
   p.n_stages = stages;
   const size_t smem = (size_t)stages * p.row_pitch + (size_t)stages * 16 + fixed;
-  VB200_CUDA_TRY(cudaFuncSetAttribute(resize_aa_stream_kernel<T, NP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VB200_CUDA_TRY(ensure_dyn_smem<resize_aa_stream_kernel<T, NP, NW>>(smem));
   int64_t done = 0;
   while (done < planes) {
     const int64_t chunk = planes - done < 65535 ? planes - done : 65535;
@@ -323,7 +323,7 @@ int dispatch_lw(const void* in, void* out, int64_t planes, const StreamParams& p
 
 int resize_aa_stream_try(const void* in, void* out, int dtype, int64_t planes, int in_h, int in_w, int out_h,
                          int out_w, int mode, cudaStream_t st) {
-  const char* force = getenv("VB200_RESIZE_PATH");            // "generic" disables the fast path
+  const char* force = env_override(ENV_RESIZE_PATH);            // "generic" disables the fast path
   if (force && force[0] == 'g') return 0;
   if (mode != VB200_RESIZE_BILINEAR) return 0;
   if (dtype != VB200_F16 && dtype != VB200_BF16 && dtype != VB200_U8 && dtype != VB200_F32) return 0;

@@ -637,7 +637,7 @@ int roi_align_path(int dtype, const void* input, int batch, int channels, int he
                        line_bytes + 1024 <= (size_t)max_smem_optin();
   const int64_t pairs = (int64_t)batch * channels * num_rois;
   int path = pairs >= 4096 ? (line_ok ? 2 : plane_ok ? 1 : 0) : 0;
-  const char* force = getenv("VB200_ROI_ALIGN_PATH");   // "generic" | "plane" | "line" (testing / profiling)
+  const char* force = env_override(ENV_ROI_ALIGN_PATH);   // "generic" | "plane" | "line" (testing / profiling)
   if (force && force[0] == 'g') path = 0;
   if (force && force[0] == 'p') path = plane_ok ? 1 : 0;
   if (force && force[0] == 'l') path = line_ok ? 2 : 0;
@@ -689,7 +689,7 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       const int pitch = line_pitch(width);
       const size_t smem = line_plane_bytes(height, pitch) + kLineStageBytes;
       LineTab* tab = (LineTab*)workspace;
-      const char* fa = getenv("VB200_ROI_LINE_AXIS");   // diagnosis: "x" | "y" pins the lane axis
+      const char* fa = env_override(ENV_ROI_LINE_AXIS);   // diagnosis: "x" | "y" pins the lane axis
       const int force_axis = fa ? (fa[0] == 'y' ? 2 : fa[0] == 'x' ? 1 : 0) : 0;
       roi_align_line_geometry_kernel<7, 2><<<ceil_div(num_rois * 32, 256), 256, 0, st>>>(
           (const float*)rois, tab, num_rois, height, width, (float)spatial_scale, aligned, pitch, force_axis);
@@ -697,7 +697,7 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       if (rc) return rc;
       const int64_t pairs = (int64_t)batch * channels * num_rois;
       const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
-      VB200_CUDA_TRY(cudaFuncSetAttribute(roi_align_line_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VB200_CUDA_TRY(ensure_dyn_smem<roi_align_line_kernel<7, 2>>(smem));
       // programmatic dependent launch: the gather kernel zeroes its pads and stages its first plane while
       // the geometry kernel is still running, and waits (griddepcontrol.wait) before it reads the table
       cudaLaunchConfig_t cfg = {};
@@ -730,8 +730,7 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       const size_t smem = plane_bytes + 128;
 #define VB200_LAUNCH_PLANE(SR)                                                                                     \
   {                                                                                                                \
-    VB200_CUDA_TRY(cudaFuncSetAttribute(roi_align_plane_kernel<SR>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                        (int)smem));                                                               \
+    VB200_CUDA_TRY(ensure_dyn_smem<roi_align_plane_kernel<SR>>(smem));                                                               \
     roi_align_plane_kernel<SR><<<grid, nthreads, smem, st>>>((const float*)input, geo, rb, (float*)output,         \
                                                              batch, channels, height, width, num_rois,            \
                                                              pooled_h, pooled_w, pitch);                          \

@@ -124,10 +124,18 @@ void check_nms_inputs(const at::Tensor& dets, const at::Tensor& scores) {
               "dimension 0, got ", dets.size(0), " and ", scores.size(0));
 }
 
-// The reference instantiates float / double / Half.  float and double run natively (both arithmetics
-// are reproduced bit for bit); Half is widened to float (its reference kernel already multiplies in float).
-at::Tensor nms_operand(const at::Tensor& t) {
-  return (t.scalar_type() == at::kDouble ? t : t.to(at::kFloat)).contiguous();
+// The reference instantiates float / double / Half (cuda/nms_kernel.cu:32-54); all three run natively, each
+// with the arithmetic of its compiled reference kernel.  Other dtypes are rejected as the reference's dispatch does.
+// A contiguous view whose storage offset breaks the one-box alignment of the vector loads is copied.
+int nms_dtype(const at::Tensor& t, const char* op) {
+  const auto st = t.scalar_type();
+  TORCH_CHECK(st == at::kFloat || st == at::kDouble || st == at::kHalf, op, ": \"nms_kernel\" not implemented for '", st, "'");
+  return st == at::kDouble ? VB200_F64 : st == at::kHalf ? VB200_F16 : VB200_F32;
+}
+at::Tensor nms_operand(const at::Tensor& t, size_t align) {
+  at::Tensor c = t.contiguous();
+  if (((uintptr_t)c.data_ptr() % align) != 0) c = c.clone();
+  return c;
 }
 
 at::Tensor nms(const at::Tensor& dets, const at::Tensor& scores, double iou_threshold) {
@@ -135,14 +143,14 @@ at::Tensor nms(const at::Tensor& dets, const at::Tensor& scores, double iou_thre
   TORCH_CHECK(dets.scalar_type() == scores.scalar_type(), "dets should have the same type as scores");
   at::cuda::CUDAGuard guard(dets.device());
   if (dets.numel() == 0) return at::empty({0}, dets.options().dtype(at::kLong));
-  at::Tensor boxes = nms_operand(dets), sc = nms_operand(scores);
-  const int dt = boxes.scalar_type() == at::kDouble ? VB200_F64 : VB200_F32;
+  const int dt = nms_dtype(dets, "nms");
+  at::Tensor boxes = nms_operand(dets, 4 * dets.element_size()), sc = nms_operand(scores, scores.element_size());
   const int64_t n = boxes.size(0);
   const size_t wsb = vb200_nms_workspace_bytes(n);
   at::Tensor ws = workspace(wsb, boxes);
   at::Tensor keep = at::empty({n}, boxes.options().dtype(at::kLong));
   at::Tensor count = at::empty({1}, boxes.options().dtype(at::kLong));
-  check_rc(vb200_nms(boxes.data_ptr(), sc.data_ptr(), dt, n, iou_threshold, g_nms_semantics.load(), ws.data_ptr(),
+  check_rc(vb200_nms(boxes.data_ptr(), sc.data_ptr(), dt, n, iou_threshold, dt == VB200_F16 ? VB200_NMS_CUDA : g_nms_semantics.load(), ws.data_ptr(),
                      wsb, keep.data_ptr<int64_t>(), count.data_ptr<int64_t>(), cur_stream()),
            "nms");
   const int64_t k = count.item<int64_t>();   // the reference's masked_select sync (nms_kernel.cu:257)
@@ -155,9 +163,9 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
   TORCH_CHECK(idxs.dim() == 1 && idxs.size(0) == dets.size(0), "idxs should be a 1d tensor with one entry per box");
   at::cuda::CUDAGuard guard(dets.device());
   if (dets.numel() == 0) return at::empty({0}, dets.options().dtype(at::kLong));
-  at::Tensor boxes = nms_operand(dets), sc = nms_operand(scores);
-  TORCH_CHECK(boxes.scalar_type() == sc.scalar_type(), "boxes should have the same type as scores");
-  const int dt = boxes.scalar_type() == at::kDouble ? VB200_F64 : VB200_F32;
+  TORCH_CHECK(dets.scalar_type() == scores.scalar_type(), "boxes should have the same type as scores");
+  const int dt = nms_dtype(dets, "batched_nms");
+  at::Tensor boxes = nms_operand(dets, 4 * dets.element_size()), sc = nms_operand(scores, scores.element_size());
   at::Tensor cls = idxs.to(at::kLong).contiguous();
   const int64_t n = boxes.size(0);
   const size_t wsb = vb200_batched_nms_workspace_bytes(n);
@@ -169,7 +177,7 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
     // first attempt speculates 16-bit class ids; -1 asks for the wide-key repeat (arbitrary int64 ids)
     const int strategy = VB200_BNMS_AUTO | (attempt ? VB200_BNMS_WIDE_KEYS : 0);
     check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), dt, n, iou_threshold,
-                               g_nms_semantics.load(), strategy, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
+                               dt == VB200_F16 ? VB200_NMS_CUDA : g_nms_semantics.load(), strategy, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
                                count.data_ptr<int64_t>(), cur_stream()),
              "batched_nms");
     k = count.item<int64_t>();
