@@ -435,7 +435,7 @@ def test_deform_conv2d_reference_test_geometry(vb, oracle, batch, dtype):
         if batch:
             want = oracle.deform_conv2d(x.float().numpy(), off.float().numpy(), w.float().numpy(), bias.float().numpy(),
                                         (sh, sw), (ph, pw), (dh, dw), None if mask is None else mask.float().numpy())
-            np.testing.assert_allclose(npy(got), want, **(F32_TOL if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)))
+            np.testing.assert_allclose(npy(got), want, **(F32_TOL if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)))   # north_star: 1e-2 for 16-bit
     # non-contiguous inputs are accepted (reference calls .contiguous())
     if batch:
         xt = x.to(DEV).permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)
@@ -494,21 +494,17 @@ def test_deform_conv2d_cta_pair_variant_matches(vb, oracle):
         np.testing.assert_allclose(npy(two), want, rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
 def test_deform_conv2d_zero_offset_is_conv2d(vb, dtype, tol):
-    """Property at a larger size: offsets 0 and no mask == plain convolution (cuDNN, fp32)."""
+    """Property at a larger size: offsets 0 and no mask == plain convolution (fp64 convolution of the same rounded values
+    as the ground truth, so the bound is on OUR error only: 1e-5 fp32 / 1e-2 bf16 as north_star states)."""
     from vision_b200 import workloads
 
     x, off, w, b, _ = workloads.cfg4_deform_conv2d(batch=4, c_in=256, c_out=256, hw=64, dtype=dtype, offset_scale=0.0, use_mask=False)
     x, off, w, b = x.to(DEV), off.to(DEV), w.to(DEV), b.to(DEV)
     got = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, None)
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        want = torch.nn.functional.conv2d(x.float(), w.float(), b.float(), stride=1, padding=1)
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
-    np.testing.assert_allclose(npy(got), npy(want), rtol=tol, atol=tol)
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=1, padding=1)
+    np.testing.assert_allclose(got.double().cpu().numpy(), want.cpu().numpy(), rtol=tol, atol=tol)
 
 
 # =============================== resize =========================================

@@ -517,89 +517,189 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
 }
 
 // ---------------------------------------------------------------------------
-// roi_pool: one thread per output element, bin window shared arithmetic
-// (roi_pool_kernel.cu:15-78) — integer/compare work, bit-exact incl. argmax.
+// Plane-major work split shared by roi_pool / ps_roi_align (and the roi_align plane kernels): all
+// (plane, RoI) pairs in plane-major order, cut evenly over the CTAs; a CTA stages a plane into shared
+// memory only when its range enters it.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256)
-roi_pool_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
-                int32_t* __restrict__ argmax, int64_t total, int C, int H, int W, int PH, int PW,
-                typename Acc<T>::type scale) {
-  using A = typename Acc<T>::type;
-  for (int64_t index = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; index < total;
-       index += (int64_t)gridDim.x * blockDim.x) {
-    const int pw = (int)(index % PW);
-    const int ph = (int)((index / PW) % PH);
-    const int c = (int)((index / PW / PH) % C);
-    const int64_t n = index / PW / PH / C;
-    const T* r = rois + n * 5;
-    const int b = (int)to_acc(r[0]);
-    const int rsw = (int)round(mul_rn((A)to_acc(r[1]), scale));
-    const int rsh = (int)round(mul_rn((A)to_acc(r[2]), scale));
-    const int rew = (int)round(mul_rn((A)to_acc(r[3]), scale));
-    const int reh = (int)round(mul_rn((A)to_acc(r[4]), scale));
-    const int rw = max(rew - rsw + 1, 1), rh = max(reh - rsh + 1, 1);
-    const A bh = div_rn((A)rh, (A)PH), bw = div_rn((A)rw, (A)PW);
-    int hs = (int)floor(mul_rn((A)ph, bh)), ws = (int)floor(mul_rn((A)pw, bw));
-    int he = (int)ceil(mul_rn((A)(ph + 1), bh)), we = (int)ceil(mul_rn((A)(pw + 1), bw));
-    hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
-    ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
-    const bool empty = (he <= hs) || (we <= ws);
-    A maxval = empty ? (A)0 : (A)-3.402823466e+38F;   // -FLT_MAX, also for double (reference uses -FLT_MAX)
-    int maxidx = -1;
-    const T* in = input + ((int64_t)b * C + c) * H * W;
-    for (int h = hs; h < he; ++h)
-      for (int w = ws; w < we; ++w) {
-        const int ii = h * W + w;
-        const A v = to_acc(in[ii]);
-        if (v > maxval) { maxval = v; maxidx = ii; }
-      }
-    output[index] = from_acc<T, A>(maxval);
-    argmax[index] = maxidx;
+__device__ __forceinline__ void stage_plane_flat(T* __restrict__ dst, const T* __restrict__ src, int count) {
+  // flat copy of one contiguous H*W plane: 16-byte vectors when source and element count allow it
+  const int tid = threadIdx.x, NT = blockDim.x;
+  if ((((uintptr_t)src) & 15u) == 0) {
+    const int nvec = (int)(((size_t)count * sizeof(T)) / 16);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = tid; i < nvec; i += NT) d4[i] = __ldg(s4 + i);
+    for (int i = (int)((size_t)nvec * 16 / sizeof(T)) + tid; i < count; i += NT) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < count; i += NT) dst[i] = src[i];
   }
 }
 
 // ---------------------------------------------------------------------------
-// ps_roi_align: one thread per output element, reference arithmetic order
-// (ps_roi_align_kernel.cu:68-140) with uncontracted coordinates.
+// roi_pool (reference semantics: csrc/ops/cuda/roi_pool_kernel.cu:15-78, cpu/roi_pool_kernel.cpp:24-92).
+// Not the reference's thread-per-output design: a WARP owns one (RoI, plane) pair and its lanes are the
+// bin columns x Q sub-lanes; it walks the bin rows once, every lane scanning its own columns of the bin window
+// top to bottom (so each input word of the RoI is read about once per plane instead of once per overlapping
+// output thread), then the Q sub-lanes of a bin combine (value, index) pairs with the reference's tie rule
+// (strict '>' in a row-major scan == larger value, then smaller flat index).  RESIDENT: the plane sits in
+// shared memory (each input byte leaves HBM once); otherwise the same code reads the plane through L1/L2.
+// The RoI's integer geometry is derived once per (RoI, plane), not once per output element.
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
-ps_roi_align_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
-                    int32_t* __restrict__ mapping, int64_t total, int C, int H, int W, int PH, int PW,
-                    int Cout, typename Acc<T>::type scale, int sampling_ratio) {
+template <typename A>
+struct PoolGeom { int batch, rsw, rsh; A bh, bw; };
+
+template <typename T, typename A>
+__device__ __forceinline__ PoolGeom<A> pool_geometry(const T* __restrict__ r, A scale, int PH, int PW) {
+  PoolGeom<A> g;
+  g.batch = (int)to_acc(r[0]);
+  g.rsw = (int)round(mul_rn((A)to_acc(r[1]), scale));
+  g.rsh = (int)round(mul_rn((A)to_acc(r[2]), scale));
+  const int rew = (int)round(mul_rn((A)to_acc(r[3]), scale));
+  const int reh = (int)round(mul_rn((A)to_acc(r[4]), scale));
+  const int rw = max(rew - g.rsw + 1, 1), rh = max(reh - g.rsh + 1, 1);   // malformed RoIs become 1x1
+  g.bh = div_rn((A)rh, (A)PH);
+  g.bw = div_rn((A)rw, (A)PW);
+  return g;
+}
+
+template <typename T, bool RESIDENT>
+__global__ void __launch_bounds__(RESIDENT ? 1024 : 256, RESIDENT ? 1 : 4)
+roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                      int32_t* __restrict__ argmax, int B, int C, int H, int W, int K, int PH, int PW,
+                      typename Acc<T>::type scale) {
   using A = typename Acc<T>::type;
-  for (int64_t index = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; index < total;
-       index += (int64_t)gridDim.x * blockDim.x) {
-    const int pw = (int)(index % PW);
-    const int ph = (int)((index / PW) % PH);
-    const int co = (int)((index / PW / PH) % Cout);
-    const int64_t n = index / PW / PH / Cout;
-    const int c_in = (co * PH + ph) * PW + pw;
-    const RoiGeom<A> g = roi_geometry<T, A>(rois + n * 5, scale, PH, PW, sampling_ratio, true, true);
-    const A hstart = add_rn(mul_rn((A)ph, g.bin_h), g.start_h);
-    const A wstart = add_rn(mul_rn((A)pw, g.bin_w), g.start_w);
-    const T* in = input + ((int64_t)g.batch * C + c_in) * H * W;
-    A sum = 0;
-    for (int iy = 0; iy < g.gh; ++iy) {
-      const A y = add_rn(hstart, div_rn(mul_rn((A)((float)iy + .5f), g.bin_h), (A)g.gh));
-      const AxisEnt<A> ey = axis_entry<A>(y, H);
-      for (int ix = 0; ix < g.gw; ++ix) {
-        const A x = add_rn(wstart, div_rn(mul_rn((A)((float)ix + .5f), g.bin_w), (A)g.gw));
-        const AxisEnt<A> ex = axis_entry<A>(x, W);
-        A val = 0;
-        if (ey.lo >= 0 && ex.lo >= 0) {
-          const A v1 = to_acc(in[ey.lo * W + ex.lo]), v2 = to_acc(in[ey.lo * W + ex.hi]);
-          const A v3 = to_acc(in[ey.hi * W + ex.lo]), v4 = to_acc(in[ey.hi * W + ex.hi]);
-          const A w1 = mul_rn(ey.h, ex.h), w2 = mul_rn(ey.h, ex.l), w3 = mul_rn(ey.l, ex.h), w4 = mul_rn(ey.l, ex.l);
-          val = add_rn(add_rn(add_rn(mul_rn(w1, v1), mul_rn(w2, v2)), mul_rn(w3, v3)), mul_rn(w4, v4));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* plane_s = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+  const int64_t total = (int64_t)B * C * K;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per, w1 = min(total, w0 + per);
+  // lane -> (bin column, sub-lane): Q = largest power of two with PW * Q <= 32 (1 when PW >= 17)
+  int Q = 1;
+  while (PW * Q * 2 <= 32) Q *= 2;
+  const int pw_l = lane / Q, q = lane - pw_l * Q;
+  const A neg_max = (A)-3.402823466e+38F;   // -FLT_MAX for every dtype, as the reference initialises it
+
+  int64_t w = w0;
+  while (w < w1) {
+    const int pl = (int)(w / K);
+    const int r0 = (int)(w - (int64_t)pl * K);
+    const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
+    const int b = pl / C, c = pl - b * C;
+    const T* __restrict__ plane = input + (int64_t)pl * H * W;
+    if (RESIDENT) {
+      __syncthreads();                       // previous plane no longer read
+      stage_plane_flat<T>(plane_s, plane, H * W);
+      __syncthreads();
+      plane = plane_s;
+    }
+    for (int n = r0 + warp; n < r1; n += NW) {
+      const PoolGeom<A> g = pool_geometry<T, A>(rois + (int64_t)n * 5, scale, PH, PW);
+      if (g.batch != b) continue;
+      T* __restrict__ outp = output + ((int64_t)n * C + c) * PH * PW;
+      int32_t* __restrict__ argp = argmax + ((int64_t)n * C + c) * PH * PW;
+      for (int pw0 = 0; pw0 < PW; pw0 += 32 / Q) {
+        const int pw = pw0 + pw_l;
+        const bool act = pw < PW && pw_l < 32 / Q;
+        int ws = 0, we = 0;
+        if (act) {
+          ws = (int)floor(mul_rn((A)pw, g.bw));
+          we = (int)ceil(mul_rn((A)(pw + 1), g.bw));
+          ws = min(max(ws + g.rsw, 0), W);
+          we = min(max(we + g.rsw, 0), W);
         }
-        sum = add_rn(sum, val);
+        for (int ph = 0; ph < PH; ++ph) {
+          int hs = (int)floor(mul_rn((A)ph, g.bh));
+          int he = (int)ceil(mul_rn((A)(ph + 1), g.bh));
+          hs = min(max(hs + g.rsh, 0), H);
+          he = min(max(he + g.rsh, 0), H);
+          A best = neg_max;
+          int idx = -1;
+          for (int h = hs; h < he; ++h) {
+            const T* __restrict__ row = plane + h * W;
+            for (int x = ws + q; x < we; x += Q) {
+              const A v = to_acc(row[x]);
+              if (v > best) { best = v; idx = h * W + x; }
+            }
+          }
+          for (int o = 1; o < Q; o <<= 1) {
+            const A ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > best || (ov == best && (unsigned)oi < (unsigned)idx)) { best = ov; idx = oi; }
+          }
+          if (act && q == 0) {
+            const bool empty = (he <= hs) || (we <= ws);
+            outp[ph * PW + pw] = from_acc<T, A>(empty ? (A)0 : best);
+            argp[ph * PW + pw] = idx;
+          }
+        }
       }
     }
-    sum = div_rn(sum, g.count);
-    output[index] = from_acc<T, A>(sum);
-    mapping[index] = c_in;
+    w += (r1 - r0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ps_roi_align (reference semantics: csrc/ops/cuda/ps_roi_align_kernel.cu:68-140).  Position-sensitive pooling
+// reads input channel c_in = (c_out * PH + ph) * PW + pw for bin (ph, pw) only, i.e. an input plane serves exactly
+// ONE bin position of one output channel, for every RoI.  So the work is organised by input plane: a CTA holds
+// plane (b, c_in) (RESIDENT: in shared memory, one pass over HBM) and its THREADS are the RoIs - each thread
+// evaluates its RoI's single bin on that plane (gh x gw samples).  The bin arithmetic is the reference's, with
+// uncontracted coordinates, so degenerate RoIs give the same inf / NaN.
+// ---------------------------------------------------------------------------
+template <typename T, bool RESIDENT>
+__global__ void __launch_bounds__(RESIDENT ? 1024 : 256, RESIDENT ? 1 : 4)
+ps_roi_align_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                          int32_t* __restrict__ mapping, int B, int C, int H, int W, int K, int PH, int PW, int Cout,
+                          typename Acc<T>::type scale, int sampling_ratio) {
+  using A = typename Acc<T>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* plane_s = reinterpret_cast<T*>(smem_raw);
+  const int64_t total = (int64_t)B * C * K;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per, w1 = min(total, w0 + per);
+  int64_t w = w0;
+  while (w < w1) {
+    const int pl = (int)(w / K);
+    const int r0 = (int)(w - (int64_t)pl * K);
+    const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
+    const int b = pl / C, c_in = pl - b * C;
+    const int pw = c_in % PW, ph = (c_in / PW) % PH, co = c_in / (PW * PH);
+    const T* __restrict__ plane = input + (int64_t)pl * H * W;
+    if (RESIDENT) {
+      __syncthreads();
+      stage_plane_flat<T>(plane_s, plane, H * W);
+      __syncthreads();
+      plane = plane_s;
+    }
+    for (int n = r0 + (int)threadIdx.x; n < r1; n += (int)blockDim.x) {
+      const RoiGeom<A> g = roi_geometry<T, A>(rois + (int64_t)n * 5, scale, PH, PW, sampling_ratio, true, true);
+      if (g.batch != b) continue;
+      const A hstart = add_rn(mul_rn((A)ph, g.bin_h), g.start_h);
+      const A wstart = add_rn(mul_rn((A)pw, g.bin_w), g.start_w);
+      A sum = 0;
+      for (int iy = 0; iy < g.gh; ++iy) {
+        const A y = add_rn(hstart, div_rn(mul_rn((A)((float)iy + .5f), g.bin_h), (A)g.gh));
+        const AxisEnt<A> ey = axis_entry<A>(y, H);
+        for (int ix = 0; ix < g.gw; ++ix) {
+          const A x = add_rn(wstart, div_rn(mul_rn((A)((float)ix + .5f), g.bin_w), (A)g.gw));
+          const AxisEnt<A> ex = axis_entry<A>(x, W);
+          A val = 0;
+          if (ey.lo >= 0 && ex.lo >= 0) {
+            const A v1 = to_acc(plane[ey.lo * W + ex.lo]), v2 = to_acc(plane[ey.lo * W + ex.hi]);
+            const A v3 = to_acc(plane[ey.hi * W + ex.lo]), v4 = to_acc(plane[ey.hi * W + ex.hi]);
+            const A w1 = mul_rn(ey.h, ex.h), w2 = mul_rn(ey.h, ex.l), w3 = mul_rn(ey.l, ex.h), w4 = mul_rn(ey.l, ex.l);
+            val = add_rn(add_rn(add_rn(mul_rn(w1, v1), mul_rn(w2, v2)), mul_rn(w3, v3)), mul_rn(w4, v4));
+          }
+          sum = add_rn(sum, val);
+        }
+      }
+      const int64_t o = (((int64_t)n * Cout + co) * PH + ph) * PW + pw;
+      output[o] = from_acc<T, A>(div_rn(sum, g.count));
+      mapping[o] = c_in;
+    }
+    w += (r1 - r0);
   }
 }
 
@@ -757,14 +857,34 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
   return VB200_EUNSUPPORTED;
 }
 
+// Plane residency pays when the RoIs of a plane touch more bytes than the plane has; tiny problems read through L2.
 template <typename T>
-static int launch_roi_pool(const void* input, const void* rois, void* output, int32_t* argmax, int C, int H, int W,
+static bool plane_resident_ok(int H, int W, int64_t bytes_touched_per_plane) {
+  const size_t plane_bytes = (size_t)H * W * sizeof(T);
+  return plane_bytes + 1024 <= (size_t)max_smem_optin() && bytes_touched_per_plane >= (int64_t)plane_bytes;
+}
+
+template <typename T>
+static int launch_roi_pool(const void* input, const void* rois, void* output, int32_t* argmax, int B, int C, int H, int W,
                            int K, int PH, int PW, double scale, cudaStream_t st) {
-  const int64_t total = (int64_t)K * C * PH * PW;
-  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count() * 32 ? ceil_div64(total, 256) : (int64_t)sm_count() * 32);
-  roi_pool_kernel<T><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, argmax, total, C, H, W, PH, PW,
-                                          (typename Acc<T>::type)scale);
-  return check_launch("roi_pool_kernel");
+  using A = typename Acc<T>::type;
+  const int64_t pairs = (int64_t)B * C * K;
+  if (pairs == 0) return 0;
+  // a RoI reads its whole window; count a conservative 16 x 16 window per RoI for the residency decision
+  const bool resident = plane_resident_ok<T>(H, W, (int64_t)K * 256 * (int64_t)sizeof(T) / (B > 1 ? B : 1));
+  if (resident) {
+    const size_t smem = (size_t)H * W * sizeof(T) + 16;
+    const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+    VB200_CUDA_TRY(ensure_dyn_smem<roi_pool_plane_kernel<T, true>>(smem));
+    roi_pool_plane_kernel<T, true><<<grid, 1024, smem, st>>>((const T*)input, (const T*)rois, (T*)output, argmax, B, C, H, W, K,
+                                                            PH, PW, (A)scale);
+  } else {
+    const int64_t want = ceil_div64(pairs, 8);          // 8 warps per CTA, one (RoI, plane) pair per warp
+    const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+    roi_pool_plane_kernel<T, false><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, argmax, B, C, H, W, K, PH,
+                                                         PW, (A)scale);
+  }
+  return check_launch("roi_pool_plane_kernel");
 }
 
 extern "C" int vb200_roi_pool_forward(const void* input, const void* rois, void* output, int32_t* argmax,
@@ -776,24 +896,37 @@ extern "C" int vb200_roi_pool_forward(const void* input, const void* rois, void*
   VB200_REQUIRE((int64_t)batch * channels * height * width < (1ll << 31), "roi_pool: input too large for 32-bit indexing");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case VB200_F32: return launch_roi_pool<float>(input, rois, output, argmax, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
-    case VB200_F16: return launch_roi_pool<__half>(input, rois, output, argmax, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
-    case VB200_F64: return launch_roi_pool<double>(input, rois, output, argmax, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F32: return launch_roi_pool<float>(input, rois, output, argmax, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F16: return launch_roi_pool<__half>(input, rois, output, argmax, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F64: return launch_roi_pool<double>(input, rois, output, argmax, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
   }
   set_error("roi_pool: unsupported dtype %d", dtype);
   return VB200_EUNSUPPORTED;
 }
 
 template <typename T>
-static int launch_ps_roi_align(const void* input, const void* rois, void* output, int32_t* mapping, int C, int H, int W,
+static int launch_ps_roi_align(const void* input, const void* rois, void* output, int32_t* mapping, int B, int C, int H, int W,
                                int K, int PH, int PW, double scale, int sr, cudaStream_t st) {
+  using A = typename Acc<T>::type;
   const int Cout = C / (PH * PW);
-  const int64_t total = (int64_t)K * Cout * PH * PW;
-  if (total == 0) return 0;
-  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count() * 32 ? ceil_div64(total, 256) : (int64_t)sm_count() * 32);
-  ps_roi_align_kernel<T><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, mapping, total, C, H, W, PH,
-                                              PW, Cout, (typename Acc<T>::type)scale, sr);
-  return check_launch("ps_roi_align_kernel");
+  const int64_t pairs = (int64_t)B * C * K;
+  if (pairs == 0 || Cout == 0) return 0;
+  const int grid_s = sr > 0 ? sr : 2;
+  // a RoI touches gh * gw * 4 sectors of 32 bytes on its plane
+  const bool resident = plane_resident_ok<T>(H, W, (int64_t)K * grid_s * grid_s * 4 * 32 / (B > 1 ? B : 1));
+  if (resident) {
+    const size_t smem = (size_t)H * W * sizeof(T) + 16;
+    const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+    VB200_CUDA_TRY(ensure_dyn_smem<ps_roi_align_plane_kernel<T, true>>(smem));
+    ps_roi_align_plane_kernel<T, true><<<grid, 1024, smem, st>>>((const T*)input, (const T*)rois, (T*)output, mapping, B, C, H, W,
+                                                                K, PH, PW, Cout, (A)scale, sr);
+  } else {
+    const int64_t want = ceil_div64(pairs, 256);
+    const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+    ps_roi_align_plane_kernel<T, false><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, mapping, B, C, H, W, K,
+                                                             PH, PW, Cout, (A)scale, sr);
+  }
+  return check_launch("ps_roi_align_plane_kernel");
 }
 
 extern "C" int vb200_ps_roi_align_forward(const void* input, const void* rois, void* output,
@@ -808,9 +941,9 @@ extern "C" int vb200_ps_roi_align_forward(const void* input, const void* rois, v
   VB200_REQUIRE((int64_t)batch * channels * height * width < (1ll << 31), "ps_roi_align: input too large for 32-bit indexing");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case VB200_F32: return launch_ps_roi_align<float>(input, rois, output, channel_mapping, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
-    case VB200_F16: return launch_ps_roi_align<__half>(input, rois, output, channel_mapping, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
-    case VB200_F64: return launch_ps_roi_align<double>(input, rois, output, channel_mapping, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
+    case VB200_F32: return launch_ps_roi_align<float>(input, rois, output, channel_mapping, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
+    case VB200_F16: return launch_ps_roi_align<__half>(input, rois, output, channel_mapping, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
+    case VB200_F64: return launch_ps_roi_align<double>(input, rois, output, channel_mapping, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, sampling_ratio, st);
   }
   set_error("ps_roi_align: unsupported dtype %d", dtype);
   return VB200_EUNSUPPORTED;
