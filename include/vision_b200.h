@@ -111,6 +111,29 @@ VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, vo
                                int height, int width, int num_rois, int pooled_h, int pooled_w,
                                double spatial_scale, int sampling_ratio, vb200_stream stream);
 
+/* ---- backward of the RoI ops --------------------------------------------
+ * Replace roi_align_backward_kernel (csrc/ops/cuda/roi_align_kernel.cu:396-468, schema roi_align.cpp:76-77),
+ * roi_pool_backward_kernel (cuda/roi_pool_kernel.cu:190-260, schema roi_pool.cpp:69-70) and
+ * ps_roi_align_backward_kernel (cuda/ps_roi_align_kernel.cu:391-458, schema ps_roi_align.cpp:76-77).
+ * grad [num_rois, C_out, pooled_h, pooled_w] DENSE (the shim makes it contiguous), rois [num_rois, 5],
+ * grad_input [batch, channels, height, width] - written IN FULL (no pre-zeroing).  Unlike the reference (atomics,
+ * alertNotDeterministic) the fp32 / fixed-sampling-grid path is bit-reproducible: every grad_input plane is
+ * accumulated in shared memory by row-owning warps in a fixed order.  Other dtypes (F16, F64), adaptive sampling
+ * (sampling_ratio <= 0) and planes larger than shared memory use an atomic scatter kernel.
+ * workspace: vb200_roi_backward_workspace_bytes() bytes (sampling tables; pass sampling_ratio 1 for roi_pool). */
+VB200_API size_t vb200_roi_backward_workspace_bytes(int num_rois, int pooled_h, int pooled_w, int sampling_ratio);
+VB200_API int vb200_roi_align_backward(const void* grad, const void* rois, void* grad_input, int dtype, int batch,
+                             int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                             double spatial_scale, int sampling_ratio, int aligned, void* workspace,
+                             size_t workspace_bytes, vb200_stream stream);
+VB200_API int vb200_roi_pool_backward(const void* grad, const void* rois, const int32_t* argmax, void* grad_input, int dtype,
+                            int batch, int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                            double spatial_scale, void* workspace, size_t workspace_bytes, vb200_stream stream);
+VB200_API int vb200_ps_roi_align_backward(const void* grad, const void* rois, const int32_t* channel_mapping, void* grad_input,
+                                int dtype, int batch, int channels, int height, int width, int num_rois, int pooled_h,
+                                int pooled_w, double spatial_scale, int sampling_ratio, void* workspace,
+                                size_t workspace_bytes, vb200_stream stream);
+
 /* ---- nms ---------------------------------------------------------------
  * Replaces nms_kernel, csrc/ops/cuda/nms_kernel.cu:166-258 (schema
  * torchvision::nms, csrc/ops/nms.cpp:27).  boxes [n,4] (x1,y1,x2,y2), scores [n].

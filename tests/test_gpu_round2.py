@@ -140,3 +140,194 @@ def test_deform_conv2d_cfg4_full_size_vs_reference_cuda(vb, oracle, variant):
     sl = slice(31, 32)
     want_cpu = oracle.deform_conv2d(npy(x[sl]), npy(off[sl]), npy(w), npy(b), (1, 1), (1, 1), (1, 1), None if m is None else npy(m[sl]))
     np.testing.assert_allclose(npy(got[sl]), want_cpu, rtol=1e-2, atol=1e-2)
+
+
+# =============================== roi_pool / ps_roi_align forward: new plane-major kernels ===============================
+def _rois(k, b, h, w, scale, seed, small=False):
+    g = torch.Generator().manual_seed(seed)
+    ih, iw = h / scale, w / scale
+    x1 = torch.rand(k, generator=g) * iw * 1.1 - 0.05 * iw        # a few RoIs start outside the image
+    y1 = torch.rand(k, generator=g) * ih * 1.1 - 0.05 * ih
+    span = 0.08 if small else 0.6
+    bw = torch.rand(k, generator=g) * iw * span + 0.2
+    bh = torch.rand(k, generator=g) * ih * span + 0.2
+    return torch.stack([torch.randint(0, b, (k,), generator=g).float(), x1, y1, x1 + bw, y1 + bh], dim=1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
+def test_roi_pool_plane_major_shapes_bit_exact_vs_reference_cuda(vb, oracle, dtype):
+    """Every lane mapping of roi_pool_plane_kernel (Q = 32 / PW sub-lanes: PW 1, 2, 5, 7, 16, 17, 40) on resident and
+    non-resident planes, batch > 1, RoIs partly outside, empty bins: output AND argmax identical to the reference."""
+    tv = pytest.importorskip("torchvision")
+    assert not vb.installed()
+    cases = [((2, 5, 40, 52), 300, (7, 7), 0.25), ((1, 3, 30, 30), 1200, (5, 5), 0.5), ((3, 4, 25, 33), 200, (3, 17), 1.0),
+             ((1, 2, 64, 48), 2000, (2, 40), 0.5), ((2, 6, 20, 20), 40, (1, 1), 1.0), ((1, 8, 200, 272), 600, (7, 7), 0.25),
+             ((1, 2, 300, 400), 100, (4, 2), 0.25)]                      # last: fp32 plane 480 KB > shared memory
+    for shape, k, (ph, pw), scale in cases:
+        b, c, h, w = shape
+        g = torch.Generator().manual_seed(k + pw)
+        x = torch.randn(*shape, generator=g)
+        x[:, :, ::3, ::4] = 0.75                                          # exact ties: the first maximum in row-major order wins
+        rois = _rois(k, b, h, w, scale, seed=k)
+        xd, rd = x.to(dtype).to(DEV), rois.to(dtype).to(DEV)
+        o1, a1 = torch.ops.torchvision.roi_pool(xd, rd, scale, ph, pw)
+        o2, a2 = torch.ops.vision_b200.roi_pool(xd, rd, scale, ph, pw)
+        assert torch.equal(a1, a2), (shape, ph, pw, dtype)
+        assert torch.equal(o1, o2), (shape, ph, pw, dtype)
+    if dtype == torch.float32:
+        wo, wa = oracle.roi_pool(x.numpy(), rois.numpy(), (ph, pw), scale)
+        assert np.array_equal(npy(o2), wo) and np.array_equal(npy(a2), wa)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
+def test_ps_roi_align_plane_major_vs_reference(vb, oracle, dtype):
+    tv = pytest.importorskip("torchvision")
+    assert not vb.installed()
+    for shape, k, (ph, pw), scale, sr in [((2, 50, 30, 40), 500, (5, 5), 0.5, 2), ((1, 245, 40, 52), 1500, (7, 7), 0.25, 2),
+                                         ((1, 18, 64, 64), 64, (3, 3), 1.0, -1), ((2, 8, 20, 24), 3000, (2, 2), 0.5, 3)]:
+        b, c, h, w = shape
+        g = torch.Generator().manual_seed(k)
+        x = torch.randn(*shape, generator=g)
+        rois = _rois(k, b, h, w, scale, seed=k + 1)
+        xd, rd = x.to(dtype).to(DEV), rois.to(dtype).to(DEV)
+        o1, m1 = torch.ops.torchvision.ps_roi_align(xd, rd, scale, ph, pw, sr)
+        o2, m2 = torch.ops.vision_b200.ps_roi_align(xd, rd, scale, ph, pw, sr)
+        assert torch.equal(m1, m2)
+        # fp16: the reference rounds EVERY scalar op to half (coordinates included); we compute in fp32 from the same fp16
+        # inputs, so the comparison bound is the reference's own coordinate rounding (2^-11 of a coordinate ~ 50 px)
+        tol = dict(rtol=1e-5, atol=1e-5) if dtype != torch.float16 else dict(rtol=5e-2, atol=5e-2)
+        np.testing.assert_allclose(npy(o2), npy(o1), **tol)
+        if dtype == torch.float32:
+            want, wm = oracle.ps_roi_align(x.numpy(), rois.numpy(), (ph, pw), scale, sr)
+            assert np.array_equal(npy(o2), want) and np.array_equal(npy(m2), wm)       # bit-exact vs the CPU reference arithmetic
+
+
+# =============================== backward kernels (SURVEY §8f1) ===============================
+def _bwd_case(seed, b, c, h, w, k, small=False, scale=0.25):
+    g = torch.Generator().manual_seed(seed)
+    rois = _rois(k, b, h, w, scale, seed=seed + 7, small=small)
+    return g, rois
+
+
+@pytest.mark.parametrize("aligned", [False, True])
+@pytest.mark.parametrize("sr", [1, 2, 3])
+def test_roi_align_backward_plane_path_vs_reference_and_deterministic(vb, aligned, sr):
+    """fp32 plane-resident backward: close to the reference CUDA backward run in fp64 (ground truth), at least as close as
+    the reference's own fp32 atomics kernel, bit-identical between two runs, and equal (to rounding) to our atomic kernel."""
+    tv = pytest.importorskip("torchvision")
+    assert not vb.installed()
+    from test_gpu_parity import force_env
+    for (b, c, h, w, k, ph, pw, small) in [(2, 6, 50, 68, 700, 7, 7, False), (1, 3, 24, 30, 400, 7, 7, True), (1, 2, 40, 40, 300, 3, 20, False),
+                                           (3, 2, 9, 11, 100, 2, 2, False)]:
+        g, rois = _bwd_case(b * 100 + k + sr, b, c, h, w, k, small=small)
+        grad = torch.randn(k, c, ph, pw, generator=g) * 0.25
+        gd, rd = grad.to(DEV), rois.to(DEV)
+        args = (0.25, ph, pw, b, c, h, w, sr, aligned)
+        truth = torch.ops.torchvision._roi_align_backward(gd.double(), rd.double(), *args)
+        ref32 = torch.ops.torchvision._roi_align_backward(gd, rd, *args)
+        before = vb.launch_count()
+        ours = torch.ops.vision_b200._roi_align_backward(gd, rd, *args)
+        assert vb.launch_count() > before and ours.shape == (b, c, h, w) and ours.dtype == torch.float32
+        again = torch.ops.vision_b200._roi_align_backward(gd, rd, *args)
+        assert torch.equal(ours, again)                                        # deterministic
+        err = (ours.double() - truth).abs().max().item()
+        err_ref = (ref32.double() - truth).abs().max().item()
+        scale_ = truth.abs().max().item() + 1e-12
+        assert err <= 1e-5 * (1 + scale_), (err, err_ref, scale_)
+        np.testing.assert_allclose(npy(ours), truth.float().cpu().numpy(), rtol=1e-5, atol=1e-5 * max(1.0, scale_))
+        with force_env("VB200_ROI_BWD_PATH", "atomic"):
+            atom = torch.ops.vision_b200._roi_align_backward(gd, rd, *args)
+        np.testing.assert_allclose(npy(atom), truth.float().cpu().numpy(), rtol=1e-5, atol=1e-5 * max(1.0, scale_))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float16])
+def test_roi_align_backward_other_dtypes_and_adaptive_grid(vb, dtype):
+    tv = pytest.importorskip("torchvision")
+    assert not vb.installed()
+    b, c, h, w, k = 2, 4, 20, 26, 150
+    g, rois = _bwd_case(11, b, c, h, w, k)
+    grad = (torch.randn(k, c, 5, 5, generator=g) * 0.25).to(dtype).to(DEV)
+    rd = rois.to(dtype).to(DEV)
+    for sr in (2, -1):
+        args = (0.25, 5, 5, b, c, h, w, sr, False)
+        ref = torch.ops.torchvision._roi_align_backward(grad, rd, *args)
+        ours = torch.ops.vision_b200._roi_align_backward(grad, rd, *args)
+        tol = dict(rtol=1e-9, atol=1e-9) if dtype == torch.float64 else dict(rtol=3e-2, atol=3e-2)   # fp16 atomics round every add
+        np.testing.assert_allclose(npy(ours.double()), npy(ref.double()), **tol)
+    # fp32 adaptive grid takes the atomic kernel too
+    g32, r32 = grad.float(), rd.float()
+    args = (0.25, 5, 5, b, c, h, w, -1, True)
+    np.testing.assert_allclose(npy(torch.ops.vision_b200._roi_align_backward(g32, r32, *args)),
+                               npy(torch.ops.torchvision._roi_align_backward(g32.double(), r32.double(), *args).float()), rtol=1e-5, atol=1e-5)
+
+
+def test_roi_pool_and_ps_roi_align_backward_vs_reference(vb):
+    tv = pytest.importorskip("torchvision")
+    assert not vb.installed()
+    for (b, c, h, w, k, p) in [(2, 5, 40, 52, 600, 7), (1, 3, 16, 16, 900, 2), (1, 2, 300, 400, 50, 3)]:
+        g, rois = _bwd_case(k, b, c, h, w, k)
+        x = torch.randn(b, c, h, w, generator=g)
+        x[:, :, ::2, ::2] = 1.5                                        # ties: neighbouring bins share their argmax
+        xd, rd = x.to(DEV), rois.to(DEV)
+        out, am = torch.ops.torchvision.roi_pool(xd, rd, 0.25, p, p)
+        grad = torch.randn(out.shape, generator=g).to(DEV) * 0.25
+        args = (0.25, p, p, b, c, h, w)
+        truth = torch.ops.torchvision._roi_pool_backward(grad.double(), rd.double(), am, *args)
+        ours = torch.ops.vision_b200._roi_pool_backward(grad, rd, am, *args)
+        assert torch.equal(ours, torch.ops.vision_b200._roi_pool_backward(grad, rd, am, *args))
+        np.testing.assert_allclose(npy(ours), truth.float().cpu().numpy(), rtol=1e-5, atol=1e-5 * max(1.0, truth.abs().max().item()))
+    for (b, cout, h, w, k, p, sr) in [(2, 3, 30, 40, 500, 5, 2), (1, 2, 20, 20, 800, 3, 1), (1, 1, 300, 400, 40, 2, 2)]:
+        c = cout * p * p
+        g, rois = _bwd_case(k + p, b, c, h, w, k)
+        rd = rois.to(DEV)
+        xd = torch.randn(b, c, h, w, generator=g).to(DEV)
+        out, mapping = torch.ops.torchvision.ps_roi_align(xd, rd, 0.25, p, p, sr)
+        grad = torch.randn(out.shape, generator=g).to(DEV) * 0.25
+        args = (0.25, p, p, sr, b, c, h, w)
+        truth = torch.ops.torchvision._ps_roi_align_backward(grad.double(), rd.double(), mapping, *args)
+        ours = torch.ops.vision_b200._ps_roi_align_backward(grad, rd, mapping, *args)
+        assert torch.equal(ours, torch.ops.vision_b200._ps_roi_align_backward(grad, rd, mapping, *args))
+        np.testing.assert_allclose(npy(ours), truth.float().cpu().numpy(), rtol=1e-5, atol=1e-5 * max(1.0, truth.abs().max().item()))
+
+
+def test_autograd_through_both_api_surfaces(vb):
+    """(1) vision_b200.ops.* are differentiable (autograd formulas registered on the vision_b200:: ops);
+    (2) after install() torchvision.ops.roi_align(...).backward() runs OUR backward kernel (launch counter) and matches the
+    reference's gradient; gradcheck in fp64 mirrors test/test_ops.py:193-217."""
+    tv = pytest.importorskip("torchvision")
+    from torch.autograd import gradcheck
+    from vision_b200 import workloads
+
+    assert not vb.installed()
+    x, rois, kw = workloads.cfg2_roi_align(channels=16, k=300)
+    xd, rd = x.to(DEV), rois.to(DEV)
+    xr = xd.clone().requires_grad_(True)
+    tv.ops.roi_align(xr, rd, **kw).square().sum().backward()
+    ref_grad = xr.grad.clone()
+    xo = xd.clone().requires_grad_(True)
+    vb.ops.roi_align(xo, rd, **kw).square().sum().backward()
+    np.testing.assert_allclose(npy(xo.grad), npy(ref_grad), rtol=1e-4, atol=1e-4 * ref_grad.abs().max().item())
+    vb.install()
+    try:
+        xi = xd.clone().requires_grad_(True)
+        before = vb.launch_count()
+        out = tv.ops.roi_align(xi, rd, **kw)
+        mid = vb.launch_count()
+        out.square().sum().backward()
+        assert mid > before and vb.launch_count() > mid                       # forward AND backward ran on our kernels
+        np.testing.assert_allclose(npy(xi.grad), npy(ref_grad), rtol=1e-4, atol=1e-4 * ref_grad.abs().max().item())
+        for op, extra in ((tv.ops.roi_pool, {}), (tv.ops.ps_roi_align, dict(sampling_ratio=2))):
+            xp = torch.randn(1, 18, 20, 24, device=DEV, requires_grad=True)
+            r = torch.tensor([[0, 2.0, 3.0, 60.0, 50.0], [0, 10.0, 10.0, 30.0, 70.0]], device=DEV)
+            before = vb.launch_count()
+            op(xp, r, 3, 0.25, **extra).sum().backward()
+            assert vb.launch_count() >= before + 2 and xp.grad.abs().sum().item() > 0
+    finally:
+        vb.uninstall()
+    # gradcheck, fp64 (the reference's test shapes)
+    torch.manual_seed(0)
+    xg = torch.rand(1, 8, 5, 5, dtype=torch.float64, device=DEV, requires_grad=True)
+    r = torch.tensor([[0, 0, 0, 4, 4], [0, 0, 2, 3, 4], [0, 2, 2, 4, 4]], dtype=torch.float64, device=DEV)
+    assert gradcheck(lambda z: vb.ops.roi_align(z, r, 2, spatial_scale=1, sampling_ratio=1), (xg,), atol=1e-5)
+    assert gradcheck(lambda z: vb.ops.ps_roi_align(z, r, 2, spatial_scale=1, sampling_ratio=1), (xg,), atol=1e-5)
+    assert gradcheck(lambda z: vb.ops.roi_pool(z, r, 2, spatial_scale=1), (xg,), atol=1e-5)

@@ -71,6 +71,20 @@ def gpu_reference():
     o = tv.ops.roi_align(xg, rd, **kw); go = torch.randn_like(o)
     print("cfg2 roi_align backward (reference atomics) ms:", timed(lambda: torch.autograd.grad(o, xg, go, retain_graph=True), 10), flush=True)
     del xg, o, go
+    go = torch.randn(1000, 256, 7, 7, device=DEV)
+    t_ref = timed(lambda: torch.ops.torchvision._roi_align_backward(go, rd, 0.25, 7, 7, 1, 256, 200, 272, 2, False), 10)
+    t_our = timed(lambda: torch.ops.vision_b200._roi_align_backward(go, rd, 0.25, 7, 7, 1, 256, 200, 272, 2, False), 10)
+    print("cfg2 _roi_align_backward op ms: ref", t_ref, "ours (deterministic plane kernel)", t_our, flush=True)
+    o, am = torch.ops.torchvision.roi_pool(xd, rd, 0.25, 7, 7)
+    t_ref = timed(lambda: torch.ops.torchvision._roi_pool_backward(go, rd, am, 0.25, 7, 7, 1, 256, 200, 272), 10)
+    t_our = timed(lambda: torch.ops.vision_b200._roi_pool_backward(go, rd, am, 0.25, 7, 7, 1, 256, 200, 272), 10)
+    print("cfg2 _roi_pool_backward op ms: ref", t_ref, "ours", t_our, flush=True)
+    o, mp = torch.ops.torchvision.ps_roi_align(xp, rd, 0.25, 7, 7, 2)
+    gp = torch.randn_like(o)
+    t_ref = timed(lambda: torch.ops.torchvision._ps_roi_align_backward(gp, rd, mp, 0.25, 7, 7, 2, 1, 245, 200, 272), 10)
+    t_our = timed(lambda: torch.ops.vision_b200._ps_roi_align_backward(gp, rd, mp, 0.25, 7, 7, 2, 1, 245, 200, 272), 10)
+    print("_ps_roi_align_backward(245ch) op ms: ref", t_ref, "ours", t_our, flush=True)
+    del go, o, am, mp, gp
     # cfg3
     b, s, i = [t.to(DEV) for t in workloads.cfg3_batched_nms()]
     print("cfg3 batched_nms ms: ref", timed(lambda: tv.ops.batched_nms(b, s, i, 0.5), 5, 2), "ours", timed(lambda: vb.ops.batched_nms(b, s, i, 0.5), 20), flush=True)

@@ -1,0 +1,129 @@
+"""Autograd formulas and fake (meta) kernels of the ``vision_b200::`` ops.
+
+The reference registers these next to its kernels (torchvision/_meta_registrations.py,
+torchvision/_autograd_registrations.py:340-361 in the tree; C++ Autograd keys in the 0.26 wheel).  The ``torchvision::``
+ops keep the reference's registrations after install() - only their CUDA kernels (forward AND ``_*_backward``) are
+replaced - so this module only concerns direct users of ``vision_b200.ops``: without it a ``requires_grad`` input would
+silently produce a non-differentiable output.
+"""
+from __future__ import annotations
+
+import torch
+
+_done = False
+
+
+def register() -> None:
+    global _done
+    if _done:
+        return
+    _done = True
+    lib = torch.library
+    ops = torch.ops.vision_b200
+
+    # ---- roi_align ----
+    def roi_align_setup(ctx, inputs, output):
+        inp, rois, scale, ph, pw, sr, aligned = inputs
+        ctx.save_for_backward(rois)
+        ctx.in_shape = tuple(inp.shape)
+        ctx.args = (scale, ph, pw, sr, aligned)
+
+    def roi_align_backward(ctx, grad):
+        (rois,) = ctx.saved_tensors
+        scale, ph, pw, sr, aligned = ctx.args
+        b, c, h, w = ctx.in_shape
+        gi = ops._roi_align_backward(grad, rois, scale, ph, pw, b, c, h, w, sr, aligned)
+        return gi, None, None, None, None, None, None
+
+    lib.register_autograd("vision_b200::roi_align", roi_align_backward, setup_context=roi_align_setup)
+
+    @lib.register_fake("vision_b200::roi_align")
+    def _(inp, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio, aligned):
+        torch._check(rois.size(1) == 5, lambda: "rois must have shape as Tensor[K, 5]")
+        torch._check(inp.dtype == rois.dtype, lambda: "Expected tensor for input to have the same type as tensor for rois")
+        return inp.new_empty((rois.size(0), inp.size(1), pooled_height, pooled_width))
+
+    @lib.register_fake("vision_b200::_roi_align_backward")
+    def _(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width, sampling_ratio, aligned):
+        return grad.new_empty((batch_size, channels, height, width))
+
+    # ---- roi_pool ----
+    def roi_pool_setup(ctx, inputs, output):
+        inp, rois, scale, ph, pw = inputs
+        ctx.save_for_backward(rois, output[1])
+        ctx.mark_non_differentiable(output[1])
+        ctx.in_shape = tuple(inp.shape)
+        ctx.args = (scale, ph, pw)
+
+    def roi_pool_backward(ctx, grad, _grad_argmax):
+        rois, argmax = ctx.saved_tensors
+        scale, ph, pw = ctx.args
+        b, c, h, w = ctx.in_shape
+        gi = ops._roi_pool_backward(grad, rois, argmax, scale, ph, pw, b, c, h, w)
+        return gi, None, None, None, None
+
+    lib.register_autograd("vision_b200::roi_pool", roi_pool_backward, setup_context=roi_pool_setup)
+
+    @lib.register_fake("vision_b200::roi_pool")
+    def _(inp, rois, spatial_scale, pooled_height, pooled_width):
+        shape = (rois.size(0), inp.size(1), pooled_height, pooled_width)
+        return inp.new_empty(shape), inp.new_empty(shape, dtype=torch.int32)
+
+    @lib.register_fake("vision_b200::_roi_pool_backward")
+    def _(grad, rois, argmax, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width):
+        return grad.new_empty((batch_size, channels, height, width))
+
+    # ---- ps_roi_align ----
+    def ps_roi_align_setup(ctx, inputs, output):
+        inp, rois, scale, ph, pw, sr = inputs
+        ctx.save_for_backward(rois, output[1])
+        ctx.mark_non_differentiable(output[1])
+        ctx.in_shape = tuple(inp.shape)
+        ctx.args = (scale, ph, pw, sr)
+
+    def ps_roi_align_backward(ctx, grad, _grad_mapping):
+        rois, mapping = ctx.saved_tensors
+        scale, ph, pw, sr = ctx.args
+        b, c, h, w = ctx.in_shape
+        gi = ops._ps_roi_align_backward(grad, rois, mapping, scale, ph, pw, sr, b, c, h, w)
+        return gi, None, None, None, None, None
+
+    lib.register_autograd("vision_b200::ps_roi_align", ps_roi_align_backward, setup_context=ps_roi_align_setup)
+
+    @lib.register_fake("vision_b200::ps_roi_align")
+    def _(inp, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio):
+        torch._check(inp.size(1) % (pooled_height * pooled_width) == 0,
+                     lambda: "input channels must be a multiple of pooling height * pooling width")
+        shape = (rois.size(0), inp.size(1) // (pooled_height * pooled_width), pooled_height, pooled_width)
+        return inp.new_empty(shape), inp.new_empty(shape, dtype=torch.int32)
+
+    @lib.register_fake("vision_b200::_ps_roi_align_backward")
+    def _(grad, rois, channel_mapping, spatial_scale, pooled_height, pooled_width, sampling_ratio, batch_size, channels, height,
+          width):
+        return grad.new_empty((batch_size, channels, height, width))
+
+    # ---- nms / batched_nms: data-dependent output length ----
+    @lib.register_fake("vision_b200::nms")
+    def _(dets, scores, iou_threshold):
+        ctx = torch.library.get_ctx()
+        n = ctx.new_dynamic_size()
+        return dets.new_empty((n,), dtype=torch.int64)
+
+    @lib.register_fake("vision_b200::batched_nms")
+    def _(boxes, scores, idxs, iou_threshold):
+        ctx = torch.library.get_ctx()
+        n = ctx.new_dynamic_size()
+        return boxes.new_empty((n,), dtype=torch.int64)
+
+    # ---- resize ----
+    @lib.register_fake("vision_b200::resize")
+    def _(inp, out_h, out_w, mode, antialias):
+        return inp.new_empty(tuple(inp.shape[:-2]) + (out_h, out_w))
+
+    # ---- deform_conv2d ----
+    @lib.register_fake("vision_b200::deform_conv2d")
+    def _(inp, weight, offset, mask, bias, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups, offset_groups, use_mask):
+        kh, kw = weight.shape[-2:]
+        out_h = (inp.shape[2] + 2 * pad_h - (dil_h * (kh - 1) + 1)) // stride_h + 1
+        out_w = (inp.shape[3] + 2 * pad_w - (dil_w * (kw - 1) + 1)) // stride_w + 1
+        return inp.new_empty((inp.shape[0], weight.shape[0], out_h, out_w))

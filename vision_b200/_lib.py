@@ -40,7 +40,8 @@ def core() -> ctypes.CDLL:
             lib.vb200_launch_count.restype = ctypes.c_uint64
             lib.vb200_reload_env.restype = None
             for name in ("vb200_nms_workspace_bytes", "vb200_batched_nms_workspace_bytes",
-                         "vb200_roi_align_workspace_bytes", "vb200_deform_conv2d_workspace_bytes"):
+                         "vb200_roi_align_workspace_bytes", "vb200_deform_conv2d_workspace_bytes",
+                         "vb200_roi_backward_workspace_bytes"):
                 getattr(lib, name).restype = ctypes.c_size_t
             _core = lib
         return _core
@@ -59,6 +60,9 @@ def load_ops() -> None:
 
         torch.ops.load_library(SHIM_LIB)
         _shim_loaded = True
+    from . import _autograd
+
+    _autograd.register()      # autograd formulas + fake kernels of the vision_b200:: ops
 
 
 # every symbol include/vision_b200.h declares (checked by tests/test_abi.py)
@@ -68,4 +72,5 @@ ABI_SYMBOLS = (
     "vb200_ps_roi_align_forward", "vb200_nms_workspace_bytes", "vb200_nms",
     "vb200_batched_nms_workspace_bytes", "vb200_batched_nms", "vb200_deform_conv2d_workspace_bytes",
     "vb200_deform_conv2d_forward", "vb200_resize",
+    "vb200_roi_backward_workspace_bytes", "vb200_roi_align_backward", "vb200_roi_pool_backward", "vb200_ps_roi_align_backward",
 )

@@ -549,17 +549,23 @@ __device__ __forceinline__ void stage_plane_flat(T* __restrict__ dst, const T* _
 template <typename A>
 struct PoolGeom { int batch, rsw, rsh; A bh, bw; };
 
+// The reference kernel is instantiated on T, so for Half every scalar op of the box arithmetic (c10::Half operators:
+// computed in float, rounded to half) rounds to T.  rnd<T> is that rounding; identity for float / double.
+template <typename T> __device__ __forceinline__ typename Acc<T>::type rnd(typename Acc<T>::type v) { return v; }
+template <> __device__ __forceinline__ float rnd<__half>(float v) { return __half2float(__float2half_rn(v)); }
+
 template <typename T, typename A>
-__device__ __forceinline__ PoolGeom<A> pool_geometry(const T* __restrict__ r, A scale, int PH, int PW) {
+__device__ __forceinline__ PoolGeom<A> pool_geometry(const T* __restrict__ r, A scale_in, int PH, int PW) {
   PoolGeom<A> g;
+  const A scale = rnd<T>(scale_in);
   g.batch = (int)to_acc(r[0]);
-  g.rsw = (int)round(mul_rn((A)to_acc(r[1]), scale));
-  g.rsh = (int)round(mul_rn((A)to_acc(r[2]), scale));
-  const int rew = (int)round(mul_rn((A)to_acc(r[3]), scale));
-  const int reh = (int)round(mul_rn((A)to_acc(r[4]), scale));
+  g.rsw = (int)round(rnd<T>(mul_rn((A)to_acc(r[1]), scale)));
+  g.rsh = (int)round(rnd<T>(mul_rn((A)to_acc(r[2]), scale)));
+  const int rew = (int)round(rnd<T>(mul_rn((A)to_acc(r[3]), scale)));
+  const int reh = (int)round(rnd<T>(mul_rn((A)to_acc(r[4]), scale)));
   const int rw = max(rew - g.rsw + 1, 1), rh = max(reh - g.rsh + 1, 1);   // malformed RoIs become 1x1
-  g.bh = div_rn((A)rh, (A)PH);
-  g.bw = div_rn((A)rw, (A)PW);
+  g.bh = rnd<T>(div_rn(rnd<T>((A)rh), rnd<T>((A)PH)));
+  g.bw = rnd<T>(div_rn(rnd<T>((A)rw), rnd<T>((A)PW)));
   return g;
 }
 
@@ -604,14 +610,14 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
         const bool act = pw < PW && pw_l < 32 / Q;
         int ws = 0, we = 0;
         if (act) {
-          ws = (int)floor(mul_rn((A)pw, g.bw));
-          we = (int)ceil(mul_rn((A)(pw + 1), g.bw));
+          ws = (int)floor(rnd<T>(mul_rn(rnd<T>((A)pw), g.bw)));
+          we = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(pw + 1)), g.bw)));
           ws = min(max(ws + g.rsw, 0), W);
           we = min(max(we + g.rsw, 0), W);
         }
         for (int ph = 0; ph < PH; ++ph) {
-          int hs = (int)floor(mul_rn((A)ph, g.bh));
-          int he = (int)ceil(mul_rn((A)(ph + 1), g.bh));
+          int hs = (int)floor(rnd<T>(mul_rn(rnd<T>((A)ph), g.bh)));
+          int he = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(ph + 1)), g.bh)));
           hs = min(max(hs + g.rsh, 0), H);
           he = min(max(he + g.rsh, 0), H);
           A best = neg_max;

@@ -113,6 +113,73 @@ std::tuple<at::Tensor, at::Tensor> ps_roi_align(const at::Tensor& input, const a
   return std::make_tuple(out, mapping);
 }
 
+// ---- backward of the RoI ops (schemas: roi_align.cpp:76-77, roi_pool.cpp:69-70, ps_roi_align.cpp:76-77) ---------
+void check_bwd_inputs(const at::Tensor& grad, const at::Tensor& rois, const char* op) {
+  TORCH_CHECK(grad.is_cuda(), "grad must be a CUDA tensor");
+  TORCH_CHECK(rois.is_cuda(), "rois must be a CUDA tensor");
+  TORCH_CHECK(grad.get_device() == rois.get_device(), op, ": grad and rois must be on the same GPU");
+  TORCH_CHECK(grad.scalar_type() == rois.scalar_type(), op, ": expected grad and rois to have the same dtype");
+  TORCH_CHECK(rois.dim() == 2 && rois.size(1) == 5, "rois must have shape as Tensor[K, 5]");
+}
+
+at::Tensor roi_align_backward(const at::Tensor& grad, const at::Tensor& rois, double spatial_scale, int64_t pooled_height,
+                              int64_t pooled_width, int64_t batch_size, int64_t channels, int64_t height, int64_t width,
+                              int64_t sampling_ratio, bool aligned) {
+  check_bwd_inputs(grad, rois, "roi_align_backward");
+  at::cuda::CUDAGuard guard(grad.device());
+  // written in full by the kernel (plane by plane); the fallback path zero-fills itself
+  at::Tensor grad_input = at::empty({batch_size, channels, height, width}, grad.options());
+  if (grad_input.numel() == 0) return grad_input;
+  const int dt = dtype_code(grad.scalar_type(), "roi_align_backward");
+  at::Tensor g = grad.contiguous(), r = rois.contiguous();
+  const size_t wsb = vb200_roi_backward_workspace_bytes((int)r.size(0), (int)pooled_height, (int)pooled_width, (int)sampling_ratio);
+  at::Tensor ws = workspace(wsb, grad);
+  check_rc(vb200_roi_align_backward(g.data_ptr(), r.data_ptr(), grad_input.data_ptr(), dt, (int)batch_size, (int)channels,
+                                    (int)height, (int)width, (int)r.size(0), (int)pooled_height, (int)pooled_width, spatial_scale,
+                                    (int)sampling_ratio, aligned ? 1 : 0, wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+           "roi_align_backward");
+  return grad_input;
+}
+
+at::Tensor roi_pool_backward(const at::Tensor& grad, const at::Tensor& rois, const at::Tensor& argmax, double spatial_scale,
+                             int64_t pooled_height, int64_t pooled_width, int64_t batch_size, int64_t channels, int64_t height,
+                             int64_t width) {
+  check_bwd_inputs(grad, rois, "roi_pool_backward");
+  TORCH_CHECK(argmax.is_cuda() && argmax.scalar_type() == at::kInt, "argmax must be a CUDA int32 tensor");
+  at::cuda::CUDAGuard guard(grad.device());
+  at::Tensor grad_input = at::empty({batch_size, channels, height, width}, grad.options());
+  if (grad_input.numel() == 0) return grad_input;
+  const int dt = dtype_code(grad.scalar_type(), "roi_pool_backward");
+  at::Tensor g = grad.contiguous(), r = rois.contiguous(), am = argmax.contiguous();
+  const size_t wsb = vb200_roi_backward_workspace_bytes((int)r.size(0), (int)pooled_height, (int)pooled_width, 1);
+  at::Tensor ws = workspace(wsb, grad);
+  check_rc(vb200_roi_pool_backward(g.data_ptr(), r.data_ptr(), am.data_ptr<int32_t>(), grad_input.data_ptr(), dt, (int)batch_size,
+                                   (int)channels, (int)height, (int)width, (int)r.size(0), (int)pooled_height, (int)pooled_width,
+                                   spatial_scale, wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+           "roi_pool_backward");
+  return grad_input;
+}
+
+at::Tensor ps_roi_align_backward(const at::Tensor& grad, const at::Tensor& rois, const at::Tensor& channel_mapping,
+                                 double spatial_scale, int64_t pooled_height, int64_t pooled_width, int64_t sampling_ratio,
+                                 int64_t batch_size, int64_t channels, int64_t height, int64_t width) {
+  check_bwd_inputs(grad, rois, "ps_roi_align_backward");
+  TORCH_CHECK(channel_mapping.is_cuda(), "channel_mapping must be a CUDA tensor");
+  at::cuda::CUDAGuard guard(grad.device());
+  at::Tensor grad_input = at::empty({batch_size, channels, height, width}, grad.options());
+  if (grad_input.numel() == 0) return grad_input;
+  const int dt = dtype_code(grad.scalar_type(), "ps_roi_align_backward");
+  at::Tensor g = grad.contiguous(), r = rois.contiguous(), cm = channel_mapping.contiguous();
+  const size_t wsb = vb200_roi_backward_workspace_bytes((int)r.size(0), (int)pooled_height, (int)pooled_width, (int)sampling_ratio);
+  at::Tensor ws = workspace(wsb, grad);
+  check_rc(vb200_ps_roi_align_backward(g.data_ptr(), r.data_ptr(), cm.data_ptr<int32_t>(), grad_input.data_ptr(), dt, (int)batch_size,
+                                       (int)channels, (int)height, (int)width, (int)r.size(0), (int)pooled_height,
+                                       (int)pooled_width, spatial_scale, (int)sampling_ratio, wsb ? ws.data_ptr() : nullptr, wsb,
+                                       cur_stream()),
+           "ps_roi_align_backward");
+  return grad_input;
+}
+
 // ---- nms -------------------------------------------------------------------
 void check_nms_inputs(const at::Tensor& dets, const at::Tensor& scores) {
   TORCH_CHECK(dets.is_cuda(), "dets must be a CUDA tensor");
@@ -284,6 +351,9 @@ void install(bool on) {
   lib->impl("roi_pool", TORCH_FN(roi_pool));
   lib->impl("ps_roi_align", TORCH_FN(ps_roi_align));
   lib->impl("deform_conv2d", TORCH_FN(deform_conv2d));
+  lib->impl("_roi_align_backward", TORCH_FN(roi_align_backward));
+  lib->impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
+  lib->impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
   g_override = std::move(lib);
 }
 bool installed() { return (bool)g_override; }
@@ -305,6 +375,9 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("ps_roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio) -> (Tensor, Tensor)");
   m.def("deform_conv2d(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> Tensor");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
+  m.def("_roi_align_backward(Tensor grad, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width, int sampling_ratio, bool aligned) -> Tensor");
+  m.def("_roi_pool_backward(Tensor grad, Tensor rois, Tensor argmax, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
+  m.def("_ps_roi_align_backward(Tensor grad, Tensor rois, Tensor channel_mapping, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
   m.def("_install(bool on) -> ()", &install);
   m.def("_installed() -> bool", &installed);
   m.def("_set_nms_semantics(int s) -> ()", &set_nms_semantics);
@@ -321,4 +394,7 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("ps_roi_align", TORCH_FN(ps_roi_align));
   m.impl("deform_conv2d", TORCH_FN(deform_conv2d));
   m.impl("resize", TORCH_FN(resize));
+  m.impl("_roi_align_backward", TORCH_FN(roi_align_backward));
+  m.impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
+  m.impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
 }
