@@ -100,7 +100,15 @@ def _worker(rank, world, port, q):
         res = sh.sharded_batched_nms(fake, probs, 0.5, capacity=64)
         ok2 = len(res) == world and all(
             torch.equal(res[r][j], torch.arange(0, 5 + r + j, 2, dtype=torch.int64)) for r in range(world) for j in range(2))
-        q.put((rank, ok1, ok2))
+        # chunked gather (the overlapped path; no side stream on CPU): rank-major result, lazily packed
+        og = sh.OverlappedGather()
+        mine = imgs[s:e]
+        lazy = sh.sharded_apply_overlapped(lambda t: t * 2, mine, chunks=3, gather=og)
+        ok3 = tuple(lazy.shape) == tuple(imgs.shape) and torch.equal(lazy.materialize(), imgs * 2) and \
+            torch.equal(lazy.rank(1 - rank).flatten(0, 1), (imgs * 2)[(1 - rank) * 3:(2 - rank) * 3])
+        one = sh.sharded_apply_overlapped(lambda t: t + 1, mine, chunks=1, gather=og)
+        ok3 = ok3 and torch.equal(one, imgs + 1)
+        q.put((rank, ok1, ok2 and ok3))
     finally:
         dist.destroy_process_group()
 

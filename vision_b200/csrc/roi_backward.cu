@@ -213,6 +213,98 @@ roi_align_bwd_plane_kernel(const float* __restrict__ grad, const BwdHdr* __restr
   }
 }
 
+// Same algorithm for the common shapes (PH*sr <= 32 y samples, 2*PW*sr <= 32 x taps, PH*PW <= 64 bins - e.g. 7x7 bins with
+// sampling_ratio 2): a hit needs one table load per lane and two coalesced loads of the RoI's bin gradients, all
+// independent of each other, so they are issued for hit i+1 BEFORE hit i is processed (the general kernel above chains
+// three L2 round trips per hit and is latency-bound); the bin gradient of a (sample, tap) pair is then a shuffle.
+struct HitLoads { uint2 yy, e; float gA, gB; };
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+roi_align_bwd_plane_fast_kernel(const float* __restrict__ grad, const BwdHdr* __restrict__ hdr, const uint2* __restrict__ ys,
+                                const uint2* __restrict__ xe, float* __restrict__ grad_input, int B, int C, int H, int W, int K,
+                                int PH, int PW, int sr, int band) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NYS = PH * sr, NXE = 2 * PW * sr, NB = PH * PW;
+  const float inv_count = 1.0f / (float)(sr * sr);
+  const bool pow2 = (sr & (sr - 1)) == 0;
+  const float count = (float)(sr * sr);
+  const unsigned sr_recip = (65536u + (unsigned)sr - 1u) / (unsigned)sr;      // j / sr == (j * sr_recip) >> 16 for j < 32, sr <= 32
+  const int r0 = warp * band, r1 = min(H, r0 + band);
+  const int4* __restrict__ hdr4 = reinterpret_cast<const int4*>(hdr);
+  for (int pl = blockIdx.x; pl < B * C; pl += gridDim.x) {
+    const int b = pl / C, c = pl - b * C;
+    {
+      float4* p4 = reinterpret_cast<float4*>(plane);
+      const int n4 = (H * W + 3) >> 2;
+      for (int i = tid; i < n4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (r0 < H) {
+      auto issue = [&](HitLoads& L, int n) {
+        const float* __restrict__ g = grad + ((int64_t)n * C + c) * NB;
+        L.yy = lane < NYS ? __ldg(ys + (int64_t)n * NYS + lane) : make_uint2(0xffffffffu, 0u);
+        L.e = lane < NXE ? __ldg(xe + (int64_t)n * NXE + lane) : make_uint2(0xffffffffu, 0u);
+        L.gA = lane < NB ? __ldg(g + lane) : 0.f;
+        L.gB = lane + 32 < NB ? __ldg(g + 32 + lane) : 0.f;
+      };
+      int4 hnext = make_int4(-1, 0, -1, 0);
+      if (lane < K) hnext = __ldg(hdr4 + lane);
+      for (int n0 = 0; n0 < K; n0 += 32) {
+        const int4 h = hnext;
+        hnext = make_int4(-1, 0, -1, 0);
+        if (n0 + 32 + lane < K) hnext = __ldg(hdr4 + n0 + 32 + lane);           // next chunk's headers travel under this chunk's hits
+        const bool hit = (n0 + lane < K) && h.x == b && h.y < r1 && h.z >= r0;
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        HitLoads cur, nxt;
+        if (m) issue(cur, n0 + __ffs(m) - 1);
+        while (m) {
+          const int i = __ffs(m) - 1;
+          m &= m - 1;
+          if (m) issue(nxt, n0 + __ffs(m) - 1);
+          const int flags = __shfl_sync(0xffffffffu, h.w, i);
+          const int lo = (int)cur.yy.x;
+          const float l = __uint_as_float(cur.yy.y);
+          const bool inb = lo >= 0 && lo < r1 && (lo + (l > 0.f ? 1 : 0)) >= r0;
+          unsigned mm = __ballot_sync(0xffffffffu, inb);
+          const bool valid = cur.e.x != 0xffffffffu;
+          const int col = (int)(cur.e.x & 0xffffu), pw = (int)(cur.e.x >> 16);
+          const float wx = __uint_as_float(cur.e.y);
+          bool leader = valid;
+          unsigned group = 0u;
+          if (flags & 1) {
+            const unsigned same = __match_any_sync(0xffffffffu, valid ? col : 0x10000 + lane);
+            group = valid ? same : 0u;
+            leader = valid && (__ffs(same) - 1 == lane);
+          }
+          while (mm) {
+            const int j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const int lo_j = __shfl_sync(0xffffffffu, lo, j);
+            const float l_j = __shfl_sync(0xffffffffu, l, j);
+            const int ph = (int)(((unsigned)j * sr_recip) >> 16);
+            const int t = valid ? ph * PW + pw : 0;
+            const float ga = __shfl_sync(0xffffffffu, cur.gA, t & 31), gb = __shfl_sync(0xffffffffu, cur.gB, t & 31);
+            float gv = t < 32 ? ga : gb;
+            gv = pow2 ? gv * inv_count : __fdiv_rn(gv, count);
+            float a = wx * gv;
+            if (flags & 1) a = ordered_group_sum(a, group);
+            if (leader) {
+              if (lo_j >= r0) plane[lo_j * W + col] += (1.f - l_j) * a;
+              if (l_j > 0.f && lo_j + 1 >= r0 && lo_j + 1 < r1) plane[(lo_j + 1) * W + col] += l_j * a;
+            }
+          }
+          cur = nxt;
+        }
+      }
+    }
+    __syncthreads();
+    store_plane(grad_input + (int64_t)pl * H * W, plane, H * W);
+    __syncthreads();
+  }
+}
+
 // ---- roi_pool backward, plane-resident -----------------------------------------------------------------------
 // Rows that can hold an argmax of RoI n: [clamp(rsh), clamp(reh + 1)) (roi_pool_kernel.cu:43-58).
 __global__ void roi_pool_bwd_hdr_kernel(const float* __restrict__ rois, BwdHdr* __restrict__ hdr, int K, int H, float scale) {
@@ -523,11 +615,19 @@ extern "C" int vb200_roi_align_backward(const void* grad, const void* rois, void
     int rc = check_launch("roi_bwd_geometry_kernel");
     if (rc) return rc;
     const size_t smem = (((size_t)height * width + 3) & ~(size_t)3) * 4;
-    VB200_CUDA_TRY(ensure_dyn_smem<roi_align_bwd_plane_kernel>(smem));
     const int planes = batch * channels;
-    roi_align_bwd_plane_kernel<<<planes < sm_count() ? planes : sm_count(), kBwdThreads, smem, st>>>(
-        (const float*)grad, ws.hdr, ws.ys, ws.xe, (float*)grad_input, batch, channels, height, width, num_rois, pooled_h, pooled_w,
-        sampling_ratio, bwd_band(height));
+    const int grid = planes < sm_count() ? planes : sm_count();
+    if (pooled_h * sampling_ratio <= 32 && 2 * pooled_w * sampling_ratio <= 32 && pooled_h * pooled_w <= 64) {
+      VB200_CUDA_TRY(ensure_dyn_smem<roi_align_bwd_plane_fast_kernel>(smem));
+      roi_align_bwd_plane_fast_kernel<<<grid, kBwdThreads, smem, st>>>((const float*)grad, ws.hdr, ws.ys, ws.xe, (float*)grad_input,
+                                                                      batch, channels, height, width, num_rois, pooled_h, pooled_w,
+                                                                      sampling_ratio, bwd_band(height));
+      return check_launch("roi_align_bwd_plane_fast_kernel");
+    }
+    VB200_CUDA_TRY(ensure_dyn_smem<roi_align_bwd_plane_kernel>(smem));
+    roi_align_bwd_plane_kernel<<<grid, kBwdThreads, smem, st>>>((const float*)grad, ws.hdr, ws.ys, ws.xe, (float*)grad_input, batch,
+                                                               channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio,
+                                                               bwd_band(height));
     return check_launch("roi_align_bwd_plane_kernel");
   }
   VB200_CUDA_TRY(cudaMemsetAsync(grad_input, 0, (size_t)in_elems * esize, st));
@@ -545,8 +645,8 @@ extern "C" int vb200_roi_align_backward(const void* grad, const void* rois, void
 
 extern "C" int vb200_ps_roi_align_backward(const void* grad, const void* rois, const int32_t* channel_mapping, void* grad_input,
                                            int dtype, int batch, int channels, int height, int width, int num_rois, int pooled_h,
-                                           int pooled_w, double spatial_scale, int sampling_ratio, void* workspace,
-                                           size_t workspace_bytes, vb200_stream stream) {
+                                           int pooled_w, double spatial_scale, int sampling_ratio, int deterministic,
+                                           void* workspace, size_t workspace_bytes, vb200_stream stream) {
   (void)channel_mapping;   // c_in = (c_out * PH + ph) * PW + pw by construction (ps_roi_align_kernel.cu:95); not re-read
   VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "ps_roi_align_backward: pooled size must be positive");
   VB200_REQUIRE(batch >= 0 && channels >= 0 && height >= 0 && width >= 0 && num_rois >= 0, "ps_roi_align_backward: negative size");
@@ -561,7 +661,10 @@ extern "C" int vb200_ps_roi_align_backward(const void* grad, const void* rois, c
   if (num_rois == 0 || Cout == 0) { VB200_CUDA_TRY(cudaMemsetAsync(grad_input, 0, (size_t)in_elems * esize, st)); return 0; }
   VB200_REQUIRE(grad && rois, "ps_roi_align_backward: null pointer");
   const BwdWs ws = carve_bwd(workspace, num_rois, pooled_h, pooled_w, sampling_ratio);
-  if (bwd_plane_ok(dtype, height, width, pooled_h, pooled_w, sampling_ratio, true) && workspace && workspace_bytes >= ws.total) {
+  // One bin per (RoI, plane): the atomic scatter is the faster kernel here (sr*sr*4 atomics per output); the plane kernel is
+  // the bit-reproducible one and runs when the caller asks for determinism.
+  if (deterministic && bwd_plane_ok(dtype, height, width, pooled_h, pooled_w, sampling_ratio, true) && workspace &&
+      workspace_bytes >= ws.total) {
     roi_bwd_geometry_kernel<<<ceil_div(num_rois * 32, 256), 256, 0, st>>>((const float*)rois, ws.hdr, ws.ys, ws.xe, num_rois, height,
                                                                            width, pooled_h, pooled_w, sampling_ratio,
                                                                            (float)spatial_scale, 1, 1);
@@ -594,7 +697,8 @@ extern "C" int vb200_ps_roi_align_backward(const void* grad, const void* rois, c
 
 extern "C" int vb200_roi_pool_backward(const void* grad, const void* rois, const int32_t* argmax, void* grad_input, int dtype,
                                        int batch, int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
-                                       double spatial_scale, void* workspace, size_t workspace_bytes, vb200_stream stream) {
+                                       double spatial_scale, int deterministic, void* workspace, size_t workspace_bytes,
+                                       vb200_stream stream) {
   VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "roi_pool_backward: pooled size must be positive");
   VB200_REQUIRE(batch >= 0 && channels >= 0 && height >= 0 && width >= 0 && num_rois >= 0, "roi_pool_backward: negative size");
   cudaStream_t st = (cudaStream_t)stream;
@@ -607,7 +711,8 @@ extern "C" int vb200_roi_pool_backward(const void* grad, const void* rois, const
   if (num_rois == 0) { VB200_CUDA_TRY(cudaMemsetAsync(grad_input, 0, (size_t)in_elems * esize, st)); return 0; }
   VB200_REQUIRE(grad && rois && argmax, "roi_pool_backward: null pointer");
   const BwdWs ws = carve_bwd(workspace, num_rois, pooled_h, pooled_w, 1);
-  if (bwd_plane_ok(dtype, height, width, pooled_h, pooled_w, 1, false) && workspace && workspace_bytes >= ws.total) {
+  // one atomic per output element is hard to beat; the plane kernel is the bit-reproducible alternative
+  if (deterministic && bwd_plane_ok(dtype, height, width, pooled_h, pooled_w, 1, false) && workspace && workspace_bytes >= ws.total) {
     roi_pool_bwd_hdr_kernel<<<ceil_div(num_rois, 256), 256, 0, st>>>((const float*)rois, ws.hdr, num_rois, height, (float)spatial_scale);
     int rc = check_launch("roi_pool_bwd_hdr_kernel");
     if (rc) return rc;

@@ -11,6 +11,7 @@
 // Tensors are plumbing only: device memory, current stream, allocator.  All checks and error
 // strings follow the reference's host functions so its tests read the same.
 #include <ATen/ATen.h>
+#include <ATen/Context.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
@@ -155,7 +156,8 @@ at::Tensor roi_pool_backward(const at::Tensor& grad, const at::Tensor& rois, con
   at::Tensor ws = workspace(wsb, grad);
   check_rc(vb200_roi_pool_backward(g.data_ptr(), r.data_ptr(), am.data_ptr<int32_t>(), grad_input.data_ptr(), dt, (int)batch_size,
                                    (int)channels, (int)height, (int)width, (int)r.size(0), (int)pooled_height, (int)pooled_width,
-                                   spatial_scale, wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+                                   spatial_scale, at::globalContext().deterministicAlgorithms() ? 1 : 0,
+                                   wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
            "roi_pool_backward");
   return grad_input;
 }
@@ -174,7 +176,8 @@ at::Tensor ps_roi_align_backward(const at::Tensor& grad, const at::Tensor& rois,
   at::Tensor ws = workspace(wsb, grad);
   check_rc(vb200_ps_roi_align_backward(g.data_ptr(), r.data_ptr(), cm.data_ptr<int32_t>(), grad_input.data_ptr(), dt, (int)batch_size,
                                        (int)channels, (int)height, (int)width, (int)r.size(0), (int)pooled_height,
-                                       (int)pooled_width, spatial_scale, (int)sampling_ratio, wsb ? ws.data_ptr() : nullptr, wsb,
+                                       (int)pooled_width, spatial_scale, (int)sampling_ratio,
+                                       at::globalContext().deterministicAlgorithms() ? 1 : 0, wsb ? ws.data_ptr() : nullptr, wsb,
                                        cur_stream()),
            "ps_roi_align_backward");
   return grad_input;
@@ -224,6 +227,32 @@ at::Tensor nms(const at::Tensor& dets, const at::Tensor& scores, double iou_thre
   return keep.narrow(0, 0, k);
 }
 
+// Device-side result of batched_nms: keep [n] (first *count entries valid, the rest unspecified) and count [1], both on
+// the device - no host synchronisation.  The sharded path gathers these padded lists with one collective.
+std::tuple<at::Tensor, at::Tensor> batched_nms_padded(const at::Tensor& dets, const at::Tensor& scores, const at::Tensor& idxs,
+                                                      double iou_threshold) {
+  check_nms_inputs(dets, scores);
+  TORCH_CHECK(idxs.is_cuda(), "idxs must be a CUDA tensor");
+  TORCH_CHECK(idxs.dim() == 1 && idxs.size(0) == dets.size(0), "idxs should be a 1d tensor with one entry per box");
+  at::cuda::CUDAGuard guard(dets.device());
+  const int64_t n = dets.size(0);
+  at::Tensor keep = at::empty({n}, dets.options().dtype(at::kLong));
+  at::Tensor count = at::zeros({1}, dets.options().dtype(at::kLong));
+  if (dets.numel() == 0) return std::make_tuple(keep, count);
+  TORCH_CHECK(dets.scalar_type() == scores.scalar_type(), "boxes should have the same type as scores");
+  const int dt = nms_dtype(dets, "batched_nms");
+  at::Tensor boxes = nms_operand(dets, 4 * dets.element_size()), sc = nms_operand(scores, scores.element_size());
+  at::Tensor cls = idxs.to(at::kLong).contiguous();
+  const size_t wsb = vb200_batched_nms_workspace_bytes(n);
+  at::Tensor ws = workspace(wsb, boxes);
+  // class ids are sorted as 16-bit keys (the common case); ids outside [0, 65536) make the kernel report count = -1
+  check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), dt, n, iou_threshold,
+                             dt == VB200_F16 ? VB200_NMS_CUDA : g_nms_semantics.load(), VB200_BNMS_AUTO, ws.data_ptr(), wsb,
+                             keep.data_ptr<int64_t>(), count.data_ptr<int64_t>(), cur_stream()),
+           "batched_nms");
+  return std::make_tuple(keep, count);
+}
+
 at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const at::Tensor& idxs, double iou_threshold) {
   check_nms_inputs(dets, scores);
   TORCH_CHECK(idxs.is_cuda(), "idxs must be a CUDA tensor");
@@ -244,8 +273,8 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
     // first attempt speculates 16-bit class ids; -1 asks for the wide-key repeat (arbitrary int64 ids)
     const int strategy = VB200_BNMS_AUTO | (attempt ? VB200_BNMS_WIDE_KEYS : 0);
     check_rc(vb200_batched_nms(boxes.data_ptr(), sc.data_ptr(), cls.data_ptr<int64_t>(), dt, n, iou_threshold,
-                               dt == VB200_F16 ? VB200_NMS_CUDA : g_nms_semantics.load(), strategy, ws.data_ptr(), wsb, keep.data_ptr<int64_t>(),
-                               count.data_ptr<int64_t>(), cur_stream()),
+                               dt == VB200_F16 ? VB200_NMS_CUDA : g_nms_semantics.load(), strategy, ws.data_ptr(), wsb,
+                               keep.data_ptr<int64_t>(), count.data_ptr<int64_t>(), cur_stream()),
              "batched_nms");
     k = count.item<int64_t>();
   }
@@ -370,6 +399,7 @@ int64_t abi_version() { return vb200_abi_version(); }
 TORCH_LIBRARY(vision_b200, m) {
   m.def("nms(Tensor dets, Tensor scores, float iou_threshold) -> Tensor");
   m.def("batched_nms(Tensor boxes, Tensor scores, Tensor idxs, float iou_threshold) -> Tensor");
+  m.def("batched_nms_padded(Tensor boxes, Tensor scores, Tensor idxs, float iou_threshold) -> (Tensor, Tensor)");
   m.def("roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio, bool aligned) -> Tensor");
   m.def("roi_pool(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width) -> (Tensor, Tensor)");
   m.def("ps_roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio) -> (Tensor, Tensor)");
@@ -389,6 +419,7 @@ TORCH_LIBRARY(vision_b200, m) {
 TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("nms", TORCH_FN(nms));
   m.impl("batched_nms", TORCH_FN(batched_nms));
+  m.impl("batched_nms_padded", TORCH_FN(batched_nms_padded));
   m.impl("roi_align", TORCH_FN(roi_align));
   m.impl("roi_pool", TORCH_FN(roi_pool));
   m.impl("ps_roi_align", TORCH_FN(ps_roi_align));

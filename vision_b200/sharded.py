@@ -1,10 +1,17 @@
 """Multi-GPU: the hot path shards on the batch / image dimension.
 
-One process per GPU (torchrun), each rank runs the op on its own images, then EXACTLY ONE
-collective: an all-gather of the per-shard outputs over NCCL (NVLink 5 / NVSwitch).  No reduce, no
-all-to-all, nothing else.  Equal-size outputs (resize, roi_align, roi_pool, ps_roi_align,
-deform_conv2d) use all_gather_into_tensor directly; NMS keep-lists (data-dependent length) are
-padded to a static capacity with their length in slot 0, so it is still a single all-gather.
+One process per GPU (torchrun), each rank runs the op on its own images, and the per-shard outputs are exchanged with
+an all-gather over NCCL (NVLink 5 / NVSwitch) - no reduce, no all-to-all, nothing else.
+
+* ``all_gather_equal``  - one ``all_gather_into_tensor`` of equal-shaped outputs.
+* ``sharded_apply_overlapped`` - the same exchange hidden behind the compute: the shard is cut into chunks along dim 0,
+  chunk i is computed on the compute stream and its all-gather is issued on a side stream as soon as the chunk is
+  ready, so chunk i's transfer runs under chunk i+1's kernel (NVSwitch gives every GPU full bandwidth to every peer,
+  so the gather of a chunk costs about (world-1)/world * bytes / 0.9 TB/s and is hidden when the kernel takes longer).
+  The gathered result is returned as a VIEW ``[world * n, ...]`` over a ``[chunks, world, chunk, ...]`` buffer (no
+  re-packing pass).
+* NMS keep-lists (data-dependent length) travel padded, with their length in front, so each image is one fixed-size
+  message; ``sharded_batched_nms`` runs all local images without a host synchronisation and gathers once.
 
 The helpers are backend-agnostic (nccl on GPUs; gloo in the CPU tests of the plumbing).
 """
@@ -29,18 +36,24 @@ def _world(group=None) -> tuple[int, int]:
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+def _gather_into(out: torch.Tensor, local: torch.Tensor, group=None) -> None:
+    """out [world, *local.shape] <- every rank's `local` (one collective)."""
+    world = out.shape[0]
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, local, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), local, group=group)
+
+
 def all_gather_equal(local: torch.Tensor, group=None) -> torch.Tensor:
     """All ranks hold the same shape: returns cat over ranks along dim 0 (one collective)."""
     rank, world = _world(group)
     if world == 1:
         return local
     local = local.contiguous()
-    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    if dist.get_backend(group) == "nccl":
-        dist.all_gather_into_tensor(out, local, group=group)
-    else:
-        dist.all_gather(list(out.chunk(world, dim=0)), local, group=group)
-    return out
+    out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+    _gather_into(out, local, group)
+    return out.reshape((world * local.shape[0],) + tuple(local.shape[1:]))
 
 
 def all_gather_varlen(local: torch.Tensor, capacity: int, group=None) -> list[torch.Tensor]:
@@ -61,6 +74,100 @@ def all_gather_varlen(local: torch.Tensor, capacity: int, group=None) -> list[to
 def sharded_apply(fn: Callable[..., torch.Tensor], local_inputs: Sequence, group=None) -> torch.Tensor:
     """Run `fn(*local_inputs)` on this rank's shard and all-gather the equal-shaped outputs."""
     return all_gather_equal(fn(*local_inputs), group=group)
+
+
+class OverlappedGather:
+    """Chunked all-gather on a side stream (see module docstring).  Reusable: buffers and the side stream persist."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank, self.world = _world(group)
+        self._stream: Optional[torch.cuda.Stream] = None
+        self._buf: Optional[torch.Tensor] = None
+
+    def _side(self, device) -> Optional["torch.cuda.Stream"]:
+        if device.type != "cuda":
+            return None
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=device)
+        return self._stream
+
+    def run(self, chunk_fn: Callable[[int], torch.Tensor], chunks: int) -> torch.Tensor:
+        """chunk_fn(i) -> this rank's output for chunk i (all chunks and all ranks: same shape).  Returns the gathered
+        result as a [world * chunks * m, ...] view in rank-major order (rank r's rows are contiguous in the view)."""
+        world = self.world
+        if world == 1:
+            outs = [chunk_fn(i) for i in range(chunks)]
+            return outs[0] if chunks == 1 else torch.cat(outs, dim=0)
+        first = chunk_fn(0)
+        dev = first.device
+        shape = (chunks, world) + tuple(first.shape)
+        if self._buf is None or tuple(self._buf.shape) != shape or self._buf.dtype != first.dtype or self._buf.device != dev:
+            self._buf = torch.empty(shape, dtype=first.dtype, device=dev)
+        buf = self._buf
+        side = self._side(dev)
+        cur = first
+        for i in range(chunks):
+            local = cur.contiguous()
+            if side is not None:
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    local.record_stream(side)
+                    _gather_into(buf[i], local, self.group)
+            else:
+                _gather_into(buf[i], local, self.group)
+            if i + 1 < chunks:
+                cur = chunk_fn(i + 1)          # runs on the compute stream while chunk i travels
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+        return _rank_major_view(buf)
+
+
+def _rank_major_view(buf: torch.Tensor) -> torch.Tensor:
+    """[chunks, world, m, ...] -> rank-major [world, chunks * m, ...] without copying when chunks == 1; otherwise a
+    permuted (non-contiguous) view that indexes like the concatenation over ranks of each rank's chunks in order."""
+    chunks, world, m = buf.shape[:3]
+    v = buf.transpose(0, 1)                                  # [world, chunks, m, ...], strided
+    return v.reshape((world * chunks * m,) + tuple(buf.shape[3:])) if chunks == 1 else _LazyCat(v)
+
+
+class _LazyCat:
+    """Rank-major result of a chunked gather: behaves like the [world * chunks * m, ...] tensor for the common
+    consumers (``shape``, ``__getitem__`` of a rank slice, ``contiguous()``, ``materialize()``) without paying the
+    re-packing pass unless the caller asks for one contiguous tensor."""
+
+    def __init__(self, v: torch.Tensor):
+        self.v = v                                            # [world, chunks, m, ...]
+        w, c, m = v.shape[:3]
+        self.shape = torch.Size((w * c * m,) + tuple(v.shape[3:]))
+        self.dtype, self.device = v.dtype, v.device
+
+    def rank(self, r: int) -> torch.Tensor:
+        """Rank r's output as a [chunks, m, ...] view (each chunk contiguous)."""
+        return self.v[r]
+
+    def materialize(self) -> torch.Tensor:
+        return self.v.reshape(self.shape)                     # one packing copy
+
+    contiguous = materialize
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+
+def sharded_apply_overlapped(fn: Callable[[torch.Tensor], torch.Tensor], local: torch.Tensor, chunks: int = 4,
+                             gather: Optional[OverlappedGather] = None, group=None):
+    """fn over `local` (split along dim 0 into `chunks` equal parts) with the all-gather of each part's output hidden
+    behind the next part's kernel.  Returns a tensor (world == 1 or chunks == 1) or a `_LazyCat` rank-major view."""
+    n = local.shape[0]
+    chunks = max(1, min(chunks, n))
+    while n % chunks:
+        chunks -= 1
+    step = n // chunks
+    g = gather or OverlappedGather(group)
+    return g.run(lambda i: fn(local[i * step:(i + 1) * step]), chunks)
 
 
 def sharded_batched_nms(fn: Callable[..., torch.Tensor], problems: Sequence[tuple], iou_threshold: float,
@@ -87,3 +194,27 @@ def sharded_batched_nms(fn: Callable[..., torch.Tensor], problems: Sequence[tupl
             pos += 1 + n
         out.append(lst)
     return out
+
+
+def sharded_batched_nms_padded(problems: Sequence[tuple], iou_threshold: float, group=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Device-resident variant for equally sized images (n boxes each): runs ``vision_b200::batched_nms_padded`` on every
+    local image WITHOUT a host synchronisation, then ONE all-gather of the padded keep lists (count in front of each).
+    Returns (keep [world, images, n] int64, count [world, images] int64); keep[r, j, :count[r, j]] are image j of rank r's
+    kept indices in descending-score order."""
+    from . import _lib
+
+    _lib.load_ops()
+    rank, world = _world(group)
+    keeps, counts = [], []
+    for (b, s, i) in problems:
+        k, c = torch.ops.vision_b200.batched_nms_padded(b, s, i, float(iou_threshold))
+        keeps.append(k)
+        counts.append(c)
+    keep = torch.stack(keeps)                                  # [images, n]
+    count = torch.cat(counts)                                  # [images]
+    if world == 1:
+        return keep.unsqueeze(0), count.unsqueeze(0)
+    packed = torch.cat([count.unsqueeze(1), keep], dim=1)      # [images, 1 + n]: one fixed-size message per image
+    g = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    _gather_into(g, packed, group)
+    return g[:, :, 1:], g[:, :, 0]
