@@ -555,7 +555,6 @@ def main():
     ctx.barrier()
     wall = time.perf_counter() - wall0
     launches = vb.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ctx.max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) / args.steps
 
     # ---- end to end: pinned host buffers; EVERY step copies its inputs H2D and its result D2H ----
@@ -588,6 +587,8 @@ def main():
             configs[name] = {"error": repr(ex)[:400]}
         ctx.barrier()
 
+    # sampled from the first headline step to the end of the last block (the headline region alone lasts ~10 ms)
+    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         peak, peak_src = peaks()
         achieved = ALG_BYTES / (ms_per_step / 1e3) / 1e9     # per GPU (every rank runs the same kernel on its own image)

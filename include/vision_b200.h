@@ -118,16 +118,18 @@ VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, vo
  * grad [num_rois, C_out, pooled_h, pooled_w] DENSE (the shim makes it contiguous), rois [num_rois, 5],
  * grad_input [batch, channels, height, width] - written IN FULL (no pre-zeroing).  Unlike the reference (atomics,
  * alertNotDeterministic) the fp32 / fixed-sampling-grid path is bit-reproducible: every grad_input plane is
- * accumulated in shared memory by row-owning warps in a fixed order.  roi_align always takes it (it is also the faster
- * kernel there); roi_pool / ps_roi_align scatter one bin per (RoI, plane), where atomics win, so they take it only when
- * `deterministic` != 0 (the shim passes torch.are_deterministic_algorithms_enabled()).  Other dtypes (F16, F64),
+ * accumulated in shared memory by row-owning warps in a fixed order.  That path runs when `deterministic` != 0 (the shim
+ * passes torch.are_deterministic_algorithms_enabled(); the reference raises in that mode).  With `deterministic` == 0
+ * roi_align still accumulates plane by plane in shared memory, but with shared-memory atomics and the RoIs dealt
+ * round-robin to the warps (no repeated work; summation order varies like the reference's), and roi_pool /
+ * ps_roi_align - one bin per (RoI, plane) - scatter with global atomics.  Other dtypes (F16, F64),
  * adaptive sampling (sampling_ratio <= 0) and planes larger than shared memory use an atomic scatter kernel.
  * workspace: vb200_roi_backward_workspace_bytes() bytes (sampling tables; pass sampling_ratio 1 for roi_pool). */
 VB200_API size_t vb200_roi_backward_workspace_bytes(int num_rois, int pooled_h, int pooled_w, int sampling_ratio);
 VB200_API int vb200_roi_align_backward(const void* grad, const void* rois, void* grad_input, int dtype, int batch,
                              int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
-                             double spatial_scale, int sampling_ratio, int aligned, void* workspace,
-                             size_t workspace_bytes, vb200_stream stream);
+                             double spatial_scale, int sampling_ratio, int aligned, int deterministic,
+                             void* workspace, size_t workspace_bytes, vb200_stream stream);
 VB200_API int vb200_roi_pool_backward(const void* grad, const void* rois, const int32_t* argmax, void* grad_input, int dtype,
                             int batch, int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
                             double spatial_scale, int deterministic, void* workspace, size_t workspace_bytes,

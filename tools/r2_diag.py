@@ -74,7 +74,10 @@ def gpu_reference():
     go = torch.randn(1000, 256, 7, 7, device=DEV)
     t_ref = timed(lambda: torch.ops.torchvision._roi_align_backward(go, rd, 0.25, 7, 7, 1, 256, 200, 272, 2, False), 10)
     t_our = timed(lambda: torch.ops.vision_b200._roi_align_backward(go, rd, 0.25, 7, 7, 1, 256, 200, 272, 2, False), 10)
-    print("cfg2 _roi_align_backward op ms: ref", t_ref, "ours (deterministic plane kernel)", t_our, flush=True)
+    torch.use_deterministic_algorithms(True)
+    t_det = timed(lambda: torch.ops.vision_b200._roi_align_backward(go, rd, 0.25, 7, 7, 1, 256, 200, 272, 2, False), 10)
+    torch.use_deterministic_algorithms(False)
+    print("cfg2 _roi_align_backward op ms: ref", t_ref, "ours default (plane + smem atomics)", t_our, "ours deterministic (row-owning warps)", t_det, flush=True)
     o, am = torch.ops.torchvision.roi_pool(xd, rd, 0.25, 7, 7)
     t_ref = timed(lambda: torch.ops.torchvision._roi_pool_backward(go, rd, am, 0.25, 7, 7, 1, 256, 200, 272), 10)
     t_our = timed(lambda: torch.ops.vision_b200._roi_pool_backward(go, rd, am, 0.25, 7, 7, 1, 256, 200, 272), 10)

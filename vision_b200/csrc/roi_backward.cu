@@ -305,6 +305,81 @@ roi_align_bwd_plane_fast_kernel(const float* __restrict__ grad, const BwdHdr* __
   }
 }
 
+// Non-deterministic sibling of the two kernels above (the default unless the caller asks for determinism): the plane is
+// still resident, but RoIs are dealt to the warps round-robin and every tap is a shared-memory atomic add, so no work is
+// repeated per band (the ownership scheme pays ~10 band hits per RoI).  fp32 shared atomics are a CAS loop on sm_100
+// (ATOMS.CAST.SPIN), cheap while contention is low - a warp's 28 taps of one line hit distinct columns.  The result differs
+// from run to run only in the summation order, as the reference's own atomic kernel does.
+__global__ void __launch_bounds__(kBwdThreads, 1)
+roi_align_bwd_plane_atomic_kernel(const float* __restrict__ grad, const BwdHdr* __restrict__ hdr, const uint2* __restrict__ ys,
+                                  const uint2* __restrict__ xe, float* __restrict__ grad_input, int B, int C, int H, int W, int K,
+                                  int PH, int PW, int sr) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* plane = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  const int NYS = PH * sr, NXE = 2 * PW * sr, NB = PH * PW;
+  const float inv_count = 1.0f / (float)(sr * sr);
+  const bool pow2 = (sr & (sr - 1)) == 0;
+  const float count = (float)(sr * sr);
+  const unsigned sr_recip = (65536u + (unsigned)sr - 1u) / (unsigned)sr;
+  for (int pl = blockIdx.x; pl < B * C; pl += gridDim.x) {
+    const int b = pl / C, c = pl - b * C;
+    {
+      float4* p4 = reinterpret_cast<float4*>(plane);
+      const int n4 = (H * W + 3) >> 2;
+      for (int i = tid; i < n4; i += blockDim.x) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    auto issue = [&](HitLoads& L, int& batch, int n) {
+      const float* __restrict__ g = grad + ((int64_t)n * C + c) * NB;
+      batch = __ldg(&hdr[n].batch);
+      L.yy = lane < NYS ? __ldg(ys + (int64_t)n * NYS + lane) : make_uint2(0xffffffffu, 0u);
+      L.e = lane < NXE ? __ldg(xe + (int64_t)n * NXE + lane) : make_uint2(0xffffffffu, 0u);
+      L.gA = lane < NB ? __ldg(g + lane) : 0.f;
+      L.gB = lane + 32 < NB ? __ldg(g + 32 + lane) : 0.f;
+    };
+    HitLoads cur, nxt;
+    int cur_b = -1, nxt_b = -1;
+    if (warp < K) issue(cur, cur_b, warp);
+    for (int n = warp; n < K; n += NW) {
+      if (n + NW < K) issue(nxt, nxt_b, n + NW);
+      if (cur_b == b) {
+        const int lo = (int)cur.yy.x;
+        const float l = __uint_as_float(cur.yy.y);
+        const bool valid = cur.e.x != 0xffffffffu;
+        const int col = (int)(cur.e.x & 0xffffu), pw = (int)(cur.e.x >> 16);
+        const float wx = __uint_as_float(cur.e.y);
+        unsigned mm = __ballot_sync(0xffffffffu, lo >= 0);
+        int cur_ph = -1;
+        float a = 0.f;
+        while (mm) {
+          const int j = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const int lo_j = __shfl_sync(0xffffffffu, lo, j);
+          const float l_j = __shfl_sync(0xffffffffu, l, j);
+          const int ph = (int)(((unsigned)j * sr_recip) >> 16);
+          if (ph != cur_ph) {                       // warp-uniform: a new bin row
+            cur_ph = ph;
+            const int t = valid ? ph * PW + pw : 0;
+            const float ga = __shfl_sync(0xffffffffu, cur.gA, t & 31), gb = __shfl_sync(0xffffffffu, cur.gB, t & 31);
+            const float gv = t < 32 ? ga : gb;
+            a = wx * (pow2 ? gv * inv_count : __fdiv_rn(gv, count));
+          }
+          if (valid) {
+            atomicAdd(plane + lo_j * W + col, (1.f - l_j) * a);
+            if (l_j > 0.f) atomicAdd(plane + (lo_j + 1) * W + col, l_j * a);
+          }
+        }
+      }
+      cur = nxt;
+      cur_b = nxt_b;
+    }
+    __syncthreads();
+    store_plane(grad_input + (int64_t)pl * H * W, plane, H * W);
+    __syncthreads();
+  }
+}
+
 // ---- roi_pool backward, plane-resident -----------------------------------------------------------------------
 // Rows that can hold an argmax of RoI n: [clamp(rsh), clamp(reh + 1)) (roi_pool_kernel.cu:43-58).
 __global__ void roi_pool_bwd_hdr_kernel(const float* __restrict__ rois, BwdHdr* __restrict__ hdr, int K, int H, float scale) {
@@ -593,8 +668,8 @@ extern "C" size_t vb200_roi_backward_workspace_bytes(int num_rois, int pooled_h,
 
 extern "C" int vb200_roi_align_backward(const void* grad, const void* rois, void* grad_input, int dtype, int batch,
                                         int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
-                                        double spatial_scale, int sampling_ratio, int aligned, void* workspace,
-                                        size_t workspace_bytes, vb200_stream stream) {
+                                        double spatial_scale, int sampling_ratio, int aligned, int deterministic,
+                                        void* workspace, size_t workspace_bytes, vb200_stream stream) {
   VB200_REQUIRE(batch >= 0 && channels >= 0 && height >= 0 && width >= 0 && num_rois >= 0, "roi_align_backward: negative size");
   VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "roi_align_backward: pooled size must be positive");
   cudaStream_t st = (cudaStream_t)stream;
@@ -617,7 +692,15 @@ extern "C" int vb200_roi_align_backward(const void* grad, const void* rois, void
     const size_t smem = (((size_t)height * width + 3) & ~(size_t)3) * 4;
     const int planes = batch * channels;
     const int grid = planes < sm_count() ? planes : sm_count();
-    if (pooled_h * sampling_ratio <= 32 && 2 * pooled_w * sampling_ratio <= 32 && pooled_h * pooled_w <= 64) {
+    const bool small_tables = pooled_h * sampling_ratio <= 32 && 2 * pooled_w * sampling_ratio <= 32 && pooled_h * pooled_w <= 64;
+    if (small_tables && !deterministic) {
+      VB200_CUDA_TRY(ensure_dyn_smem<roi_align_bwd_plane_atomic_kernel>(smem));
+      roi_align_bwd_plane_atomic_kernel<<<grid, kBwdThreads, smem, st>>>((const float*)grad, ws.hdr, ws.ys, ws.xe,
+                                                                        (float*)grad_input, batch, channels, height, width, num_rois,
+                                                                        pooled_h, pooled_w, sampling_ratio);
+      return check_launch("roi_align_bwd_plane_atomic_kernel");
+    }
+    if (small_tables) {
       VB200_CUDA_TRY(ensure_dyn_smem<roi_align_bwd_plane_fast_kernel>(smem));
       roi_align_bwd_plane_fast_kernel<<<grid, kBwdThreads, smem, st>>>((const float*)grad, ws.hdr, ws.ys, ws.xe, (float*)grad_input,
                                                                       batch, channels, height, width, num_rois, pooled_h, pooled_w,

@@ -137,7 +137,8 @@ at::Tensor roi_align_backward(const at::Tensor& grad, const at::Tensor& rois, do
   at::Tensor ws = workspace(wsb, grad);
   check_rc(vb200_roi_align_backward(g.data_ptr(), r.data_ptr(), grad_input.data_ptr(), dt, (int)batch_size, (int)channels,
                                     (int)height, (int)width, (int)r.size(0), (int)pooled_height, (int)pooled_width, spatial_scale,
-                                    (int)sampling_ratio, aligned ? 1 : 0, wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+                                    (int)sampling_ratio, aligned ? 1 : 0, at::globalContext().deterministicAlgorithms() ? 1 : 0,
+                                    wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
            "roi_align_backward");
   return grad_input;
 }
