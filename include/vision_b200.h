@@ -92,6 +92,26 @@ VB200_API int vb200_roi_align_forward(const void* input, const void* rois, void*
                             int sampling_ratio, int aligned, void* workspace,
                             size_t workspace_bytes, vb200_stream stream);
 
+/* ---- MultiScaleRoIAlign, fused -----------------------------------------
+ * Replaces _multiscale_roi_align, torchvision/ops/poolers.py:147-228: per level {where, gather rois, roi_align,
+ * scatter into a zeroed result} plus the LevelMapper (poolers.py:47-84) as a chain of tensor ops - here ONE geometry
+ * launch (LevelMapper evaluated on the device, RoIs bucketed by level) and ONE gather launch whose work list runs over
+ * the channel planes of every level; output rows are written in place (no zero-fill, no scatter).
+ * level_ptrs / heights / widths / scales: HOST arrays of num_levels entries (device pointers of [batch, channels, H_l, W_l]
+ * fp32 maps); rois [num_rois, 5] (batch index, x1, y1, x2, y2 in image coordinates); output [num_rois, channels, 7, 7];
+ * levels_out [num_rois] int32 = level index of every RoI (for the backward pass).  aligned = False as the reference
+ * calls it.  Supported: fp32, 7x7 bins, sampling_ratio 2, <= 8 levels, every plane fits shared memory
+ * (vb200_multiscale_roi_align_supported); other configurations stay on the per-level path. */
+VB200_API size_t vb200_multiscale_roi_align_workspace_bytes(int num_rois, int num_levels);
+VB200_API int vb200_multiscale_roi_align_supported(int dtype, int num_levels, const int* heights, const int* widths,
+                                         int pooled_h, int pooled_w, int sampling_ratio);
+VB200_API int vb200_multiscale_roi_align_forward(const void* const* level_ptrs, const int* heights, const int* widths,
+                                       const double* scales, int num_levels, const void* rois, void* output,
+                                       int32_t* levels_out, int dtype, int batch, int channels, int num_rois,
+                                       int pooled_h, int pooled_w, int sampling_ratio, int k_min, int k_max,
+                                       double canonical_scale, double canonical_level, double eps, void* workspace,
+                                       size_t workspace_bytes, vb200_stream stream);
+
 /* ---- roi_pool ----------------------------------------------------------
  * Replaces roi_pool_forward_kernel, csrc/ops/cuda/roi_pool_kernel.cu:127-188
  * (schema torchvision::roi_pool, csrc/ops/roi_pool.cpp:67-68).

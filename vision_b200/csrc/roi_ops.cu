@@ -343,15 +343,49 @@ __device__ __forceinline__ int bank_multiplicity(uint32_t addr, bool active, int
   return m;
 }
 
-template <int P, int SR>
+// Feature levels of the fused MultiScaleRoIAlign (torchvision/ops/poolers.py:147-228): passed by value.
+constexpr int kMaxLevels = 8;
+struct LevelDesc { const float* base; int H, W, pitch; float scale; };
+struct LevelSet {
+  LevelDesc lv[kMaxLevels];
+  int num_levels;
+  // LevelMapper (poolers.py:47-84): floor(lvl0 + log2(sqrt(area) / s0) + eps) clamped to [k_min, k_max], minus k_min
+  int k_min, k_max;
+  float s0, lvl0, eps;
+};
+
+// The reference evaluates the mapper as a chain of fp32 tensor ops; each step below is one of them, rounded once.
+__device__ __forceinline__ int map_level(const float* __restrict__ box /* x1 y1 x2 y2 */, const LevelSet& L) {
+  const float area = mul_rn(sub_rn(box[2], box[0]), sub_rn(box[3], box[1]));    // box_area (boxes.py: (x2-x1)*(y2-y1))
+  const float sq = sqrtf(area);                                                   // correctly rounded
+  float t = add_rn(add_rn(L.lvl0, log2f(div_rn(sq, L.s0))), L.eps);
+  t = floorf(t);
+  if (t != t) return -1;        // inverted box: NaN level matches no `levels == level` test in the reference -> its row stays zero
+  t = fminf(fmaxf(t, (float)L.k_min), (float)L.k_max);
+  return min(max((int)t - L.k_min, 0), L.num_levels - 1);
+}
+
+template <int P, int SR, bool MULTI>
 __global__ void __launch_bounds__(256)
 roi_align_line_geometry_kernel(const float* __restrict__ rois, LineTab* __restrict__ tab, int K, int H, int W,
-                               float scale, int aligned, int pitch, int force_axis) {
+                               float scale, int aligned, int pitch, int force_axis, int B, LevelSet L,
+                               int* __restrict__ lvl_count, int* __restrict__ bucket, int32_t* __restrict__ lvl_out) {
   constexpr int NS = P * SR, NL = NS * 2;
   asm volatile("griddepcontrol.launch_dependents;");   // the gather kernel may start staging its first plane
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (n >= K) return;
-  const RoiGeom<float> g = roi_geometry<float, float>(rois + (int64_t)n * 5, scale, P, P, SR, aligned != 0, false);
+  bool dead = false;        // RoIs the reference leaves at zero (no level) or reads out of bounds for (bad batch index): all-zero weights
+  if (MULTI) {
+    int lvl = map_level(rois + (int64_t)n * 5 + 1, L);
+    if (lvl < 0) { dead = true; lvl = 0; }
+    H = L.lv[lvl].H; W = L.lv[lvl].W; pitch = L.lv[lvl].pitch; scale = L.lv[lvl].scale;
+    if (lane == 0) {
+      bucket[(int64_t)lvl * K + atomicAdd(lvl_count + lvl, 1)] = n;     // order inside a level is irrelevant: outputs are addressed by RoI id
+      lvl_out[n] = lvl;
+    }
+  }
+  RoiGeom<float> g = roi_geometry<float, float>(rois + (int64_t)n * 5, scale, P, P, SR, aligned != 0, false);
+  if (g.batch < 0 || g.batch >= B) { dead = true; g.batch = 0; }
   const bool act = lane < NL;
   const int j = act ? lane >> 1 : 0, c = lane & 1;
   int xlo, ylo; float xl, yl;
@@ -365,7 +399,7 @@ roi_align_line_geometry_kernel(const float* __restrict__ rois, LineTab* __restri
   // lanes beyond the taps repeat lane 0's address with weight 0: a broadcast, never an extra bank conflict
   const uint32_t my_off = (lane_is_y ? ay : ax) * 4u + (lane_is_y ? 1u : 0u);   // bit 0: lane axis
   const uint32_t off0 = __shfl_sync(0xffffffffu, my_off, 0);
-  t->lane[lane] = act ? make_uint2(my_off, __float_as_uint(c ? l : 1.f - l)) : make_uint2(off0, 0u);
+  t->lane[lane] = (act && !dead) ? make_uint2(my_off, __float_as_uint(c ? l : 1.f - l)) : make_uint2(act ? my_off : off0, 0u);
   if (lane < NS) {   // loop-axis sample `lane`
     int lo; float ll;
     if (lane_is_y) packed_axis(axis_entry<float>(sample_coord<float>(g.start_w, g.bin_w, lane / SR, lane % SR, SR), W), W, lo, ll);
@@ -403,10 +437,14 @@ constexpr int kLineStageBytes = (kLineThreads / 32) * 2 * 128;   // per warp: tw
 
 __host__ __device__ inline size_t line_plane_bytes(int H, int pitch) { return (((size_t)(H + 2) * pitch * 4) + 15) & ~(size_t)15; }
 
-template <int P, int SR>
+// MULTI: fused MultiScaleRoIAlign - the work list runs over the planes of ALL feature levels (each level has its own
+// H, W, pitch and RoI bucket, filled by the geometry kernel's device-side LevelMapper); outputs are addressed by RoI id,
+// so there is no per-level gather / scatter / zero-fill pass.
+template <int P, int SR, bool MULTI>
 __global__ void __launch_bounds__(kLineThreads, 1)
 roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict__ tab, float* __restrict__ output,
-                      int B, int C, int H, int W, int K, int pitch) {
+                      int B, int C, int H, int W, int K, int pitch, LevelSet L, const int* __restrict__ lvl_count,
+                      const int* __restrict__ bucket) {
   constexpr int NS = P * SR, NL = NS * 2, NB = P * P;
   static_assert(NL <= 32 && SR == 2 && P <= 8 && NS == 14, "lane mapping: 4 lanes per bin column, two finished bins per lane");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -414,16 +452,16 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
   const uint32_t plane_s = smem_u32(plane);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
-  const uint32_t stage_s = plane_s + (uint32_t)line_plane_bytes(H, pitch) + (uint32_t)warp * 256u;
-  const int64_t total = (int64_t)B * C * K;
-  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
-  const int64_t w0 = (int64_t)blockIdx.x * per;
-  const int64_t w1 = min(total, w0 + per);
-
-  // zero columns [W, pitch) of every row and the two zero rows, once
-  for (int r = warp; r < H; r += NW)
-    for (int col = W + lane; col < pitch; col += 32) plane[r * pitch + col] = 0.f;
-  for (int i = H * pitch + tid; i < (H + 2) * pitch; i += blockDim.x) plane[i] = 0.f;
+  // the per-warp staging slots sit behind the LARGEST plane of the call
+  int Hmax = H, pmax = pitch;
+  if (MULTI) {
+    size_t best = 0;
+    for (int l = 0; l < L.num_levels; ++l) {
+      const size_t bts = line_plane_bytes(L.lv[l].H, L.lv[l].pitch);
+      if (bts > best) { best = bts; Hmax = L.lv[l].H; pmax = L.lv[l].pitch; }
+    }
+  }
+  const uint32_t stage_s = plane_s + (uint32_t)line_plane_bytes(Hmax, pmax) + (uint32_t)warp * 256u;
 
   const int q = lane & 3, grp = lane >> 2;
   const bool hi = (q & 2) != 0, lo = (q & 1) != 0;
@@ -431,15 +469,51 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
   // output offsets of this lane's two finished bins (loop-axis bins 2q, 2q+1 of lane group grp)
   const int off_x = 2 * q * P + grp, off_y = 2 * q + grp * P;       // lane axis x: bin = k * P + grp; y: the transpose
   const bool st0 = grp < P && 2 * q < P, st1 = grp < P && 2 * q + 1 < P;
-  const int64_t ostep = (int64_t)NW * C * NB;
 
+  int64_t total = (int64_t)B * C * K;
+  int Kl[kMaxLevels];
+  if (MULTI) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // the level counts come from the geometry kernel
+    total = 0;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+      Kl[l] = l < L.num_levels ? __ldg(lvl_count + l) : 0;
+      total += (int64_t)B * C * Kl[l];
+    }
+  }
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per;
+  const int64_t w1 = min(total, w0 + per);
+
+  int cur_H = -1, cur_pitch = -1;
   int64_t w = w0;
   while (w < w1) {
-    const int pl = (int)(w / K);              // plane index = b * C + c
-    const int r0 = (int)(w - (int64_t)pl * K);
-    const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
+    // ---- locate the (level, plane, first RoI) of work item w ----
+    int lvl = 0, Kc = K;
+    int64_t wl = w;
+    const int* __restrict__ ids = nullptr;
+    if (MULTI) {
+#pragma unroll
+      for (int l = 0; l < kMaxLevels; ++l) {
+        const int64_t pl_ = (int64_t)B * C * Kl[l];
+        if (lvl == l && wl >= pl_) { wl -= pl_; lvl = l + 1; }
+      }
+      Kc = Kl[lvl];
+      H = L.lv[lvl].H; W = L.lv[lvl].W; pitch = L.lv[lvl].pitch; input = L.lv[lvl].base;
+      ids = bucket + (int64_t)lvl * K;
+    }
+    const int pl = (int)(wl / Kc);              // plane index = b * C + c
+    const int r0 = (int)(wl - (int64_t)pl * Kc);
+    const int r1 = (int)min((int64_t)Kc, r0 + (w1 - w));
     const int b = pl / C;
+    const int64_t ostep = (int64_t)NW * C * NB;
     __syncthreads();                           // everyone is done with the previous plane
+    if (H != cur_H || pitch != cur_pitch) {    // (re)zero the pads: columns [W, pitch) of every row and the two zero rows
+      for (int r = warp; r < H; r += NW)
+        for (int col = W + lane; col < pitch; col += 32) plane[r * pitch + col] = 0.f;
+      for (int i = H * pitch + tid; i < (H + 2) * pitch; i += blockDim.x) plane[i] = 0.f;
+      cur_H = H; cur_pitch = pitch;
+    }
     {
       const float* src = input + (int64_t)pl * H * W;
       for (int r = warp; r < H; r += NW) {
@@ -451,25 +525,29 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
     }
     // The geometry of the next RoI travels one iteration ahead: the lane entry in registers, the
     // 14 loop entries + header (128 B) by cp.async into this warp's staging slot.
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // the table is complete from here on (no-op after the first time)
+    if (!MULTI) asm volatile("griddepcontrol.wait;" ::: "memory");   // the table is complete from here on (no-op after the first time)
     int n = r0 + warp;
+    int id = 0, id_next = 0;
     uint2 le = make_uint2(0u, 0u);
     uint32_t slot = 0;
     if (n < r1) {
-      le = __ldg(&tab[n].lane[lane]);
-      if (lane < 8) cp_async16(stage_s + lane * 16u, reinterpret_cast<const uint4*>(tab + n) + 16 + lane);
+      id = MULTI ? __ldg(ids + n) : n;
+      if (n + NW < r1) id_next = MULTI ? __ldg(ids + n + NW) : n + NW;
+      le = __ldg(&tab[id].lane[lane]);
+      if (lane < 8) cp_async16(stage_s + lane * 16u, reinterpret_cast<const uint4*>(tab + id) + 16 + lane);
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");   // the plane has landed
     __syncthreads();
 
-    float* __restrict__ outp = output + ((int64_t)n * C + (pl - b * C)) * NB;
-    for (; n < r1; n += NW, outp += ostep) {
+    for (; n < r1; n += NW) {
       const int nn = n + NW;
       uint2 le_next = make_uint2(0u, 0u);
+      int id_next2 = 0;
       __syncwarp();
       if (nn < r1) {
-        le_next = __ldg(&tab[nn].lane[lane]);
-        if (lane < 8) cp_async16(stage_s + (slot ^ 128u) + lane * 16u, reinterpret_cast<const uint4*>(tab + nn) + 16 + lane);
+        if (nn + NW < r1) id_next2 = MULTI ? __ldg(ids + nn + NW) : nn + NW;
+        le_next = __ldg(&tab[id_next].lane[lane]);
+        if (lane < 8) cp_async16(stage_s + (slot ^ 128u) + lane * 16u, reinterpret_cast<const uint4*>(tab + id_next) + 16 + lane);
       }
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
       __syncwarp();
@@ -478,9 +556,10 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
       bool mine = true;
       if (B > 1) mine = (int)lds_u32(st + 116u) == b;      // header word 1: the RoI's batch index
       if (mine) {
+        float* __restrict__ outp = output + ((int64_t)id * C + (pl - b * C)) * NB;
         const uint32_t base0 = plane_s + (le.x & ~3u);
         const uint32_t base1 = base0 + (lane_is_y ? 4u : (uint32_t)pitch * 4u);
-        const float wl = __uint_as_float(le.y);
+        const float wl_ = __uint_as_float(le.y);
         float acc[8];
         acc[7] = 0.f;
 #pragma unroll
@@ -490,7 +569,7 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
           const float b0 = lds_f32(base0 + ee.z), b1 = lds_f32(base1 + ee.z);
           const float ta = fmaf(__uint_as_float(ee.y), a1 - a0, a0);
           const float tb = fmaf(__uint_as_float(ee.w), b1 - b0, b0);
-          acc[p] = (ta + tb) * wl;
+          acc[p] = (ta + tb) * wl_;
         }
         // fold the 4 lanes of a bin column: after two exchanges lane q holds loop-axis bins 2q, 2q+1
         float r4[4];
@@ -511,7 +590,10 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
       }
       slot ^= 128u;
       le = le_next;
+      id = id_next;
+      id_next = id_next2;
     }
+    (void)ostep;
     w += (r1 - r0);
   }
 }
@@ -797,13 +879,15 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       LineTab* tab = (LineTab*)workspace;
       const char* fa = env_override(ENV_ROI_LINE_AXIS);   // diagnosis: "x" | "y" pins the lane axis
       const int force_axis = fa ? (fa[0] == 'y' ? 2 : fa[0] == 'x' ? 1 : 0) : 0;
-      roi_align_line_geometry_kernel<7, 2><<<ceil_div(num_rois * 32, 256), 256, 0, st>>>(
-          (const float*)rois, tab, num_rois, height, width, (float)spatial_scale, aligned, pitch, force_axis);
+      LevelSet none = {};
+      roi_align_line_geometry_kernel<7, 2, false><<<ceil_div(num_rois * 32, 256), 256, 0, st>>>(
+          (const float*)rois, tab, num_rois, height, width, (float)spatial_scale, aligned, pitch, force_axis, batch, none, nullptr,
+          nullptr, nullptr);
       int rc = check_launch("roi_align_line_geometry_kernel");
       if (rc) return rc;
       const int64_t pairs = (int64_t)batch * channels * num_rois;
       const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
-      VB200_CUDA_TRY(ensure_dyn_smem<roi_align_line_kernel<7, 2>>(smem));
+      VB200_CUDA_TRY(ensure_dyn_smem<roi_align_line_kernel<7, 2, false>>(smem));
       // programmatic dependent launch: the gather kernel zeroes its pads and stages its first plane while
       // the geometry kernel is still running, and waits (griddepcontrol.wait) before it reads the table
       cudaLaunchConfig_t cfg = {};
@@ -812,8 +896,9 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      VB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, roi_align_line_kernel<7, 2>, (const float*)input, (const LineTab*)tab,
-                                        (float*)output, batch, channels, height, width, num_rois, pitch));
+      VB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, roi_align_line_kernel<7, 2, false>, (const float*)input, (const LineTab*)tab,
+                                        (float*)output, batch, channels, height, width, num_rois, pitch, none,
+                                        (const int*)nullptr, (const int*)nullptr));
       return check_launch("roi_align_line_kernel");
     }
     const bool use_plane = path == 1;
@@ -861,6 +946,80 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
                                             pooled_w, spatial_scale, sampling_ratio, aligned, st);
   set_error("roi_align: unsupported dtype %d (float, double, half as the reference)", dtype);
   return VB200_EUNSUPPORTED;
+}
+
+// ---- fused MultiScaleRoIAlign ------------------------------------------------------------------------------------
+namespace {
+struct MsWs { LineTab* tab; int* lvl_count; int* bucket; size_t total; };
+MsWs carve_ms(void* base, int K, int num_levels) {
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* q = base ? (void*)(p + off) : nullptr; off += (bytes + 255) & ~(size_t)255; return q; };
+  MsWs w;
+  w.tab = (LineTab*)take((size_t)K * sizeof(LineTab));
+  w.lvl_count = (int*)take(kMaxLevels * sizeof(int));
+  w.bucket = (int*)take((size_t)num_levels * K * sizeof(int));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t vb200_multiscale_roi_align_workspace_bytes(int num_rois, int num_levels) {
+  if (num_rois <= 0 || num_levels <= 0) return 0;
+  return carve_ms(nullptr, num_rois, num_levels).total;
+}
+
+extern "C" int vb200_multiscale_roi_align_supported(int dtype, int num_levels, const int* heights, const int* widths, int pooled_h,
+                                                    int pooled_w, int sampling_ratio) {
+  if (dtype != VB200_F32 || num_levels < 1 || num_levels > kMaxLevels) return 0;
+  if (pooled_h != 7 || pooled_w != 7 || sampling_ratio != 2) return 0;
+  for (int l = 0; l < num_levels; ++l) {
+    if (heights[l] < 2 || widths[l] < 2) return 0;
+    if (line_plane_bytes(heights[l], line_pitch(widths[l])) + kLineStageBytes + 1024 > (size_t)max_smem_optin()) return 0;
+  }
+  return 1;
+}
+
+extern "C" int vb200_multiscale_roi_align_forward(const void* const* level_ptrs, const int* heights, const int* widths,
+                                                  const double* scales, int num_levels, const void* rois, void* output,
+                                                  int32_t* levels_out, int dtype, int batch, int channels, int num_rois,
+                                                  int pooled_h, int pooled_w, int sampling_ratio, int k_min, int k_max,
+                                                  double canonical_scale, double canonical_level, double eps, void* workspace,
+                                                  size_t workspace_bytes, vb200_stream stream) {
+  VB200_REQUIRE(vb200_multiscale_roi_align_supported(dtype, num_levels, heights, widths, pooled_h, pooled_w, sampling_ratio),
+                "multiscale_roi_align: unsupported configuration (fp32, 7x7 bins, sampling_ratio 2, <= 8 levels, planes that fit shared memory)");
+  if (num_rois == 0 || channels == 0 || batch == 0) return 0;
+  VB200_REQUIRE(level_ptrs && rois && output && levels_out, "multiscale_roi_align: null pointer");
+  const MsWs ws = carve_ms(workspace, num_rois, num_levels);
+  VB200_REQUIRE(workspace && ((uintptr_t)workspace % 16) == 0 && workspace_bytes >= ws.total, "multiscale_roi_align: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  LevelSet L = {};
+  L.num_levels = num_levels;
+  L.k_min = k_min; L.k_max = k_max;
+  L.s0 = (float)canonical_scale; L.lvl0 = (float)canonical_level; L.eps = (float)eps;
+  size_t smem = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    VB200_REQUIRE(level_ptrs[l] != nullptr, "multiscale_roi_align: null level pointer");
+    VB200_REQUIRE((int64_t)batch * channels * heights[l] * widths[l] < (1ll << 31), "multiscale_roi_align: level too large for 32-bit indexing");
+    L.lv[l].base = (const float*)level_ptrs[l];
+    L.lv[l].H = heights[l]; L.lv[l].W = widths[l]; L.lv[l].pitch = line_pitch(widths[l]);
+    L.lv[l].scale = (float)scales[l];
+    const size_t bts = line_plane_bytes(heights[l], L.lv[l].pitch);
+    smem = bts > smem ? bts : smem;
+  }
+  smem += kLineStageBytes;
+  VB200_REQUIRE((int64_t)num_rois * channels * 49 < (1ll << 31), "multiscale_roi_align: output too large for 32-bit indexing");
+  VB200_CUDA_TRY(cudaMemsetAsync(ws.lvl_count, 0, kMaxLevels * sizeof(int), st));
+  roi_align_line_geometry_kernel<7, 2, true><<<ceil_div(num_rois * 32, 256), 256, 0, st>>>(
+      (const float*)rois, ws.tab, num_rois, 0, 0, 0.f, 0, 0, 0, batch, L, ws.lvl_count, ws.bucket, levels_out);
+  int rc = check_launch("roi_align_line_geometry_kernel");
+  if (rc) return rc;
+  const int64_t pairs = (int64_t)batch * channels * num_rois;
+  const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+  VB200_CUDA_TRY(ensure_dyn_smem<roi_align_line_kernel<7, 2, true>>(smem));
+  roi_align_line_kernel<7, 2, true><<<grid, kLineThreads, smem, st>>>(nullptr, ws.tab, (float*)output, batch, channels, 0, 0, num_rois, 0,
+                                                                     L, ws.lvl_count, ws.bucket);
+  return check_launch("roi_align_line_kernel");
 }
 
 // Plane residency pays when the RoIs of a plane touch more bytes than the plane has; tiny problems read through L2.
