@@ -369,3 +369,75 @@ def test_autograd_through_both_api_surfaces(vb):
     assert gradcheck(lambda z: vb.ops.roi_align(z, r, 2, spatial_scale=1, sampling_ratio=1), (xg,), atol=1e-5)
     assert gradcheck(lambda z: vb.ops.ps_roi_align(z, r, 2, spatial_scale=1, sampling_ratio=1), (xg,), atol=1e-5)
     assert gradcheck(lambda z: vb.ops.roi_pool(z, r, 2, spatial_scale=1), (xg,), atol=1e-5)
+
+
+# =============================== fused MultiScaleRoIAlign ===============================
+def _fpn_case(batch=2, channels=32, seed=0, n_boxes=(700, 500)):
+    from collections import OrderedDict
+
+    g = torch.Generator().manual_seed(seed)
+    ih, iw = 800, 1088
+    feats = OrderedDict()
+    for name, s in (("0", 4), ("1", 8), ("2", 16), ("3", 32)):
+        feats[name] = torch.randn(batch, channels, ih // s, iw // s, generator=g)
+    boxes = []
+    for n in n_boxes[:batch]:
+        size = torch.exp(torch.rand(n, 2, generator=g) * 4.6 + 2.0)            # 7 .. 730 px: every level is hit
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([iw, ih]) * 0.9
+        b = torch.cat([xy, torch.minimum(xy + size, torch.tensor([float(iw), float(ih)]))], dim=1)
+        # exact LevelMapper boundaries (sqrt(area) = 112, 224, 448 -> log2 ratios -1, 0, 1), a zero-area and an inverted box
+        b[0] = torch.tensor([10.0, 10.0, 122.0, 122.0]); b[1] = torch.tensor([10.0, 10.0, 234.0, 234.0])
+        b[2] = torch.tensor([10.0, 10.0, 458.0, 458.0]); b[3] = torch.tensor([50.0, 60.0, 50.0, 90.0])
+        b[4] = torch.tensor([300.0, 200.0, 250.0, 260.0]); b[5] = torch.tensor([0.0, 0.0, 224.0 * 2, 112.0])
+        boxes.append(b)
+    return feats, boxes, [(ih, iw)] * batch
+
+
+def test_multiscale_roi_align_fused_vs_reference(vb):
+    tv = pytest.importorskip("torchvision")
+    from torchvision.ops import MultiScaleRoIAlign
+    from torchvision.ops.poolers import _convert_to_roi_format
+
+    assert not vb.installed()
+    feats, boxes, shapes = _fpn_case()
+    fd = type(feats)((k, v.to(DEV)) for k, v in feats.items())
+    bd = [b.to(DEV) for b in boxes]
+    m = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    ref_cuda = m(fd, bd, shapes)                                     # reference: per-level loop on its own CUDA kernels
+    ref_levels = m.map_levels(bd)
+    # the reference CPU kernel on the reference's own level assignment = the parity target
+    rois = _convert_to_roi_format(boxes)
+    want = torch.zeros(rois.shape[0], 32, 7, 7)
+    for lvl, (f, s) in enumerate(zip(feats.values(), m.scales)):
+        idx = torch.where(ref_levels.cpu() == lvl)[0]
+        want[idx] = tv.ops.roi_align(f, rois[idx], 7, s, 2)
+    vb.install()
+    try:
+        before = vb.launch_count()
+        ours = m(fd, bd, shapes)
+        used = vb.launch_count() - before
+        assert used == 2, used                                       # ONE geometry launch + ONE gather launch for all four levels
+        out2, levels = torch.ops.vision_b200.multiscale_roi_align(list(fd.values()), _convert_to_roi_format(bd), list(m.scales), 7, 7, 2,
+                                                                  m.map_levels.k_min, m.map_levels.k_max, float(m.map_levels.s0),
+                                                                  float(m.map_levels.lvl0), float(m.map_levels.eps))
+        valid = ref_levels >= 0                                      # the inverted box has a NaN level in the reference (row stays zero)
+        assert torch.equal(levels.long()[valid], ref_levels[valid])
+        assert torch.equal(ours, out2)
+        np.testing.assert_allclose(npy(ours), want.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(npy(ours), npy(ref_cuda), rtol=1e-4, atol=1e-4)     # the CUDA reference is itself ~7e-5 from its CPU kernel
+        # a shape the fused kernel does not cover (14x14 bins, the mask head) keeps working through the per-level loop
+        m14 = MultiScaleRoIAlign(["0", "1", "2", "3"], 14, 2)
+        o14 = m14(fd, bd, shapes)
+    finally:
+        vb.uninstall()
+    np.testing.assert_allclose(npy(o14), npy(m14(fd, bd, shapes)), rtol=1e-4, atol=1e-4)
+    # gradients of the fused op, per level, against the reference's autograd through its per-level loop
+    fr = type(feats)((k, v.to(DEV).requires_grad_(True)) for k, v in feats.items())
+    m(fr, bd, shapes).square().sum().backward()
+    fo = [v.to(DEV).requires_grad_(True) for v in feats.values()]
+    out, _ = torch.ops.vision_b200.multiscale_roi_align(fo, _convert_to_roi_format(bd), list(m.scales), 7, 7, 2, m.map_levels.k_min,
+                                                        m.map_levels.k_max, float(m.map_levels.s0), float(m.map_levels.lvl0),
+                                                        float(m.map_levels.eps))
+    out.square().sum().backward()
+    for a, b_ in zip(fo, fr.values()):
+        np.testing.assert_allclose(npy(a.grad), npy(b_.grad), rtol=1e-3, atol=1e-3 * max(1.0, b_.grad.abs().max().item()))

@@ -114,9 +114,33 @@ def gpu_reference():
           "ours", timed(lambda: vb.transforms.resize(img, [224, 224], antialias=False), 5), flush=True)
 
 
+def multiscale():
+    from collections import OrderedDict
+    from torchvision.ops import MultiScaleRoIAlign
+    g = torch.Generator().manual_seed(0)
+    ih, iw = 800, 1088
+    feats = OrderedDict((str(i), torch.randn(1, 256, ih // s, iw // s, generator=g).to(DEV)) for i, s in enumerate((4, 8, 16, 32)))
+    size = torch.exp(torch.rand(1000, 2, generator=g) * 4.0 + 2.5)
+    xy = torch.rand(1000, 2, generator=g) * torch.tensor([iw, ih]) * 0.8
+    boxes = [torch.cat([xy, torch.minimum(xy + size, torch.tensor([float(iw), float(ih)]))], dim=1).to(DEV)]
+    m = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    t_ref = timed(lambda: m(feats, boxes, [(ih, iw)]), 10)
+    vb.install()
+    t_fused = timed(lambda: m(feats, boxes, [(ih, iw)]), 20)
+    from torchvision.ops import poolers
+    fused = poolers._multiscale_roi_align
+    poolers._multiscale_roi_align = vb._install._state["orig_msra"]
+    t_loop = timed(lambda: m(feats, boxes, [(ih, iw)]), 20)
+    poolers._multiscale_roi_align = fused
+    vb.uninstall()
+    print("MultiScaleRoIAlign 4 levels x 256 ch, 1000 boxes, ms: reference", t_ref, "ours per-level loop", t_loop, "ours fused", t_fused, flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "dcn"):
         dcn_headroom()
+    if which in ("all", "ms"):
+        multiscale()
     if which in ("all", "ref"):
         gpu_reference()

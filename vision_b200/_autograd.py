@@ -102,6 +102,30 @@ def register() -> None:
           width):
         return grad.new_empty((batch_size, channels, height, width))
 
+    # ---- fused MultiScaleRoIAlign: gradients per level through _roi_align_backward on that level's RoIs ----
+    def ms_setup(ctx, inputs, output):
+        feats, rois, scales, ph, pw, sr = inputs[:6]
+        ctx.save_for_backward(rois, output[1])
+        ctx.mark_non_differentiable(output[1])
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.args = (list(scales), ph, pw, sr)
+
+    def ms_backward(ctx, grad, _grad_levels):
+        rois, levels = ctx.saved_tensors
+        scales, ph, pw, sr = ctx.args
+        grads = []
+        for lvl, (b, c, h, w) in enumerate(ctx.shapes):
+            idx = torch.where(levels == lvl)[0]
+            grads.append(ops._roi_align_backward(grad[idx].contiguous(), rois[idx].contiguous(), scales[lvl], ph, pw, b, c, h, w, sr, False))
+        return (grads,) + (None,) * 10
+
+    lib.register_autograd("vision_b200::multiscale_roi_align", ms_backward, setup_context=ms_setup)
+
+    @lib.register_fake("vision_b200::multiscale_roi_align")
+    def _(features, rois, scales, pooled_height, pooled_width, sampling_ratio, k_min, k_max, canonical_scale, canonical_level, eps):
+        f0 = features[0]
+        return (f0.new_empty((rois.size(0), f0.size(1), pooled_height, pooled_width)), f0.new_empty((rois.size(0),), dtype=torch.int32))
+
     # ---- nms / batched_nms: data-dependent output length ----
     @lib.register_fake("vision_b200::nms")
     def _(dets, scores, iou_threshold):

@@ -6,7 +6,9 @@
    Autograd, Autocast, CPU and quantized registrations are untouched.
 2. ``batched_nms`` is Python in the reference (torchvision/ops/boxes.py:57-126): the module
    attribute is rebound (detection models call ``box_ops.batched_nms`` at call time).
-3. ``resize`` has no torchvision kernel (transforms/v2/functional/_geometry.py:283-362 calls
+3. ``MultiScaleRoIAlign`` (torchvision/ops/poolers.py:147-228): the module-level ``_multiscale_roi_align`` is rebound
+   to the fused kernel (device-side LevelMapper + one gather launch over all FPN levels) when the shape is covered.
+4. ``resize`` has no torchvision kernel (transforms/v2/functional/_geometry.py:283-362 calls
    F.interpolate): the entries of ``_KERNEL_REGISTRY[resize]`` for Tensor / Image / Video are swapped.
 CPU tensors and unsupported dtypes/modes keep flowing to the reference implementation.
 """
@@ -52,6 +54,20 @@ def install() -> None:
     tv_boxes.batched_nms = batched_nms
     torchvision.ops.batched_nms = batched_nms
 
+    # ---- MultiScaleRoIAlign: the per-level loop of poolers.py:147-228 becomes one fused call when the kernel covers it ----
+    from torchvision.ops import poolers as tv_poolers
+    from . import ops as _ops_mod
+
+    orig_msra = tv_poolers._multiscale_roi_align
+
+    def _multiscale_roi_align(x_filtered, boxes, output_size, sampling_ratio, scales, mapper):
+        if (scales is not None and mapper is not None and not torch.jit.is_scripting() and not torch.jit.is_tracing()
+                and not torchvision._is_tracing() and _ops_mod.multiscale_roi_align_supported(x_filtered, boxes, output_size, sampling_ratio)):
+            return _ops_mod.multiscale_roi_align(x_filtered, boxes, output_size, sampling_ratio, scales, mapper)
+        return orig_msra(x_filtered, boxes, output_size, sampling_ratio, scales, mapper)
+
+    tv_poolers._multiscale_roi_align = _multiscale_roi_align
+
     # ---- resize ----
     registry = tv_utils._KERNEL_REGISTRY[tv_geo.resize]
     saved = dict(registry)
@@ -71,7 +87,7 @@ def install() -> None:
     registry[tv_tensors.Video] = tv_utils._kernel_tv_tensor_wrapper(resize_video)
 
     _state.update(dict(tv_boxes=tv_boxes, torchvision=torchvision, orig_batched_nms=orig_batched_nms,
-                       registry=registry, saved_registry=saved))
+                       registry=registry, saved_registry=saved, tv_poolers=tv_poolers, orig_msra=orig_msra))
 
 
 def uninstall() -> None:
@@ -80,6 +96,7 @@ def uninstall() -> None:
     torch.ops.vision_b200._install(False)
     _state["tv_boxes"].batched_nms = _state["orig_batched_nms"]
     _state["torchvision"].ops.batched_nms = _state["orig_batched_nms"]
+    _state["tv_poolers"]._multiscale_roi_align = _state["orig_msra"]
     reg = _state["registry"]
     reg.clear()
     reg.update(_state["saved_registry"])

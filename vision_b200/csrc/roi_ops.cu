@@ -351,14 +351,14 @@ struct LevelSet {
   int num_levels;
   // LevelMapper (poolers.py:47-84): floor(lvl0 + log2(sqrt(area) / s0) + eps) clamped to [k_min, k_max], minus k_min
   int k_min, k_max;
-  float s0, lvl0, eps;
+  float inv_s0, lvl0, eps;
 };
 
 // The reference evaluates the mapper as a chain of fp32 tensor ops; each step below is one of them, rounded once.
 __device__ __forceinline__ int map_level(const float* __restrict__ box /* x1 y1 x2 y2 */, const LevelSet& L) {
   const float area = mul_rn(sub_rn(box[2], box[0]), sub_rn(box[3], box[1]));    // box_area (boxes.py: (x2-x1)*(y2-y1))
   const float sq = sqrtf(area);                                                   // correctly rounded
-  float t = add_rn(add_rn(L.lvl0, log2f(div_rn(sq, L.s0))), L.eps);
+  float t = add_rn(add_rn(L.lvl0, log2f(mul_rn(sq, L.inv_s0))), L.eps);   // torch's CUDA tensor / python-scalar is a * (1 / b)
   t = floorf(t);
   if (t != t) return -1;        // inverted box: NaN level matches no `levels == level` test in the reference -> its row stays zero
   t = fminf(fmaxf(t, (float)L.k_min), (float)L.k_max);
@@ -996,7 +996,7 @@ extern "C" int vb200_multiscale_roi_align_forward(const void* const* level_ptrs,
   LevelSet L = {};
   L.num_levels = num_levels;
   L.k_min = k_min; L.k_max = k_max;
-  L.s0 = (float)canonical_scale; L.lvl0 = (float)canonical_level; L.eps = (float)eps;
+  L.inv_s0 = 1.0f / (float)canonical_scale; L.lvl0 = (float)canonical_level; L.eps = (float)eps;
   size_t smem = 0;
   for (int l = 0; l < num_levels; ++l) {
     VB200_REQUIRE(level_ptrs[l] != nullptr, "multiscale_roi_align: null level pointer");

@@ -114,6 +114,48 @@ std::tuple<at::Tensor, at::Tensor> ps_roi_align(const at::Tensor& input, const a
   return std::make_tuple(out, mapping);
 }
 
+// ---- fused MultiScaleRoIAlign (torchvision/ops/poolers.py:147-228) ----------------------------------------------
+std::tuple<at::Tensor, at::Tensor> multiscale_roi_align(at::TensorList features, const at::Tensor& rois, at::ArrayRef<double> scales,
+                                                        int64_t pooled_height, int64_t pooled_width, int64_t sampling_ratio,
+                                                        int64_t k_min, int64_t k_max, double canonical_scale, double canonical_level,
+                                                        double eps) {
+  const int64_t nl = (int64_t)features.size();
+  TORCH_CHECK(nl >= 1 && nl <= 8 && (int64_t)scales.size() == nl, "multiscale_roi_align: 1..8 levels with one scale each");
+  TORCH_CHECK(rois.is_cuda() && rois.dim() == 2 && rois.size(1) == 5, "rois must have shape as Tensor[K, 5]");
+  at::cuda::CUDAGuard guard(rois.device());
+  const at::Tensor& f0 = features[0];
+  const int64_t B = f0.size(0), C = f0.size(1), K = rois.size(0);
+  std::vector<at::Tensor> keep;
+  std::vector<const void*> ptrs;
+  std::vector<int> hs, ws_;
+  for (const at::Tensor& f : features) {
+    TORCH_CHECK(f.is_cuda() && f.dim() == 4 && f.size(0) == B && f.size(1) == C && f.scalar_type() == f0.scalar_type() &&
+                    f.get_device() == rois.get_device(), "multiscale_roi_align: levels must share device, dtype, batch and channels");
+    keep.push_back(f.contiguous());
+    ptrs.push_back(keep.back().data_ptr());
+    hs.push_back((int)f.size(2));
+    ws_.push_back((int)f.size(3));
+  }
+  TORCH_CHECK(f0.scalar_type() == rois.scalar_type(), "Expected tensor for argument #1 'input' to have the same type as tensor for argument #2 'rois'");
+  const int dt = dtype_code(f0.scalar_type(), "multiscale_roi_align");
+  TORCH_CHECK(vb200_multiscale_roi_align_supported(dt, (int)nl, hs.data(), ws_.data(), (int)pooled_height, (int)pooled_width,
+                                                   (int)sampling_ratio),
+              "multiscale_roi_align: unsupported configuration (use the per-level path)");
+  at::Tensor out = at::empty({K, C, pooled_height, pooled_width}, f0.options());
+  at::Tensor levels = at::empty({K}, f0.options().dtype(at::kInt));
+  if (out.numel() == 0) return std::make_tuple(out, levels);
+  at::Tensor r = rois.contiguous();
+  const size_t wsb = vb200_multiscale_roi_align_workspace_bytes((int)K, (int)nl);
+  at::Tensor ws = workspace(wsb, f0);
+  std::vector<double> sc(scales.begin(), scales.end());
+  check_rc(vb200_multiscale_roi_align_forward(ptrs.data(), hs.data(), ws_.data(), sc.data(), (int)nl, r.data_ptr(), out.data_ptr(),
+                                              levels.data_ptr<int32_t>(), dt, (int)B, (int)C, (int)K, (int)pooled_height,
+                                              (int)pooled_width, (int)sampling_ratio, (int)k_min, (int)k_max, canonical_scale,
+                                              canonical_level, eps, ws.data_ptr(), wsb, cur_stream()),
+           "multiscale_roi_align");
+  return std::make_tuple(out, levels);
+}
+
 // ---- backward of the RoI ops (schemas: roi_align.cpp:76-77, roi_pool.cpp:69-70, ps_roi_align.cpp:76-77) ---------
 void check_bwd_inputs(const at::Tensor& grad, const at::Tensor& rois, const char* op) {
   TORCH_CHECK(grad.is_cuda(), "grad must be a CUDA tensor");
@@ -406,6 +448,7 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("ps_roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio) -> (Tensor, Tensor)");
   m.def("deform_conv2d(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> Tensor");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
+  m.def("multiscale_roi_align(Tensor[] features, Tensor rois, float[] scales, int pooled_height, int pooled_width, int sampling_ratio, int k_min, int k_max, float canonical_scale, float canonical_level, float eps) -> (Tensor, Tensor)");
   m.def("_roi_align_backward(Tensor grad, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width, int sampling_ratio, bool aligned) -> Tensor");
   m.def("_roi_pool_backward(Tensor grad, Tensor rois, Tensor argmax, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
   m.def("_ps_roi_align_backward(Tensor grad, Tensor rois, Tensor channel_mapping, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
@@ -429,4 +472,5 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("_roi_align_backward", TORCH_FN(roi_align_backward));
   m.impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   m.impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
+  m.impl("multiscale_roi_align", TORCH_FN(multiscale_roi_align));
 }

@@ -127,3 +127,34 @@ def deform_conv2d(input: Tensor, offset: Tensor, weight: Tensor, bias=None, stri
         )
     return _ops().deform_conv2d(input, weight, offset, mask, bias, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w,
                                 n_weight_grps, n_offset_grps, use_mask)
+
+
+# ---- MultiScaleRoIAlign ------------------------------------------------------------
+def multiscale_roi_align_supported(x_filtered, boxes, output_size, sampling_ratio) -> bool:
+    """True when the fused kernel covers the call (else torchvision's per-level loop runs, each level on our roi_align)."""
+    if len(x_filtered) < 2 or len(x_filtered) > 8 or tuple(output_size) != (7, 7) or int(sampling_ratio) != 2:
+        return False
+    f0 = x_filtered[0]
+    if not all(isinstance(f, Tensor) and f.is_cuda and f.dtype == torch.float32 and f.dim() == 4 and f.shape[:2] == f0.shape[:2]
+               for f in x_filtered):
+        return False
+    if not all(isinstance(b, Tensor) and b.is_cuda and b.dtype == torch.float32 for b in boxes):
+        return False
+    import ctypes
+
+    n = len(x_filtered)
+    hs = (ctypes.c_int * n)(*[int(f.shape[2]) for f in x_filtered])
+    ws = (ctypes.c_int * n)(*[int(f.shape[3]) for f in x_filtered])
+    return bool(_lib.core().vb200_multiscale_roi_align_supported(0, n, hs, ws, 7, 7, 2))
+
+
+def multiscale_roi_align(x_filtered, boxes, output_size, sampling_ratio, scales, mapper) -> Tensor:
+    """_multiscale_roi_align (torchvision/ops/poolers.py:147-228) as ONE fused call: the LevelMapper (poolers.py:47-84) is
+    evaluated on the device, every level is pooled by the same launch and rows are written in place."""
+    if scales is None or mapper is None:
+        raise ValueError("scales and mapper should not be None")
+    rois = convert_boxes_to_roi_format(list(boxes))
+    out, _levels = _ops().multiscale_roi_align(list(x_filtered), rois, [float(s) for s in scales], int(output_size[0]),
+                                               int(output_size[1]), int(sampling_ratio), int(mapper.k_min), int(mapper.k_max),
+                                               float(mapper.s0), float(mapper.lvl0), float(mapper.eps))
+    return out
