@@ -187,6 +187,20 @@ VB200_API int vb200_batched_nms(const void* boxes, const void* scores, const int
                       void* workspace, size_t workspace_bytes, int64_t* keep_out,
                       int64_t* num_keep_out, vb200_stream stream);
 
+/* ---- detection post-processing around batched_nms -------------------------
+ * Replaces the per-image tail of RoIHeads.postprocess_detections (torchvision/models/detection/roi_heads.py:700-737)
+ * and RegionProposalNetwork.filter_proposals (rpn.py:273-298): clip_boxes_to_image -> score filter (`>` or `>=`) ->
+ * remove_small_boxes -> batched_nms -> keep[:topk] -> gather boxes / scores / labels, as one device pipeline.
+ * boxes [n,4] F32, scores [n] F32, labels [n] int64 (class ids / FPN level ids); outputs sized min(n, topk).
+ * SYNCHRONOUS: the candidate count decides the reference's batched_nms strategy (boxes.py:86) and the output count sizes
+ * the result, so the call synchronises `stream` twice and returns the number of detections in *count_host (host). */
+VB200_API size_t vb200_detection_postprocess_workspace_bytes(int64_t n);
+VB200_API int vb200_detection_postprocess(const void* boxes, const void* scores, const int64_t* labels, int dtype, int64_t n,
+                                double img_h, double img_w, double score_thresh, int score_inclusive, double min_size,
+                                double iou_threshold, int64_t topk, int semantics, void* workspace,
+                                size_t workspace_bytes, void* boxes_out, void* scores_out, int64_t* labels_out,
+                                int64_t* count_host, vb200_stream stream);
+
 /* ---- deform_conv2d -----------------------------------------------------
  * Replaces deform_conv2d_forward_kernel, csrc/ops/cuda/deform_conv2d_kernel.cu:1035-1255
  * (schema torchvision::deform_conv2d, csrc/ops/deform_conv2d.cpp:101-102).
@@ -217,6 +231,17 @@ VB200_API int vb200_deform_conv2d_forward(const void* input, const void* weight,
  * align_corners=False semantics.  dtype: F32, F16, BF16, U8. */
 VB200_API int vb200_resize(const void* input, void* output, int dtype, int64_t planes, int in_h, int in_w,
                  int out_h, int out_w, int mode, int antialias, vb200_stream stream);
+
+/* ---- fused inference preprocessing --------------------------------------
+ * Replaces ImageClassification.forward, torchvision/transforms/_presets.py:57-64 (resize -> center_crop ->
+ * convert_image_dtype(float) -> normalize) with one launch: only the crop window [crop_top, +crop_h) x [crop_left, +crop_w)
+ * of the virtual resized image (resize_h x resize_w) is computed; the value is rounded to the storage dtype where the
+ * reference materialises the resized image, scaled to [0, 1] for U8, then (x - mean[c]) / std[c].
+ * input [batch, channels, in_h, in_w] (F32 / F16 / BF16 / U8), output [batch, channels, crop_h, crop_w] F32;
+ * mean_host / std_host: HOST arrays of `channels` floats (<= 8 channels). */
+VB200_API int vb200_resize_crop_normalize(const void* input, float* output, int dtype, int64_t batch, int channels, int in_h,
+                                int in_w, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w,
+                                int mode, int antialias, const float* mean_host, const float* std_host, vb200_stream stream);
 
 #ifdef __cplusplus
 }

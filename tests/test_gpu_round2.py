@@ -421,7 +421,8 @@ def test_multiscale_roi_align_fused_vs_reference(vb):
                                                                   m.map_levels.k_min, m.map_levels.k_max, float(m.map_levels.s0),
                                                                   float(m.map_levels.lvl0), float(m.map_levels.eps))
         valid = ref_levels >= 0                                      # the inverted box has a NaN level in the reference (row stays zero)
-        assert torch.equal(levels.long()[valid], ref_levels[valid])
+        bad = torch.where(valid & (levels.long() != ref_levels))[0]
+        assert bad.numel() == 0, (bad.tolist()[:8], torch.cat(bd)[bad][:8].tolist(), levels[bad][:8].tolist(), ref_levels[bad][:8].tolist())
         assert torch.equal(ours, out2)
         np.testing.assert_allclose(npy(ours), want.numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(npy(ours), npy(ref_cuda), rtol=1e-4, atol=1e-4)     # the CUDA reference is itself ~7e-5 from its CPU kernel
@@ -441,3 +442,77 @@ def test_multiscale_roi_align_fused_vs_reference(vb):
     out.square().sum().backward()
     for a, b_ in zip(fo, fr.values()):
         np.testing.assert_allclose(npy(a.grad), npy(b_.grad), rtol=1e-3, atol=1e-3 * max(1.0, b_.grad.abs().max().item()))
+
+
+# =============================== detection post-processing fused around NMS ===============================
+def _reference_tail(boxes, scores, labels, image_shape, score_thresh, inclusive, min_size, nms_thresh, topk):
+    """The per-image tail of roi_heads.py:700-737 / rpn.py:273-298, verbatim tensor ops (reference kernels)."""
+    from torchvision.ops import boxes as box_ops
+
+    boxes = box_ops.clip_boxes_to_image(boxes, image_shape)
+    inds = torch.where(scores >= score_thresh)[0] if inclusive else torch.where(scores > score_thresh)[0]
+    boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
+    keep = box_ops.remove_small_boxes(boxes, min_size=min_size)
+    boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
+    keep = box_ops.batched_nms(boxes, scores, labels, nms_thresh)[:topk]
+    return boxes[keep], scores[keep], labels[keep]
+
+
+@pytest.mark.parametrize("n,classes,topk,inclusive", [(90_000, 90, 100, False), (4000, 5, 1000, True), (300_000, 80, 2000, False), (50, 3, 10, True)])
+def test_detection_postprocess_fused_bit_exact_vs_reference_tail(vb, n, classes, topk, inclusive):
+    tv = pytest.importorskip("torchvision")
+    from vision_b200 import detection
+
+    assert not vb.installed()
+    g = torch.Generator().manual_seed(n)
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([1100.0, 820.0]) - 20.0          # some boxes stick out of the 800 x 1088 image
+    wh = torch.exp(torch.rand(n, 2, generator=g) * 6.0 - 3.0)                           # 0.05 .. 20 px .. 400 px: small boxes get removed
+    boxes = torch.cat([xy, xy + wh], dim=1).to(DEV)
+    scores = torch.rand(n, generator=g).to(DEV)
+    scores[::17] = 0.05                                                                  # exactly at the threshold: '>' vs '>='
+    labels = torch.randint(0, classes, (n,), generator=g).to(DEV)
+    ref = _reference_tail(boxes, scores, labels, (800, 1088), 0.05, inclusive, 1e-2, 0.5, topk)
+    before = vb.launch_count()
+    ours = detection.detection_postprocess(boxes, scores, labels, (800, 1088), 0.05, inclusive, 1e-2, 0.5, topk)
+    assert vb.launch_count() > before
+    for a, b in zip(ours, ref):
+        assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b)
+    # nothing survives the filters / empty input
+    none = detection.detection_postprocess(boxes[:100], scores[:100] * 0, labels[:100], (800, 1088), 0.5, False, 1e-2, 0.5, 10)
+    assert none[0].shape == (0, 4) and none[1].shape == (0,) and none[2].dtype == torch.int64
+
+
+# =============================== fused inference preprocessing (SURVEY §8f4) ===============================
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32, torch.float16])
+def test_classification_preset_fused_vs_reference(vb, dtype):
+    """ImageClassification.forward (transforms/_presets.py:57-64) on CUDA tensors: the fused kernel against the reference's
+    four passes.  uint8: the resized image is rounded to uint8 in the reference, so a value within ~1e-4 of a .5 tie may
+    round differently (summation order) - those differ by exactly 1/255/std; everything else agrees to 1e-5."""
+    tv = pytest.importorskip("torchvision")
+    from torchvision.transforms._presets import ImageClassification
+
+    assert not vb.installed()
+    g = torch.Generator().manual_seed(3)
+    for shape, crop, rs in (((4, 3, 375, 500), 224, 256), ((3, 600, 440), 224, 232), ((2, 1, 300, 300), 200, 256)):
+        c = shape[-3]
+        img = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8)
+        x = (img if dtype == torch.uint8 else (img.float() / 255).to(dtype)).to(DEV)
+        preset = ImageClassification(crop_size=crop, resize_size=rs, mean=(0.485, 0.456, 0.406)[:c], std=(0.229, 0.224, 0.225)[:c])
+        ref = preset(x)
+        vb.install()
+        try:
+            before = vb.launch_count()
+            ours = preset(x)
+            assert vb.launch_count() == before + 1                     # ONE kernel
+        finally:
+            vb.uninstall()
+        assert ours.shape == ref.shape and ours.dtype == torch.float32
+        diff = (ours - ref).abs()
+        if dtype == torch.uint8:
+            step = 1.0 / 255 / 0.224
+            off = diff > 1e-5
+            assert float(off.float().mean()) < 2e-3 and float(diff.max()) <= step * 1.05
+        elif dtype == torch.float16:
+            assert float((diff > 1e-5).float().mean()) < 2e-3 and float(diff.max()) <= 2e-3 / 0.224      # one fp16 ulp of a value <= 1 before normalisation
+        else:
+            np.testing.assert_allclose(npy(ours), npy(ref), rtol=1e-5, atol=2e-5)

@@ -114,6 +114,23 @@ def gpu_reference():
           "ours", timed(lambda: vb.transforms.resize(img, [224, 224], antialias=False), 5), flush=True)
 
 
+def postprocess():
+    import sys as _s
+    _s.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_round2 import _reference_tail
+    from vision_b200 import detection
+    g = torch.Generator().manual_seed(0)
+    n = 90_000                         # 1000 proposals x 90 classes, as RoIHeads.postprocess_detections sees them
+    xy = torch.rand(n, 2, generator=g) * torch.tensor([1000.0, 760.0]); wh = torch.rand(n, 2, generator=g) * 300 + 1
+    boxes = torch.cat([xy, xy + wh], 1).to(DEV); scores = (torch.rand(n, generator=g) ** 8).to(DEV); labels = (torch.arange(n) % 90).to(DEV)
+    t_ref = timed(lambda: _reference_tail(boxes, scores, labels, (800, 1088), 0.05, False, 1e-2, 0.5, 100), 10)
+    t_our = timed(lambda: detection.detection_postprocess(boxes, scores, labels, (800, 1088), 0.05, False, 1e-2, 0.5, 100), 20)
+    vb.install()
+    t_mid = timed(lambda: _reference_tail(boxes, scores, labels, (800, 1088), 0.05, False, 1e-2, 0.5, 100), 10)
+    vb.uninstall()
+    print("postprocess tail (90k candidates) ms: reference ops", t_ref, "reference ops + our batched_nms", t_mid, "fused", t_our, flush=True)
+
+
 def multiscale():
     from collections import OrderedDict
     from torchvision.ops import MultiScaleRoIAlign
@@ -142,5 +159,6 @@ if __name__ == "__main__":
         dcn_headroom()
     if which in ("all", "ms"):
         multiscale()
+        postprocess()
     if which in ("all", "ref"):
         gpu_reference()

@@ -10,7 +10,7 @@ The same ops are callable directly as ``vision_b200.ops.*`` / ``vision_b200.tran
 """
 from __future__ import annotations
 
-from . import _lib, ops, transforms  # noqa: F401
+from . import _lib, detection, ops, transforms  # noqa: F401
 from ._install import install, installed, uninstall  # noqa: F401
 
 __all__ = ["ops", "transforms", "install", "uninstall", "installed", "launch_count", "set_nms_semantics"]

@@ -8,7 +8,9 @@
    attribute is rebound (detection models call ``box_ops.batched_nms`` at call time).
 3. ``MultiScaleRoIAlign`` (torchvision/ops/poolers.py:147-228): the module-level ``_multiscale_roi_align`` is rebound
    to the fused kernel (device-side LevelMapper + one gather launch over all FPN levels) when the shape is covered.
-4. ``resize`` has no torchvision kernel (transforms/v2/functional/_geometry.py:283-362 calls
+4. detection post-processing: ``RoIHeads.postprocess_detections`` and ``RegionProposalNetwork.filter_proposals`` keep their
+   tensor prologue and run the per-image tail (clip, filters, batched_nms, top-k, gathers) as one fused call.
+5. ``resize`` has no torchvision kernel (transforms/v2/functional/_geometry.py:283-362 calls
    F.interpolate): the entries of ``_KERNEL_REGISTRY[resize]`` for Tensor / Image / Video are swapped.
 CPU tensors and unsupported dtypes/modes keep flowing to the reference implementation.
 """
@@ -68,6 +70,38 @@ def install() -> None:
 
     tv_poolers._multiscale_roi_align = _multiscale_roi_align
 
+    # ---- detection post-processing around batched_nms (roi_heads.py:680-737, rpn.py:242-298) ----
+    from torchvision.models.detection import roi_heads as tv_roi_heads, rpn as tv_rpn
+    from . import detection as _det
+
+    orig_pp = tv_roi_heads.RoIHeads.postprocess_detections
+    orig_fp = tv_rpn.RegionProposalNetwork.filter_proposals
+
+    def postprocess_detections(self, class_logits, box_regression, proposals, image_shapes):
+        if _det._fusable(class_logits) and not torchvision._is_tracing():
+            return _det.roi_heads_postprocess_detections(self, class_logits, box_regression, proposals, image_shapes, _orig=orig_pp)
+        return orig_pp(self, class_logits, box_regression, proposals, image_shapes)
+
+    def filter_proposals(self, proposals, objectness, image_shapes, num_anchors_per_level):
+        if _det._fusable(proposals) and not torchvision._is_tracing():
+            return _det.rpn_filter_proposals(self, proposals, objectness, image_shapes, num_anchors_per_level, _orig=orig_fp)
+        return orig_fp(self, proposals, objectness, image_shapes, num_anchors_per_level)
+
+    tv_roi_heads.RoIHeads.postprocess_detections = postprocess_detections
+    tv_rpn.RegionProposalNetwork.filter_proposals = filter_proposals
+
+    # ---- ImageClassification preset (transforms/_presets.py:57-64): resize + center_crop + to float + normalize fused ----
+    from torchvision.transforms import _presets as tv_presets
+
+    orig_preset_forward = tv_presets.ImageClassification.forward
+
+    def preset_forward(self, img):
+        if _tf.classification_preprocess_supported(img, self.crop_size, self.resize_size, self.interpolation, self.antialias):
+            return _tf.classification_preprocess(img, self.crop_size, self.resize_size, self.mean, self.std, self.interpolation, self.antialias)
+        return orig_preset_forward(self, img)
+
+    tv_presets.ImageClassification.forward = preset_forward
+
     # ---- resize ----
     registry = tv_utils._KERNEL_REGISTRY[tv_geo.resize]
     saved = dict(registry)
@@ -87,7 +121,9 @@ def install() -> None:
     registry[tv_tensors.Video] = tv_utils._kernel_tv_tensor_wrapper(resize_video)
 
     _state.update(dict(tv_boxes=tv_boxes, torchvision=torchvision, orig_batched_nms=orig_batched_nms,
-                       registry=registry, saved_registry=saved, tv_poolers=tv_poolers, orig_msra=orig_msra))
+                       registry=registry, saved_registry=saved, tv_poolers=tv_poolers, orig_msra=orig_msra,
+                       tv_roi_heads=tv_roi_heads, tv_rpn=tv_rpn, orig_pp=orig_pp, orig_fp=orig_fp,
+                       tv_presets=tv_presets, orig_preset_forward=orig_preset_forward))
 
 
 def uninstall() -> None:
@@ -97,6 +133,9 @@ def uninstall() -> None:
     _state["tv_boxes"].batched_nms = _state["orig_batched_nms"]
     _state["torchvision"].ops.batched_nms = _state["orig_batched_nms"]
     _state["tv_poolers"]._multiscale_roi_align = _state["orig_msra"]
+    _state["tv_presets"].ImageClassification.forward = _state["orig_preset_forward"]
+    _state["tv_roi_heads"].RoIHeads.postprocess_detections = _state["orig_pp"]
+    _state["tv_rpn"].RegionProposalNetwork.filter_proposals = _state["orig_fp"]
     reg = _state["registry"]
     reg.clear()
     reg.update(_state["saved_registry"])

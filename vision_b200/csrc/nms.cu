@@ -970,3 +970,135 @@ extern "C" int vb200_batched_nms(const void* boxes, const void* scores, const in
   return bnms_core<float>(boxes, scores, idxs, n, iou_threshold, semantics, strategy, wide_keys, workspace, workspace_bytes,
                           keep_out, num_keep_out, st);
 }
+
+// =====================================================================================================================
+// Detection post-processing fused around batched_nms.
+// Reference: torchvision/models/detection/roi_heads.py:700-737 (postprocess_detections, per image) and
+// rpn.py:273-298 (filter_proposals, per image): clip_boxes_to_image -> score filter -> remove_small_boxes ->
+// batched_nms -> keep[:top_k] -> index boxes / scores / labels.  The reference runs ~30 tiny tensor ops and 4-5 host
+// synchronisations per image; here: one clip+filter kernel, one compaction, the fused batched_nms pipeline above and one
+// gather - two synchronisations (candidate count: the reference's batched_nms strategy switch depends on it, boxes.py:86;
+// output count).  Arithmetic: clamp / subtract / compare in fp32 exactly as the tensor ops do.
+// =====================================================================================================================
+namespace vb200 {
+namespace {
+
+__global__ void det_clip_filter_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, float4* __restrict__ clipped,
+                                       uint8_t* __restrict__ flag, int n, float img_h, float img_w, float score_thresh,
+                                       int score_inclusive, float min_size) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 b = __ldg(boxes + i);
+  // boxes[..., 0::2].clamp(min=0, max=width), boxes[..., 1::2].clamp(min=0, max=height)  (ops/boxes.py clip_boxes_to_image)
+  b.x = fminf(fmaxf(b.x, 0.f), img_w); b.z = fminf(fmaxf(b.z, 0.f), img_w);
+  b.y = fminf(fmaxf(b.y, 0.f), img_h); b.w = fminf(fmaxf(b.w, 0.f), img_h);
+  clipped[i] = b;
+  const float s = scores[i];
+  const bool score_ok = score_inclusive ? (s >= score_thresh) : (s > score_thresh);
+  const bool size_ok = (sub_rn(b.z, b.x) >= min_size) && (sub_rn(b.w, b.y) >= min_size);     // remove_small_boxes
+  flag[i] = (score_ok && size_ok) ? 1 : 0;
+}
+
+__global__ void det_gather_candidates_kernel(const float4* __restrict__ clipped, const float* __restrict__ scores,
+                                             const int64_t* __restrict__ labels, const int* __restrict__ cand, const int* __restrict__ n_cand,
+                                             float4* __restrict__ cb, float* __restrict__ cs, int64_t* __restrict__ cl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_cand) return;
+  const int src = cand[i];
+  cb[i] = clipped[src]; cs[i] = scores[src]; cl[i] = labels[src];
+}
+
+__global__ void det_gather_topk_kernel(const float4* __restrict__ cb, const float* __restrict__ cs, const int64_t* __restrict__ cl,
+                                       const int64_t* __restrict__ keep, const int64_t* __restrict__ num_keep, int64_t topk,
+                                       float4* __restrict__ boxes_out, float* __restrict__ scores_out, int64_t* __restrict__ labels_out,
+                                       int64_t* __restrict__ count_out) {
+  const int64_t k = min(*num_keep, topk);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *count_out = k;
+  if (i >= k) return;
+  const int64_t src = keep[i];
+  boxes_out[i] = cb[src]; scores_out[i] = cs[src]; labels_out[i] = cl[src];
+}
+
+struct DetWs { float4* clipped; uint8_t* flag; int* iota; int* cand; int* n_cand; float4* cb; float* cs; int64_t* cl; int64_t* keep;
+               int64_t* num_keep; void* cub_temp; size_t cub_bytes; size_t bnms_off; size_t total; };
+DetWs carve_det(void* base, int64_t n) {
+  Carver c(base);
+  DetWs w;
+  w.clipped = c.take<float4>(n);
+  w.flag = c.take<uint8_t>(n);
+  w.iota = c.take<int>(n);
+  w.cand = c.take<int>(n);
+  w.n_cand = c.take<int>(64);
+  w.cb = c.take<float4>(n);
+  w.cs = c.take<float>(n);
+  w.cl = c.take<int64_t>(n);
+  w.keep = c.take<int64_t>(n);
+  w.num_keep = c.take<int64_t>(32);
+  w.cub_bytes = cub_temp_bytes(n);
+  w.cub_temp = c.take<char>(w.cub_bytes);
+  w.bnms_off = c.off;
+  c.off += carve_bnms(nullptr, n).total;
+  w.total = c.off;
+  return w;
+}
+}  // namespace
+}  // namespace vb200
+
+extern "C" size_t vb200_detection_postprocess_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return carve_det(nullptr, n).total;
+}
+
+extern "C" int vb200_detection_postprocess(const void* boxes, const void* scores, const int64_t* labels, int dtype, int64_t n,
+                                           double img_h, double img_w, double score_thresh, int score_inclusive, double min_size,
+                                           double iou_threshold, int64_t topk, int semantics, void* workspace,
+                                           size_t workspace_bytes, void* boxes_out, void* scores_out, int64_t* labels_out,
+                                           int64_t* count_host, vb200_stream stream) {
+  VB200_REQUIRE(dtype == VB200_F32, "detection_postprocess: float32 boxes only (got dtype %d)", dtype);
+  VB200_REQUIRE(n >= 0 && n < (1ll << 31) && topk >= 0, "detection_postprocess: bad sizes");
+  VB200_REQUIRE(count_host != nullptr, "detection_postprocess: null count_host");
+  VB200_REQUIRE(semantics == VB200_NMS_CPU || semantics == VB200_NMS_CUDA, "detection_postprocess: bad semantics selector");
+  *count_host = 0;
+  if (n == 0 || topk == 0) return 0;
+  VB200_REQUIRE(boxes && scores && labels && workspace && boxes_out && scores_out && labels_out, "detection_postprocess: null pointer");
+  VB200_REQUIRE(((uintptr_t)boxes % 16) == 0 && ((uintptr_t)boxes_out % 16) == 0, "detection_postprocess: boxes must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DetWs w = carve_det(workspace, n);
+  if (workspace_bytes < w.total) { set_error("detection_postprocess: workspace too small (%zu < %zu)", workspace_bytes, w.total); return VB200_EWORKSPACE; }
+  const int ni = (int)n, blk = 256, grd = ceil_div(ni, blk);
+  det_clip_filter_kernel<<<grd, blk, 0, st>>>((const float4*)boxes, (const float*)scores, w.clipped, w.flag, ni, (float)img_h, (float)img_w,
+                                             (float)score_thresh, score_inclusive, (float)min_size);
+  int rc = check_launch("det_clip_filter_kernel");
+  if (rc) return rc;
+  iota_kernel<<<grd, blk, 0, st>>>(w.iota, ni);
+  rc = check_launch("iota_kernel");
+  if (rc) return rc;
+  size_t tb = w.cub_bytes;
+  VB200_CUDA_TRY(cub::DeviceSelect::Flagged(w.cub_temp, tb, w.iota, w.flag, w.cand, w.n_cand, ni, st));
+  g_launch_count.fetch_add(2, std::memory_order_relaxed);
+  det_gather_candidates_kernel<<<grd, blk, 0, st>>>(w.clipped, (const float*)scores, labels, w.cand, w.n_cand, w.cb, w.cs, w.cl);
+  rc = check_launch("det_gather_candidates_kernel");
+  if (rc) return rc;
+  // the reference's strategy switch (boxes.py:86) looks at the number of candidates: one small read-back
+  int n_cand = 0;
+  VB200_CUDA_TRY(cudaMemcpyAsync(&n_cand, w.n_cand, sizeof(int), cudaMemcpyDeviceToHost, st));
+  VB200_CUDA_TRY(cudaStreamSynchronize(st));
+  if (n_cand == 0) return 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    rc = bnms_core<float>(w.cb, w.cs, w.cl, n_cand, iou_threshold, semantics, VB200_BNMS_AUTO, attempt == 1,
+                          (char*)workspace + w.bnms_off, workspace_bytes - w.bnms_off, w.keep, w.num_keep, st);
+    if (rc) return rc;
+    const int64_t cap = topk < (int64_t)n_cand ? topk : (int64_t)n_cand;
+    det_gather_topk_kernel<<<ceil_div((int)cap, blk), blk, 0, st>>>(w.cb, w.cs, w.cl, w.keep, w.num_keep, topk, (float4*)boxes_out,
+                                                                   (float*)scores_out, labels_out, w.num_keep + 1);
+    rc = check_launch("det_gather_topk_kernel");
+    if (rc) return rc;
+    int64_t hk[2] = {0, 0};
+    VB200_CUDA_TRY(cudaMemcpyAsync(hk, w.num_keep, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VB200_CUDA_TRY(cudaStreamSynchronize(st));
+    if (hk[0] >= 0) { *count_host = hk[1]; return 0; }        // -1: class ids outside [0, 65536) -> repeat with wide keys
+  }
+  set_error("detection_postprocess: internal error (negative kept count)");
+  return VB200_EINVAL;
+}

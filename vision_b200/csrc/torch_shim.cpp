@@ -17,6 +17,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/library.h>
 
+#include <algorithm>
 #include <atomic>
 #include <memory>
 
@@ -325,6 +326,31 @@ at::Tensor batched_nms(const at::Tensor& dets, const at::Tensor& scores, const a
   return keep.narrow(0, 0, k);
 }
 
+// ---- detection post-processing around batched_nms (roi_heads.py:700-737, rpn.py:273-298) ---------------------------
+std::tuple<at::Tensor, at::Tensor, at::Tensor> detection_postprocess(const at::Tensor& boxes, const at::Tensor& scores,
+                                                                     const at::Tensor& labels, double img_h, double img_w,
+                                                                     double score_thresh, bool score_inclusive, double min_size,
+                                                                     double nms_thresh, int64_t topk) {
+  check_nms_inputs(boxes, scores);
+  TORCH_CHECK(labels.is_cuda() && labels.dim() == 1 && labels.size(0) == boxes.size(0), "labels should be a 1d tensor with one entry per box");
+  TORCH_CHECK(boxes.scalar_type() == at::kFloat && scores.scalar_type() == at::kFloat, "detection_postprocess: float32 boxes and scores");
+  at::cuda::CUDAGuard guard(boxes.device());
+  const int64_t n = boxes.size(0);
+  const int64_t cap = std::min<int64_t>(n, std::max<int64_t>(topk, 0));
+  at::Tensor ob = at::empty({cap, 4}, boxes.options()), os = at::empty({cap}, scores.options());
+  at::Tensor ol = at::empty({cap}, boxes.options().dtype(at::kLong));
+  if (cap == 0) return std::make_tuple(ob, os, ol);
+  at::Tensor b = nms_operand(boxes, 16), s = nms_operand(scores, 4), l = labels.to(at::kLong).contiguous();
+  const size_t wsb = vb200_detection_postprocess_workspace_bytes(n);
+  at::Tensor ws = workspace(wsb, boxes);
+  int64_t count = 0;
+  check_rc(vb200_detection_postprocess(b.data_ptr(), s.data_ptr(), l.data_ptr<int64_t>(), VB200_F32, n, img_h, img_w, score_thresh,
+                                       score_inclusive ? 1 : 0, min_size, nms_thresh, topk, g_nms_semantics.load(), ws.data_ptr(), wsb,
+                                       ob.data_ptr(), os.data_ptr(), ol.data_ptr<int64_t>(), &count, cur_stream()),
+           "detection_postprocess");
+  return std::make_tuple(ob.narrow(0, 0, count), os.narrow(0, 0, count), ol.narrow(0, 0, count));
+}
+
 // ---- deform_conv2d ---------------------------------------------------------
 at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset,
                          const at::Tensor& mask, const at::Tensor& bias, int64_t stride_h, int64_t stride_w,
@@ -410,6 +436,27 @@ at::Tensor resize(const at::Tensor& input, int64_t out_h, int64_t out_w, int64_t
   return out;
 }
 
+// ---- fused inference preprocessing (transforms/_presets.py:57-64) -------------------------------------------------
+at::Tensor resize_crop_normalize(const at::Tensor& input, int64_t resize_h, int64_t resize_w, int64_t crop_top, int64_t crop_left,
+                                 int64_t crop_h, int64_t crop_w, int64_t mode, bool antialias, at::ArrayRef<double> mean,
+                                 at::ArrayRef<double> std) {
+  TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+  TORCH_CHECK(input.dim() == 4, "resize_crop_normalize: input must be [B, C, H, W]");
+  const int64_t B = input.size(0), C = input.size(1);
+  TORCH_CHECK((int64_t)mean.size() == C && (int64_t)std.size() == C && C <= 8, "resize_crop_normalize: one mean / std per channel (<= 8 channels)");
+  at::cuda::CUDAGuard guard(input.device());
+  at::Tensor in_c = input.contiguous();
+  at::Tensor out = at::empty({B, C, crop_h, crop_w}, input.options().dtype(at::kFloat));
+  if (out.numel() == 0) return out;
+  float m[8], sd[8];
+  for (int64_t c = 0; c < C; ++c) { m[c] = (float)mean[c]; sd[c] = (float)std[c]; }
+  check_rc(vb200_resize_crop_normalize(in_c.data_ptr(), out.data_ptr<float>(), dtype_code(in_c.scalar_type(), "resize_crop_normalize"), B,
+                                       (int)C, (int)input.size(2), (int)input.size(3), (int)resize_h, (int)resize_w, (int)crop_top,
+                                       (int)crop_left, (int)crop_h, (int)crop_w, (int)mode, antialias ? 1 : 0, m, sd, cur_stream()),
+           "resize_crop_normalize");
+  return out;
+}
+
 // ---- install / uninstall -----------------------------------------------------
 std::unique_ptr<torch::Library> g_override;
 
@@ -448,6 +495,8 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("ps_roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio) -> (Tensor, Tensor)");
   m.def("deform_conv2d(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> Tensor");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
+  m.def("resize_crop_normalize(Tensor input, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w, int mode, bool antialias, float[] mean, float[] std) -> Tensor");
+  m.def("detection_postprocess(Tensor boxes, Tensor scores, Tensor labels, float img_h, float img_w, float score_thresh, bool score_inclusive, float min_size, float nms_thresh, int topk) -> (Tensor, Tensor, Tensor)");
   m.def("multiscale_roi_align(Tensor[] features, Tensor rois, float[] scales, int pooled_height, int pooled_width, int sampling_ratio, int k_min, int k_max, float canonical_scale, float canonical_level, float eps) -> (Tensor, Tensor)");
   m.def("_roi_align_backward(Tensor grad, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width, int sampling_ratio, bool aligned) -> Tensor");
   m.def("_roi_pool_backward(Tensor grad, Tensor rois, Tensor argmax, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
@@ -473,4 +522,6 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   m.impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
   m.impl("multiscale_roi_align", TORCH_FN(multiscale_roi_align));
+  m.impl("detection_postprocess", TORCH_FN(detection_postprocess));
+  m.impl("resize_crop_normalize", TORCH_FN(resize_crop_normalize));
 }

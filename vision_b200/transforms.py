@@ -128,3 +128,52 @@ def resize(inpt: torch.Tensor, size, interpolation=InterpolationMode.BILINEAR, m
            antialias: Optional[bool] = True) -> torch.Tensor:
     """transforms.v2.functional.resize (_geometry.py:249-263) for plain tensors / tv_tensors.Image/Video."""
     return resize_image(inpt, size=size, interpolation=interpolation, max_size=max_size, antialias=antialias)
+
+
+# ---- fused inference preprocessing (SURVEY.md §8f4) ---------------------------------------------------------------
+def classification_preprocess_supported(img, crop_size, resize_size, interpolation, antialias) -> bool:
+    if not (isinstance(img, torch.Tensor) and img.is_cuda and img.dtype in _FUSED_DTYPES and img.dim() in (3, 4)):
+        return False
+    if img.shape[-3] > 8 or img.numel() == 0:
+        return False
+    try:
+        mode = _mode_value(interpolation)
+    except ValueError:
+        return False
+    if mode not in _MODE_CODE or antialias not in (True, False):
+        return False
+    if mode == "bicubic" and not antialias:
+        return False
+    h, w = img.shape[-2:]
+    rh, rw = compute_resized_output_size((h, w), size=list(resize_size))
+    ch, cw = _crop_hw(crop_size)
+    return ch <= rh and cw <= rw and (rh, rw) != (h, w)
+
+
+def _crop_hw(crop_size):
+    if isinstance(crop_size, int):
+        return crop_size, crop_size
+    if len(crop_size) == 1:
+        return int(crop_size[0]), int(crop_size[0])
+    return int(crop_size[0]), int(crop_size[1])
+
+
+def classification_preprocess(img: torch.Tensor, crop_size, resize_size, mean, std, interpolation=InterpolationMode.BILINEAR,
+                              antialias: Optional[bool] = True) -> torch.Tensor:
+    """ImageClassification.forward (torchvision/transforms/_presets.py:57-64) as ONE kernel: resize (shorter edge to
+    `resize_size`) -> center_crop(`crop_size`) -> convert_image_dtype(float) -> normalize(mean, std).  CUDA tensors
+    [C, H, W] or [B, C, H, W], uint8 / fp16 / bf16 / fp32; returns fp32."""
+    if not classification_preprocess_supported(img, crop_size, resize_size, interpolation, antialias):
+        raise RuntimeError("vision_b200.classification_preprocess: unsupported input (CUDA tensor, bilinear or bicubic+antialias, "
+                           "crop inside the resized image); use torchvision's preset for the rest")
+    _lib.load_ops()
+    squeeze = img.dim() == 3
+    x = img.unsqueeze(0) if squeeze else img
+    h, w = x.shape[-2:]
+    rh, rw = compute_resized_output_size((h, w), size=list(resize_size))
+    ch, cw = _crop_hw(crop_size)
+    top = int(round((rh - ch) / 2.0))          # transforms/functional.py center_crop
+    left = int(round((rw - cw) / 2.0))
+    out = torch.ops.vision_b200.resize_crop_normalize(x, rh, rw, top, left, ch, cw, _MODE_CODE[_mode_value(interpolation)], bool(antialias),
+                                                      [float(m) for m in mean], [float(s) for s in std])
+    return out.squeeze(0) if squeeze else out
