@@ -131,6 +131,16 @@ VB200_API int vb200_ps_roi_align_forward(const void* input, const void* rois, vo
                                int height, int width, int num_rois, int pooled_h, int pooled_w,
                                double spatial_scale, int sampling_ratio, vb200_stream stream);
 
+/* ---- ps_roi_pool (API completeness) --------------------
+ * Replaces ps_roi_pool_forward_kernel / ps_roi_pool_backward_kernel, csrc/ops/cuda/ps_roi_pool_kernel.cu:15-142
+ * (schemas csrc/ops/ps_roi_pool.cpp:71-73).  Shapes as ps_roi_align; the backward zero-fills grad_input itself. */
+VB200_API int vb200_ps_roi_pool_forward(const void* input, const void* rois, void* output, int32_t* channel_mapping, int dtype,
+                              int batch, int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                              double spatial_scale, vb200_stream stream);
+VB200_API int vb200_ps_roi_pool_backward(const void* grad, const void* rois, void* grad_input, int dtype, int batch, int channels,
+                               int height, int width, int num_rois, int pooled_h, int pooled_w, double spatial_scale,
+                               vb200_stream stream);
+
 /* ---- backward of the RoI ops --------------------------------------------
  * Replace roi_align_backward_kernel (csrc/ops/cuda/roi_align_kernel.cu:396-468, schema roi_align.cpp:76-77),
  * roi_pool_backward_kernel (cuda/roi_pool_kernel.cu:190-260, schema roi_pool.cpp:69-70) and

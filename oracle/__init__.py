@@ -121,6 +121,19 @@ def ps_roi_align(inp, rois, output_size, spatial_scale=1.0, sampling_ratio=-1):
     return out, cm
 
 
+def ps_roi_pool(inp, rois, output_size, spatial_scale=1.0):
+    inp, rois = _f32(inp), _f32(rois).reshape(-1, 5)
+    _, c, h, w = inp.shape
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else output_size
+    assert c % (ph * pw) == 0
+    k = rois.shape[0]
+    co = c // (ph * pw)
+    out = np.zeros((k, co, ph, pw), dtype=np.float32)
+    cm = np.zeros((k, co, ph, pw), dtype=np.int32)
+    lib().orc_ps_roi_pool_f32(_p(inp), _p(rois), c, h, w, k, ph, pw, ctypes.c_float(spatial_scale), _p(out), _p(cm))
+    return out, cm
+
+
 def deform_conv2d(inp, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
                   mask=None) -> np.ndarray:
     inp, offset, weight = _f32(inp), _f32(offset), _f32(weight)

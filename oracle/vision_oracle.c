@@ -730,3 +730,40 @@ ORC_API void orc_resize_f32(const float* input, int64_t planes, int in_h, int in
 }
 
 ORC_API int orc_abi_version(void) { return 1; }
+
+/* ------------------------------------------------------------------------ */
+/* ps_roi_pool — torchvision/csrc/ops/cpu/ps_roi_pool_kernel.cpp:15-88       */
+/* (forward; bin windows clipped to size - 1 as the reference does).         */
+/* ------------------------------------------------------------------------ */
+ORC_API void orc_ps_roi_pool_f32(const float* input, const float* rois, int channels, int height, int width,
+                                 int num_rois, int pooled_height, int pooled_width, float spatial_scale,
+                                 float* output, int32_t* channel_mapping) {
+  const int channels_out = channels / (pooled_height * pooled_width);
+  for (int n = 0; n < num_rois; ++n) {
+    const float* r = rois + n * 5;
+    int b = (int)r[0];
+    int rsw = (int)roundf(r[1] * spatial_scale), rsh = (int)roundf(r[2] * spatial_scale);
+    int rew = (int)roundf(r[3] * spatial_scale), reh = (int)roundf(r[4] * spatial_scale);
+    int rw = imax_(rew - rsw, 1), rh = imax_(reh - rsh, 1);
+    float bh = (float)rh / (float)pooled_height, bw = (float)rw / (float)pooled_width;
+    int c_in = 0;
+    for (int co = 0; co < channels_out; ++co)
+      for (int ph = 0; ph < pooled_height; ++ph)
+        for (int pw = 0; pw < pooled_width; ++pw) {
+          int hs = (int)floorf((float)ph * bh), ws = (int)floorf((float)pw * bw);
+          int he = (int)ceilf((float)(ph + 1) * bh), we = (int)ceilf((float)(pw + 1) * bw);
+          hs = imin_(imax_(hs + rsh, 0), height - 1); he = imin_(imax_(he + rsh, 0), height - 1);
+          ws = imin_(imax_(ws + rsw, 0), width - 1); we = imin_(imax_(we + rsw, 0), width - 1);
+          int empty = (he <= hs) || (we <= ws);
+          const float* in = input + ((int64_t)b * channels + c_in) * height * width;
+          float sum = 0.f;
+          for (int h = hs; h < he; ++h)
+            for (int w = ws; w < we; ++w) sum += in[h * width + w];
+          float area = (float)((he - hs) * (we - ws));
+          int64_t idx = (((int64_t)n * channels_out + co) * pooled_height + ph) * pooled_width + pw;
+          output[idx] = empty ? 0.f : sum / area;
+          channel_mapping[idx] = c_in;
+          ++c_in;
+        }
+  }
+}

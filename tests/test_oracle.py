@@ -207,6 +207,9 @@ def test_roi_ops_random_shapes_live(oracle, seed):
     assert np.array_equal(m, m_ref.numpy())
     np.testing.assert_array_equal(np.nan_to_num(o, nan=7.0, posinf=8.0, neginf=9.0),
                                   np.nan_to_num(o_ref.numpy(), nan=7.0, posinf=8.0, neginf=9.0))
+    o_ref, m_ref = torch.ops.torchvision.ps_roi_pool(xp, r, scale, ph, pw)                 # cpu/ps_roi_pool_kernel.cpp
+    o, m = oracle.ps_roi_pool(xp.numpy(), r.numpy(), (ph, pw), scale)
+    assert np.array_equal(m, m_ref.numpy()) and np.array_equal(o, o_ref.numpy())
 
 
 @pytest.mark.parametrize("seed", range(4))

@@ -102,6 +102,31 @@ def register() -> None:
           width):
         return grad.new_empty((batch_size, channels, height, width))
 
+    # ---- ps_roi_pool ----
+    def ps_roi_pool_setup(ctx, inputs, output):
+        inp, rois, scale, ph, pw = inputs
+        ctx.save_for_backward(rois, output[1])
+        ctx.mark_non_differentiable(output[1])
+        ctx.in_shape = tuple(inp.shape)
+        ctx.args = (scale, ph, pw)
+
+    def ps_roi_pool_backward(ctx, grad, _grad_mapping):
+        rois, mapping = ctx.saved_tensors
+        scale, ph, pw = ctx.args
+        b, c, h, w = ctx.in_shape
+        return ops._ps_roi_pool_backward(grad, rois, mapping, scale, ph, pw, b, c, h, w), None, None, None, None
+
+    lib.register_autograd("vision_b200::ps_roi_pool", ps_roi_pool_backward, setup_context=ps_roi_pool_setup)
+
+    @lib.register_fake("vision_b200::ps_roi_pool")
+    def _(inp, rois, spatial_scale, pooled_height, pooled_width):
+        shape = (rois.size(0), inp.size(1) // (pooled_height * pooled_width), pooled_height, pooled_width)
+        return inp.new_empty(shape), inp.new_empty(shape, dtype=torch.int32)
+
+    @lib.register_fake("vision_b200::_ps_roi_pool_backward")
+    def _(grad, rois, channel_mapping, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width):
+        return grad.new_empty((batch_size, channels, height, width))
+
     # ---- fused MultiScaleRoIAlign: gradients per level through _roi_align_backward on that level's RoIs ----
     def ms_setup(ctx, inputs, output):
         feats, rois, scales, ph, pw, sr = inputs[:6]

@@ -662,6 +662,250 @@ deform_conv2d_tc2_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpack
   if (warp == TC_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
 }
 
+// =================================================================================================
+// fp32 inputs on the tensor core: three-way bf16 split (bf16x3).
+// A float v is v1 + v2 + v3 with v1 = bf16(v), v2 = bf16(v - v1), v3 = bf16(v - v1 - v2) (8 + 8 + 8 mantissa bits); the
+// product a*b is a1b1 + (a1b2 + a2b1) + (a2b2 + a1b3 + a3b1) + O(2^-24): SIX kind::f16 MMAs per K step into the same fp32
+// TMEM accumulator reproduce the fp32 result to ~1e-7 relative per product - inside the 1e-5 budget of the fp32 rows,
+// at 6x the bf16 tensor time, which is still several times faster than a SIMT fp32 implicit GEMM (or the reference's
+// im2col + SGEMM).  Same structure as deform_conv2d_tc_kernel: M = 128 pixels, N = BN couts, K step 32 channels
+// (SWIZZLE_64B); a stage holds A1 A2 A3 (8 KB each) and B1 B2 B3 (BN x 64 B each); the gather reads a channels-last
+// fp32 staging copy (one 128-byte line = 32 channels per pixel corner), blends in fp32 and writes the three splits.
+// =================================================================================================
+constexpr int T3_KB = 32, T3_STAGES = 2;
+constexpr int T3_ROW = 2 * T3_KB;                 // 64-byte tile rows
+constexpr int T3_A = TC_BM * T3_ROW;              // 8 KB per A split
+
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(a);      // exact: the residual has at most 16 significant bits
+  b = __float2bfloat16_rn(r1);
+  c = __float2bfloat16_rn(r1 - __bfloat162float(b));
+}
+
+// weights [Cout][Cin][KK] fp32 -> per (n tile, stage q = cslab32 * KK + tap): B1 | B2 | B3 swizzled tiles of BN x 32
+__global__ void __launch_bounds__(256)
+pack_weights3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, int Cout, int Cin, int KK, int BN) {
+  const int64_t total = (int64_t)Cout * Cin * KK;
+  const int n_q = (Cin / T3_KB) * KK;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % KK);
+    const int ci = (int)((e / KK) % Cin);
+    const int co = (int)(e / KK / Cin);
+    const int nt = co / BN, r = co % BN;
+    const int cslab = ci / T3_KB, kc = ci % T3_KB;
+    const int q = cslab * KK + tap;
+    const int64_t stage_base = ((int64_t)nt * n_q + q) * 3 * BN * T3_KB;            // elements
+    const int off = (r * T3_ROW + (((kc >> 3) ^ tc_swz<T3_KB>(r)) << 4) + ((kc & 7) << 1)) >> 1;
+    __nv_bfloat16 b1, b2, b3;
+    split3(w[e], b1, b2, b3);
+    packed[stage_base + off] = b1;
+    packed[stage_base + (int64_t)BN * T3_KB + off] = b2;
+    packed[stage_base + (int64_t)2 * BN * T3_KB + off] = b3;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC1_THREADS, 1)
+deform_conv2d_tc3_kernel(const float* __restrict__ nhwc, const __nv_bfloat16* __restrict__ wpacked, const float* __restrict__ offset,
+                         const float* __restrict__ mask, const float* __restrict__ bias, float* __restrict__ out, DcnParams p) {
+  constexpr int B_BYTES = BN * T3_ROW;                    // one B split
+  constexpr int STAGE_BYTES = 3 * T3_A + 3 * B_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* stages = smem;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(stages + T3_STAGES * STAGE_BYTES);
+  uint64_t* fullB = fullA + T3_STAGES;
+  uint64_t* empty = fullB + T3_STAGES;
+  uint64_t* accum_full = empty + T3_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  TcEnt* tab = reinterpret_cast<TcEnt*>(stages + ((T3_STAGES * STAGE_BYTES + (3 * T3_STAGES + 1) * 8 + 16 + 31) & ~31));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KK = p.kh * p.kw;
+  const int HWo = p.out_h * p.out_w, HWi = p.in_h * p.in_w;
+  const int tiles_per_img = ceil_div(HWo, TC_BM);
+  const int b = blockIdx.x / tiles_per_img;
+  const int pix0 = (blockIdx.x % tiles_per_img) * TC_BM;
+  const int nt = blockIdx.y;
+  const int c_per_off = p.c_in / p.offset_groups;
+  const int slabs_per_og = (c_per_off / T3_KB) * KK;      // 32-channel gather steps per offset group
+  const int n_q = (p.c_in / T3_KB) * KK;                  // stages consumed per tile
+
+  if (tid == 0) {
+    for (int s = 0; s < T3_STAGES; ++s) { mbar_init(&fullA[s], TC_GATHER_WARPS); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == TC1_GATHER_WARPS + 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC1_GATHER_WARPS) {
+    // two groups of 8 gather warps take alternate 32-channel steps
+    const int group = warp >> 3, wg = warp & 7;
+    const int cchunk = lane & 7, pq = lane >> 3;           // lane -> (pixel sub-index, 4-channel chunk of the 32-channel line)
+    const int prow0 = wg * 16 + pq;
+    const float* __restrict__ in_b = nhwc + (int64_t)b * HWi * p.c_in;
+    for (int og = 0; og < p.offset_groups; ++og) {
+      asm volatile("bar.sync 1, %0;" ::"n"(TC1_GATHER_THREADS));
+      const float* __restrict__ off_b = offset + ((int64_t)b * p.offset_groups + og) * 2 * KK * HWo;
+      const float* __restrict__ msk_b = p.use_mask ? mask + ((int64_t)b * p.offset_groups + og) * KK * HWo : nullptr;
+      for (int e = tid; e < KK * TC_BM; e += TC1_GATHER_THREADS) {
+        const int tap = e / TC_BM, px = e - tap * TC_BM;
+        const int pix = pix0 + px;
+        TcEnt se;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { se.o[q] = 0; se.w[q] = 0.f; }
+        if (pix < HWo) {
+          const int oy = pix / p.out_w, ox = pix - oy * p.out_w;
+          const int i = tap / p.kw, j = tap - i * p.kw;
+          const float oh = off_b[(int64_t)(2 * tap) * HWo + pix];
+          const float ow = off_b[(int64_t)(2 * tap + 1) * HWo + pix];
+          const float mv = p.use_mask ? msk_b[(int64_t)tap * HWo + pix] : 1.f;
+          const float y = add_rn((float)(oy * p.stride_h - p.pad_h + i * p.dil_h), oh);
+          const float x = add_rn((float)(ox * p.stride_w - p.pad_w + j * p.dil_w), ow);
+          if (!(y <= -1.f || (float)p.in_h <= y || x <= -1.f || (float)p.in_w <= x)) {
+            const int hl = (int)floorf(y), wl = (int)floorf(x);
+            const int hh_i = hl + 1, wh_i = wl + 1;
+            const float lh = y - (float)hl, lw = x - (float)wl;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const bool t0 = hl >= 0, t1 = hh_i <= p.in_h - 1, l0 = wl >= 0, l1 = wh_i <= p.in_w - 1;
+            const int hlc = max(hl, 0), hhc = min(hh_i, p.in_h - 1), wlc = max(wl, 0), whc = min(wh_i, p.in_w - 1);
+            se.o[0] = (hlc * p.in_w + wlc) * p.c_in * 4; se.w[0] = (t0 && l0) ? mv * (hh * hw) : 0.f;
+            se.o[1] = (hlc * p.in_w + whc) * p.c_in * 4; se.w[1] = (t0 && l1) ? mv * (hh * lw) : 0.f;
+            se.o[2] = (hhc * p.in_w + wlc) * p.c_in * 4; se.w[2] = (t1 && l0) ? mv * (lh * hw) : 0.f;
+            se.o[3] = (hhc * p.in_w + whc) * p.c_in * 4; se.w[3] = (t1 && l1) ? mv * (lh * lw) : 0.f;
+          }
+        }
+        tab[e] = se;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC1_GATHER_THREADS));
+      const int slab_base = og * slabs_per_og;
+      for (int sl = (slab_base + group) & 1; sl < slabs_per_og; sl += 2) {
+        const int q = slab_base + sl;
+        const int cs_local = sl / KK, tap = sl - cs_local * KK;
+        const char* __restrict__ in_c = reinterpret_cast<const char*>(in_b + og * c_per_off + cs_local * T3_KB);
+        const uint32_t lane_off = (uint32_t)cchunk * 16u;
+        float4 v[4][4];
+        float4 wq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const TcEnt* se = tab + tap * TC_BM + prow0 + 4 * i;
+          const uint4 o = *reinterpret_cast<const uint4*>(se->o);
+          wq[i] = *reinterpret_cast<const float4*>(se->w);
+          v[i][0] = __ldg(reinterpret_cast<const float4*>(in_c + (o.x + lane_off)));
+          v[i][1] = __ldg(reinterpret_cast<const float4*>(in_c + (o.y + lane_off)));
+          v[i][2] = __ldg(reinterpret_cast<const float4*>(in_c + (o.z + lane_off)));
+          v[i][3] = __ldg(reinterpret_cast<const float4*>(in_c + (o.w + lane_off)));
+        }
+        mbar_wait(&empty[q % T3_STAGES], ((uint32_t)(q / T3_STAGES) & 1u) ^ 1u);
+        unsigned char* a_tile = stages + (q % T3_STAGES) * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // fp32 blend in the reference's tap order (w1 v1 + w2 v2 + w3 v3 + w4 v4, deform_conv2d_kernel.cu:128-133)
+          float r[4];
+          r[0] = wq[i].x * v[i][0].x + wq[i].y * v[i][1].x + wq[i].z * v[i][2].x + wq[i].w * v[i][3].x;
+          r[1] = wq[i].x * v[i][0].y + wq[i].y * v[i][1].y + wq[i].z * v[i][2].y + wq[i].w * v[i][3].y;
+          r[2] = wq[i].x * v[i][0].z + wq[i].y * v[i][1].z + wq[i].z * v[i][2].z + wq[i].w * v[i][3].z;
+          r[3] = wq[i].x * v[i][0].w + wq[i].y * v[i][1].w + wq[i].z * v[i][2].w + wq[i].w * v[i][3].w;
+          __nv_bfloat16 s1[4], s2[4], s3[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) split3(r[k], s1[k], s2[k], s3[k]);
+          const int prow = prow0 + 4 * i;
+          // this lane's 4 channels are half of a 16-byte chunk: chunk (cchunk >> 1), byte half (cchunk & 1)
+          const int boff = prow * T3_ROW + ((((cchunk >> 1) ^ tc_swz<T3_KB>(prow)) << 4) | ((cchunk & 1) << 3));
+          *reinterpret_cast<uint2*>(a_tile + boff) = *reinterpret_cast<const uint2*>(s1);
+          *reinterpret_cast<uint2*>(a_tile + T3_A + boff) = *reinterpret_cast<const uint2*>(s2);
+          *reinterpret_cast<uint2*>(a_tile + 2 * T3_A + boff) = *reinterpret_cast<const uint2*>(s3);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&fullA[q % T3_STAGES]);
+      }
+    }
+    // ================= epilogue: TMEM -> registers -> NCHW fp32 =================
+    mbar_wait(accum_full, 0u);
+    tc_fence_after();
+    const int lane_base = (warp & 3) * 32;
+    const int col_q = warp >> 2;
+    const int pix = pix0 + lane_base + lane;
+    constexpr int COLS_PER_WARP = BN / (TC1_GATHER_WARPS / 4);
+#pragma unroll 1
+    for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
+      const int col = col_q * COLS_PER_WARP + c0;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
+      if (pix < HWo) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = nt * BN + col + j;
+          out[((int64_t)b * p.c_out + co) * HWo + pix] = __uint_as_float(r[j]) + (bias ? bias[co] : 0.f);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == TC1_GATHER_WARPS) {
+    if (lane == 0) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(wpacked) + (int64_t)nt * n_q * 3 * B_BYTES;
+      for (int q = 0; q < n_q; ++q) {
+        const int st = q % T3_STAGES;
+        const uint32_t ph = (uint32_t)(q / T3_STAGES) & 1u;
+        mbar_wait(&empty[st], ph ^ 1u);
+        mbar_expect_tx(&fullB[st], (uint32_t)(3 * B_BYTES));
+        bulk_g2s(stages + st * STAGE_BYTES + 3 * T3_A, wsrc + (int64_t)q * 3 * B_BYTES, (uint32_t)(3 * B_BYTES), &fullB[st]);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // bf16 x bf16 -> fp32
+      for (int q = 0; q < n_q; ++q) {
+        const int st = q % T3_STAGES;
+        const uint32_t ph = (uint32_t)(q / T3_STAGES) & 1u;
+        mbar_wait(&fullA[st], ph);
+        mbar_wait(&fullB[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(stages + st * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + 3 * T3_A;
+        // small terms first (a3b1, a1b3, a2b2), then the first-order cross terms, then a1b1
+        constexpr int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+#pragma unroll
+          for (int k = 0; k < T3_KB / 16; ++k)
+            umma_f16(tmem_base, smem_desc_k<T3_KB>(a_addr + ia[t] * T3_A + k * 32), smem_desc_k<T3_KB>(b_addr + ib[t] * B_BYTES + k * 32),
+                     idesc, (q | t | k) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(accum_full);
+    }
+  }
+  __syncthreads();
+  if (warp == TC1_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+}
+
+size_t tc3_smem_bytes(int BN, int KK) {
+  return (size_t)T3_STAGES * (3 * T3_A + 3 * BN * T3_ROW) + 128 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
+}
+int tc3_pick_bn(const DcnParams& p) {
+  const int KK = p.kh * p.kw;
+  const int cands[2] = {256, 128};
+  for (int c = 0; c < 2; ++c)
+    if (p.c_out % cands[c] == 0 && tc3_smem_bytes(cands[c], KK) <= (size_t)max_smem_optin()) return cands[c];
+  return 0;
+}
+bool tc3_eligible(int dtype, const DcnParams& p) {
+  if (dtype != VB200_F32 || p.groups != 1) return false;
+  if (p.c_in % p.offset_groups != 0 || (p.c_in / p.offset_groups) % T3_KB != 0) return false;
+  if (p.c_out % 128 != 0 || tc3_pick_bn(p) == 0) return false;
+  if ((int64_t)p.in_h * p.in_w * p.c_in * 4 >= (1ll << 31)) return false;      // 32-bit byte offsets into one image
+  const char* env = env_override(ENV_DCN_PATH);
+  if (env && env[0] == 's') return false;
+  return true;
+}
+
 size_t tc2_smem_bytes(int KK) {
   return (size_t)TC2_STAGES * (TC_BM + 256) * 128 + 256 + (size_t)KK * TC_BM * sizeof(TcEnt) + 1024;
 }
@@ -720,10 +964,8 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
   const size_t nhwc_bytes = align256((size_t)p.batch * HWi * p.c_in * sizeof(T));
   const size_t w_bytes = align256((size_t)p.c_out * p.c_in * KK * sizeof(T));
-  if (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0) {
-    set_error("deform_conv2d: tensor-core path needs %zu bytes of 256-byte aligned workspace", nhwc_bytes + w_bytes);
-    return VB200_EWORKSPACE;
-  }
+  if (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0)
+    return 0;       // no usable workspace: the SIMT kernel serves the call (a C-ABI caller may pass none)
   T* nhwc = (T*)workspace;
   T* wpacked = (T*)((char*)workspace + nhwc_bytes);
   if (HWi % 2 == 0 && p.c_in % 64 == 0 && ((uintptr_t)input % 4) == 0) {
@@ -774,7 +1016,40 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
 
 }  // namespace
 
+int launch_tc3(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
+               const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
+  const size_t nhwc_bytes = align256((size_t)p.batch * HWi * p.c_in * 4);
+  const size_t w_bytes = align256((size_t)p.c_out * p.c_in * KK * 3 * 2);
+  if (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0) return 0;   // SIMT kernel serves the call
+  float* nhwc = (float*)workspace;
+  __nv_bfloat16* wpacked = (__nv_bfloat16*)((char*)workspace + nhwc_bytes);
+  dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
+  nchw_to_nhwc_kernel<float><<<tg, 256, 0, st>>>((const float*)input, nhwc, p.c_in, HWi);
+  int rc = check_launch("nchw_to_nhwc_kernel");
+  if (rc) return rc;
+  const int BN = tc3_pick_bn(p);
+  pack_weights3_kernel<<<sm_count() * 4, 256, 0, st>>>((const float*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+  rc = check_launch("pack_weights3_kernel");
+  if (rc) return rc;
+  dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
+  const size_t smem = tc3_smem_bytes(BN, KK);
+  if (BN == 256) {
+    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc3_kernel<256>>(smem));
+    deform_conv2d_tc3_kernel<256><<<grid, TC1_THREADS, smem, st>>>(nhwc, wpacked, (const float*)offset, (const float*)mask,
+                                                                  (const float*)bias, (float*)out, p);
+  } else {
+    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc3_kernel<128>>(smem));
+    deform_conv2d_tc3_kernel<128><<<grid, TC1_THREADS, smem, st>>>(nhwc, wpacked, (const float*)offset, (const float*)mask,
+                                                                  (const float*)bias, (float*)out, p);
+  }
+  rc = check_launch("deform_conv2d_tc3_kernel");
+  return rc ? rc : 1;
+}
+
 size_t deform_conv2d_tc_workspace(int dtype, const DcnParams& p) {
+  if (tc3_eligible(dtype, p))
+    return align256((size_t)p.batch * p.in_h * p.in_w * p.c_in * 4) + align256((size_t)p.c_out * p.c_in * p.kh * p.kw * 6);
   if (!tc_eligible(dtype, p)) return 0;
   const size_t nhwc = align256((size_t)p.batch * p.in_h * p.in_w * p.c_in * 2);
   const size_t w = align256((size_t)p.c_out * p.c_in * p.kh * p.kw * 2);
@@ -783,6 +1058,7 @@ size_t deform_conv2d_tc_workspace(int dtype, const DcnParams& p) {
 
 int deform_conv2d_tc_try(const void* input, const void* weight, const void* offset, const void* mask, const void* bias,
                          void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (tc3_eligible(dtype, p)) return launch_tc3(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);
   if (!tc_eligible(dtype, p)) return 0;
   if (dtype == VB200_BF16)
     return launch_tc<__nv_bfloat16>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);

@@ -791,6 +791,92 @@ ps_roi_align_plane_kernel(const T* __restrict__ input, const T* __restrict__ roi
   }
 }
 
+// ---------------------------------------------------------------------------
+// ps_roi_pool (reference semantics: csrc/ops/cuda/ps_roi_pool_kernel.cu:15-78).  Same organisation as ps_roi_align:
+// input plane c_in serves bin (ph, pw) of output channel c_out for every RoI, so a CTA holds the plane and its threads
+// are the RoIs; each averages its bin window (integer bounds, clipped to size - 1 as the reference's forward does).
+// The window is summed in the reference's order (rows, then columns, one rounding per add).
+// ---------------------------------------------------------------------------
+template <typename T, bool RESIDENT>
+__global__ void __launch_bounds__(RESIDENT ? 1024 : 256, RESIDENT ? 1 : 4)
+ps_roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
+                         int32_t* __restrict__ mapping, int B, int C, int H, int W, int K, int PH, int PW, int Cout,
+                         typename Acc<T>::type scale) {
+  using A = typename Acc<T>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* plane_s = reinterpret_cast<T*>(smem_raw);
+  const int64_t total = (int64_t)B * C * K;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t w0 = (int64_t)blockIdx.x * per, w1 = min(total, w0 + per);
+  int64_t w = w0;
+  while (w < w1) {
+    const int pl = (int)(w / K);
+    const int r0 = (int)(w - (int64_t)pl * K);
+    const int r1 = (int)min((int64_t)K, r0 + (w1 - w));
+    const int b = pl / C, c_in = pl - b * C;
+    const int pw = c_in % PW, ph = (c_in / PW) % PH, co = c_in / (PW * PH);
+    const T* __restrict__ plane = input + (int64_t)pl * H * W;
+    if (RESIDENT) {
+      __syncthreads();
+      stage_plane_flat<T>(plane_s, plane, H * W);
+      __syncthreads();
+      plane = plane_s;
+    }
+    for (int n = r0 + (int)threadIdx.x; n < r1; n += (int)blockDim.x) {
+      const T* __restrict__ r = rois + (int64_t)n * 5;
+      if ((int)to_acc(r[0]) != b) continue;
+      const A sc = rnd<T>(scale);
+      const int rsw = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[1]), sc))), rsh = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[2]), sc)));
+      const int rew = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[3]), sc))), reh = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[4]), sc)));
+      const int rw = max(rew - rsw, 1), rh = max(reh - rsh, 1);               // too small RoIs become 1x1
+      const A bh = rnd<T>(div_rn(rnd<T>((A)rh), rnd<T>((A)PH))), bw = rnd<T>(div_rn(rnd<T>((A)rw), rnd<T>((A)PW)));
+      int hs = (int)floor(rnd<T>(mul_rn(rnd<T>((A)ph), bh))), ws = (int)floor(rnd<T>(mul_rn(rnd<T>((A)pw), bw)));
+      int he = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(ph + 1)), bh))), we = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(pw + 1)), bw)));
+      hs = min(max(hs + rsh, 0), H - 1); he = min(max(he + rsh, 0), H - 1);
+      ws = min(max(ws + rsw, 0), W - 1); we = min(max(we + rsw, 0), W - 1);
+      const bool empty = (he <= hs) || (we <= ws);
+      A sum = 0;
+      for (int h = hs; h < he; ++h)
+        for (int x = ws; x < we; ++x) sum = rnd<T>(add_rn(sum, (A)to_acc(plane[h * W + x])));
+      const A area = rnd<T>((A)((he - hs) * (we - ws)));
+      const int64_t o = (((int64_t)n * Cout + co) * PH + ph) * PW + pw;
+      output[o] = from_acc<T, A>(empty ? (A)0 : rnd<T>(div_rn(sum, area)));
+      mapping[o] = c_in;
+    }
+    w += (r1 - r0);
+  }
+}
+
+// backward of ps_roi_pool (ps_roi_pool_kernel.cu:80-142): grad / bin_area spread over the bin window (clipped to the
+// full size here, as the reference's backward does) - an atomic scatter, one thread per (RoI, output element).
+template <typename T>
+__global__ void __launch_bounds__(256)
+ps_roi_pool_bwd_kernel(const T* __restrict__ grad, const T* __restrict__ rois, T* __restrict__ grad_input, int64_t total, int C,
+                       int H, int W, int PH, int PW, int Cout, typename Acc<T>::type scale) {
+  using A = typename Acc<T>::type;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pw = (int)(i % PW), ph = (int)((i / PW) % PH), co = (int)((i / PW / PH) % Cout);
+    const int64_t n = i / PW / PH / Cout;
+    const T* __restrict__ r = rois + n * 5;
+    const int b = (int)to_acc(r[0]);
+    const A sc = rnd<T>(scale);
+    const int rsw = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[1]), sc))), rsh = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[2]), sc)));
+    const int rew = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[3]), sc))), reh = (int)roundf((float)rnd<T>(mul_rn((A)to_acc(r[4]), sc)));
+    const int rw = max(rew - rsw, 1), rh = max(reh - rsh, 1);
+    const A bh = rnd<T>(div_rn(rnd<T>((A)rh), rnd<T>((A)PH))), bw = rnd<T>(div_rn(rnd<T>((A)rw), rnd<T>((A)PW)));
+    int hs = (int)floor(rnd<T>(mul_rn(rnd<T>((A)ph), bh))), ws = (int)floor(rnd<T>(mul_rn(rnd<T>((A)pw), bw)));
+    int he = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(ph + 1)), bh))), we = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(pw + 1)), bw)));
+    hs = min(max(hs + rsh, 0), H); he = min(max(he + rsh, 0), H);
+    ws = min(max(ws + rsw, 0), W); we = min(max(we + rsw, 0), W);
+    if (he <= hs || we <= ws) continue;
+    const int c_in = (co * PH + ph) * PW + pw;
+    const A v = rnd<T>(div_rn((A)to_acc(grad[i]), rnd<T>((A)((he - hs) * (we - ws)))));
+    T* __restrict__ gi = grad_input + ((int64_t)b * C + c_in) * H * W;
+    for (int h = hs; h < he; ++h)
+      for (int x = ws; x < we; ++x) atomicAdd(gi + h * W + x, from_acc<T, A>(v));
+  }
+}
+
 template <typename T>
 int launch_roi_align_generic(const void* input, const void* rois, void* output, int C, int H, int W, int K,
                              int PH, int PW, double scale, int sr, int aligned, cudaStream_t st) {
@@ -1112,4 +1198,72 @@ extern "C" int vb200_ps_roi_align_forward(const void* input, const void* rois, v
   }
   set_error("ps_roi_align: unsupported dtype %d", dtype);
   return VB200_EUNSUPPORTED;
+}
+
+template <typename T>
+static int launch_ps_roi_pool(const void* input, const void* rois, void* output, int32_t* mapping, int B, int C, int H, int W, int K,
+                              int PH, int PW, double scale, cudaStream_t st) {
+  using A = typename Acc<T>::type;
+  const int Cout = C / (PH * PW);
+  const int64_t pairs = (int64_t)B * C * K;
+  if (pairs == 0 || Cout == 0) return 0;
+  const bool resident = plane_resident_ok<T>(H, W, (int64_t)K * 64 * (int64_t)sizeof(T) / (B > 1 ? B : 1));
+  if (resident) {
+    const size_t smem = (size_t)H * W * sizeof(T) + 16;
+    const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+    VB200_CUDA_TRY(ensure_dyn_smem<ps_roi_pool_plane_kernel<T, true>>(smem));
+    ps_roi_pool_plane_kernel<T, true><<<grid, 1024, smem, st>>>((const T*)input, (const T*)rois, (T*)output, mapping, B, C, H, W, K, PH,
+                                                               PW, Cout, (A)scale);
+  } else {
+    const int64_t want = ceil_div64(pairs, 256);
+    const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+    ps_roi_pool_plane_kernel<T, false><<<grid, 256, 0, st>>>((const T*)input, (const T*)rois, (T*)output, mapping, B, C, H, W, K, PH, PW,
+                                                            Cout, (A)scale);
+  }
+  return check_launch("ps_roi_pool_plane_kernel");
+}
+
+extern "C" int vb200_ps_roi_pool_forward(const void* input, const void* rois, void* output, int32_t* channel_mapping, int dtype,
+                                         int batch, int channels, int height, int width, int num_rois, int pooled_h, int pooled_w,
+                                         double spatial_scale, vb200_stream stream) {
+  VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "ps_roi_pool: pooled size must be positive");
+  VB200_REQUIRE(channels % (pooled_h * pooled_w) == 0, "input channels must be a multiple of pooling height * pooling width");
+  if (num_rois == 0 || channels == 0) return 0;
+  VB200_REQUIRE(input && rois && output && channel_mapping, "ps_roi_pool: null pointer");
+  VB200_REQUIRE((int64_t)batch * channels * height * width < (1ll << 31), "ps_roi_pool: input too large for 32-bit indexing");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case VB200_F32: return launch_ps_roi_pool<float>(input, rois, output, channel_mapping, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F16: return launch_ps_roi_pool<__half>(input, rois, output, channel_mapping, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+    case VB200_F64: return launch_ps_roi_pool<double>(input, rois, output, channel_mapping, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale, st);
+  }
+  set_error("ps_roi_pool: unsupported dtype %d", dtype);
+  return VB200_EUNSUPPORTED;
+}
+
+extern "C" int vb200_ps_roi_pool_backward(const void* grad, const void* rois, void* grad_input, int dtype, int batch, int channels,
+                                          int height, int width, int num_rois, int pooled_h, int pooled_w, double spatial_scale,
+                                          vb200_stream stream) {
+  VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "ps_roi_pool_backward: pooled size must be positive");
+  const int64_t in_elems = (int64_t)batch * channels * height * width;
+  if (in_elems == 0) return 0;
+  VB200_REQUIRE(grad_input, "ps_roi_pool_backward: null grad_input");
+  VB200_REQUIRE(in_elems < (1ll << 31), "ps_roi_pool_backward: tensor too large for 32-bit indexing");
+  VB200_REQUIRE(dtype == VB200_F32 || dtype == VB200_F64 || dtype == VB200_F16, "ps_roi_pool_backward: unsupported dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t esize = dtype == VB200_F64 ? 8 : dtype == VB200_F16 ? 2 : 4;
+  VB200_CUDA_TRY(cudaMemsetAsync(grad_input, 0, (size_t)in_elems * esize, st));
+  const int Cout = channels / (pooled_h * pooled_w);
+  const int64_t total = (int64_t)num_rois * Cout * pooled_h * pooled_w;
+  if (total == 0) return 0;
+  VB200_REQUIRE(grad && rois, "ps_roi_pool_backward: null pointer");
+  const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count() * 16 ? ceil_div64(total, 256) : (int64_t)sm_count() * 16);
+#define VB200_PSP_BWD(T)                                                                                                         \
+  ps_roi_pool_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)grad, (const T*)rois, (T*)grad_input, total, channels, height, width,   \
+                                                 pooled_h, pooled_w, Cout, (typename Acc<T>::type)spatial_scale)
+  if (dtype == VB200_F32) VB200_PSP_BWD(float);
+  else if (dtype == VB200_F64) VB200_PSP_BWD(double);
+  else VB200_PSP_BWD(__half);
+#undef VB200_PSP_BWD
+  return check_launch("ps_roi_pool_bwd_kernel");
 }

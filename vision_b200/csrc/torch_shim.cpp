@@ -115,6 +115,40 @@ std::tuple<at::Tensor, at::Tensor> ps_roi_align(const at::Tensor& input, const a
   return std::make_tuple(out, mapping);
 }
 
+std::tuple<at::Tensor, at::Tensor> ps_roi_pool(const at::Tensor& input, const at::Tensor& rois, double spatial_scale,
+                                               int64_t pooled_height, int64_t pooled_width) {
+  check_roi_inputs(input, rois);
+  at::cuda::CUDAGuard guard(input.device());
+  const int64_t K = rois.size(0), N = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
+  TORCH_CHECK(C % (pooled_height * pooled_width) == 0, "input channels must be a multiple of pooling height * pooling width");
+  const int64_t Cout = C / (pooled_height * pooled_width);
+  at::Tensor out = at::empty({K, Cout, pooled_height, pooled_width}, input.options());
+  at::Tensor mapping = at::empty({K, Cout, pooled_height, pooled_width}, input.options().dtype(at::kInt));
+  if (out.numel() == 0) return std::make_tuple(out, mapping);
+  at::Tensor in_c = input.contiguous(), rois_c = rois.contiguous();
+  check_rc(vb200_ps_roi_pool_forward(in_c.data_ptr(), rois_c.data_ptr(), out.data_ptr(), mapping.data_ptr<int32_t>(),
+                                     dtype_code(input.scalar_type(), "ps_roi_pool"), (int)N, (int)C, (int)H, (int)W, (int)K,
+                                     (int)pooled_height, (int)pooled_width, spatial_scale, cur_stream()),
+           "ps_roi_pool");
+  return std::make_tuple(out, mapping);
+}
+
+at::Tensor ps_roi_pool_backward(const at::Tensor& grad, const at::Tensor& rois, const at::Tensor& channel_mapping, double spatial_scale,
+                                int64_t pooled_height, int64_t pooled_width, int64_t batch_size, int64_t channels, int64_t height,
+                                int64_t width) {
+  TORCH_CHECK(grad.is_cuda() && rois.is_cuda() && channel_mapping.is_cuda(), "grad, rois and channel_mapping must be CUDA tensors");
+  TORCH_CHECK(grad.scalar_type() == rois.scalar_type(), "ps_roi_pool_backward: expected grad and rois to have the same dtype");
+  at::cuda::CUDAGuard guard(grad.device());
+  at::Tensor grad_input = at::empty({batch_size, channels, height, width}, grad.options());
+  if (grad_input.numel() == 0) return grad_input;
+  at::Tensor g = grad.contiguous(), r = rois.contiguous();
+  check_rc(vb200_ps_roi_pool_backward(g.data_ptr(), r.data_ptr(), grad_input.data_ptr(), dtype_code(grad.scalar_type(), "ps_roi_pool_backward"),
+                                      (int)batch_size, (int)channels, (int)height, (int)width, (int)r.size(0), (int)pooled_height,
+                                      (int)pooled_width, spatial_scale, cur_stream()),
+           "ps_roi_pool_backward");
+  return grad_input;
+}
+
 // ---- fused MultiScaleRoIAlign (torchvision/ops/poolers.py:147-228) ----------------------------------------------
 std::tuple<at::Tensor, at::Tensor> multiscale_roi_align(at::TensorList features, const at::Tensor& rois, at::ArrayRef<double> scales,
                                                         int64_t pooled_height, int64_t pooled_width, int64_t sampling_ratio,
@@ -470,6 +504,8 @@ void install(bool on) {
   lib->impl("roi_pool", TORCH_FN(roi_pool));
   lib->impl("ps_roi_align", TORCH_FN(ps_roi_align));
   lib->impl("deform_conv2d", TORCH_FN(deform_conv2d));
+  lib->impl("ps_roi_pool", TORCH_FN(ps_roi_pool));
+  lib->impl("_ps_roi_pool_backward", TORCH_FN(ps_roi_pool_backward));
   lib->impl("_roi_align_backward", TORCH_FN(roi_align_backward));
   lib->impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   lib->impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
@@ -494,6 +530,8 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("roi_pool(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width) -> (Tensor, Tensor)");
   m.def("ps_roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, int sampling_ratio) -> (Tensor, Tensor)");
   m.def("deform_conv2d(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> Tensor");
+  m.def("ps_roi_pool(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width) -> (Tensor, Tensor)");
+  m.def("_ps_roi_pool_backward(Tensor grad, Tensor rois, Tensor channel_mapping, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
   m.def("resize_crop_normalize(Tensor input, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w, int mode, bool antialias, float[] mean, float[] std) -> Tensor");
   m.def("detection_postprocess(Tensor boxes, Tensor scores, Tensor labels, float img_h, float img_w, float score_thresh, bool score_inclusive, float min_size, float nms_thresh, int topk) -> (Tensor, Tensor, Tensor)");
@@ -522,6 +560,8 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   m.impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
   m.impl("multiscale_roi_align", TORCH_FN(multiscale_roi_align));
+  m.impl("ps_roi_pool", TORCH_FN(ps_roi_pool));
+  m.impl("_ps_roi_pool_backward", TORCH_FN(ps_roi_pool_backward));
   m.impl("detection_postprocess", TORCH_FN(detection_postprocess));
   m.impl("resize_crop_normalize", TORCH_FN(resize_crop_normalize));
 }

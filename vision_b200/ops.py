@@ -101,6 +101,15 @@ def ps_roi_align(input: Tensor, boxes, output_size, spatial_scale: float = 1.0, 
     return output
 
 
+def ps_roi_pool(input: Tensor, boxes, output_size, spatial_scale: float = 1.0) -> Tensor:
+    """torchvision.ops.ps_roi_pool (ps_roi_pool.py:11-52)."""
+    _require_cuda(input, "input")
+    rois = _rois(boxes)
+    output_size = _pair(output_size)
+    output, _ = _ops().ps_roi_pool(input, rois, float(spatial_scale), output_size[0], output_size[1])
+    return output
+
+
 # ---- deform_conv2d --------------------------------------------------------------
 def deform_conv2d(input: Tensor, offset: Tensor, weight: Tensor, bias=None, stride=(1, 1), padding=(0, 0),
                   dilation=(1, 1), mask=None) -> Tensor:
