@@ -218,7 +218,9 @@ VB200_API int vb200_detection_postprocess(const void* boxes, const void* scores,
  * offset [batch, offset_groups*2*kh*kw, out_h, out_w],
  * mask [batch, offset_groups*kh*kw, out_h, out_w] (ignored if !use_mask),
  * bias [c_out] (may be NULL), out [batch,c_out,out_h,out_w].
- * dtype: F32 (SIMT path), BF16/F16 (tcgen05 tensor-core path, fp32 accumulate).
+ * dtype: BF16 / F16 (tcgen05 tensor-core path, fp32 accumulate), F32 (tcgen05 with a three-way bf16 split of both
+ * operands, six MMAs per K step: fp32-level accuracy; SIMT kernel for shapes the tensor-core tiling does not cover),
+ * F64 (plain double kernel - the reference's gradcheck tests run in double).
  * workspace: vb200_deform_conv2d_workspace_bytes() bytes (may be 0). */
 VB200_API size_t vb200_deform_conv2d_workspace_bytes(int dtype, int batch, int c_in, int in_h, int in_w,
                                            int c_out, int kh, int kw, int out_h, int out_w,
@@ -230,6 +232,25 @@ VB200_API int vb200_deform_conv2d_forward(const void* input, const void* weight,
                                 int dil_h, int dil_w, int groups, int offset_groups,
                                 int use_mask, void* workspace, size_t workspace_bytes,
                                 vb200_stream stream);
+
+/* ---- deform_conv2d backward ----------------------------------------------
+ * Replace the kernels of deform_conv2d_backward_kernel, csrc/ops/cuda/deform_conv2d_kernel.cu:319-1033 (schema
+ * csrc/ops/deform_conv2d.cpp:103-104).  The two dense contractions (weight^T x grad_out, grad_out x columns^T) are plain
+ * GEMMs issued by the caller (the torch shim uses cuBLAS through at::matmul); these entry points are the passes around them:
+ *   vb200_deform_conv2d_sample_columns: columns [n_imgs, c_in*kh*kw, out_h*out_w] = mask * bilinear(input) (replaces
+ *     deformable_im2col, :136-209; layout is image-major here);
+ *   vb200_deform_conv2d_backward_inputs: from dcol [n_imgs, c_in*kh*kw, out_h*out_w] = weight^T x grad_out, ONE pass writes
+ *     grad_offset and grad_mask (no atomics) and scatters grad_input (atomics into a pre-zeroed tensor) - the reference's
+ *     deformable_col2im_kernel (:319-401) and deformable_col2im_coord_kernel (:538-643) fused.
+ * dtype: F32, F64, F16, BF16.  Weight groups are the caller's concern (c_in = all input channels). */
+VB200_API int vb200_deform_conv2d_sample_columns(const void* input, const void* offset, const void* mask, void* columns, int dtype,
+                                       int n_imgs, int c_in, int in_h, int in_w, int kh, int kw, int stride_h, int stride_w,
+                                       int pad_h, int pad_w, int dil_h, int dil_w, int offset_groups, int use_mask,
+                                       vb200_stream stream);
+VB200_API int vb200_deform_conv2d_backward_inputs(const void* dcol, const void* input, const void* offset, const void* mask,
+                                        void* grad_input, void* grad_offset, void* grad_mask, int dtype, int n_imgs, int c_in,
+                                        int in_h, int in_w, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                                        int dil_h, int dil_w, int offset_groups, int use_mask, vb200_stream stream);
 
 /* ---- resize ------------------------------------------------------------
  * Replaces the interpolate path of resize_image,

@@ -269,7 +269,7 @@ def test_roi_align_backward_other_dtypes_and_adaptive_grid(vb, dtype):
         assert ours.dtype == dtype
         if dtype == torch.float64:
             ref = torch.ops.torchvision._roi_align_backward(grad, rd, *args)
-            np.testing.assert_allclose(npy(ours.double()), npy(ref.double()), rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(ours.cpu().numpy(), ref.cpu().numpy(), rtol=1e-9, atol=1e-9)
         else:
             # fp16: both kernels round every atomic add to half, and the reference also rounds its coordinates to half; the
             # ground truth is the fp64 scatter of the same fp16 values - bound: a few half ulps of the largest accumulated value
@@ -540,7 +540,7 @@ def test_ps_roi_pool_forward_backward_vs_reference(vb, oracle, dtype):
         truth = torch.ops.torchvision._ps_roi_pool_backward(grad.double(), rd.double(), m1, *args)
         ours = torch.ops.vision_b200._ps_roi_pool_backward(grad, rd, m1, *args)
         tol = {torch.float32: 1e-5, torch.float64: 1e-12, torch.float16: 3e-2}[dtype]
-        np.testing.assert_allclose(npy(ours.double()), npy(truth), rtol=tol, atol=tol * max(1.0, truth.abs().max().item()))
+        np.testing.assert_allclose(ours.double().cpu().numpy(), truth.cpu().numpy(), rtol=tol, atol=tol * max(1.0, truth.abs().max().item()))
     vb.install()
     try:
         xr = torch.randn(1, 18, 20, 24, device=DEV, requires_grad=True)
@@ -550,3 +550,74 @@ def test_ps_roi_pool_forward_backward_vs_reference(vb, oracle, dtype):
         assert vb.launch_count() >= before + 2 and xr.grad.abs().sum().item() > 0
     finally:
         vb.uninstall()
+
+
+# =============================== deform_conv2d backward ===============================
+def _dcn_args(batch, dtype, seed=0):
+    # test/test_ops.py:1113-1167 get_fn_args: groups 2, offset groups 3, stride (2,1), pad (1,0), dil (2,1), kernel (3,2)
+    g = torch.Generator().manual_seed(seed)
+    cin, cout, ng, og, sh, sw, ph, pw, dh, dw, kh, kw, ih, iw = 6, 2, 2, 3, 2, 1, 1, 0, 2, 1, 3, 2, 5, 4
+    oh = (ih + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    ow = (iw + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    mk = lambda *s: torch.randn(*s, generator=g).to(dtype).to(DEV)
+    x = torch.rand(batch, cin, ih, iw, generator=g).to(dtype).to(DEV)
+    return (x, mk(cout, cin // ng, kh, kw), mk(batch, og * 2 * kh * kw, oh, ow), mk(batch, og * kh * kw, oh, ow), mk(cout),
+            (sh, sw, ph, pw, dh, dw, ng, og))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_deform_conv2d_backward_vs_reference_cuda(vb, dtype):
+    tv = pytest.importorskip("torchvision")
+    from vision_b200 import workloads
+
+    assert not vb.installed()
+    cases = [_dcn_args(33, dtype), _dcn_args(1, dtype, seed=3)]
+    x, off, w, b, m = workloads.cfg4_deform_conv2d(device=DEV, batch=2, c_in=64, c_out=128, hw=20, dtype=dtype)
+    cases.append((x, w, off, m, b, (1, 1, 1, 1, 1, 1, 1, 1)))
+    for (x, w, off, m, b, geo) in cases:
+        for use_mask in (True, False):
+            mm = m if use_mask else torch.zeros(x.shape[0], 1, device=DEV, dtype=dtype)
+            out = torch.ops.torchvision.deform_conv2d(x, w, off, mm, b, *geo, use_mask)
+            grad = torch.randn(out.shape, device=DEV, dtype=torch.float64).to(dtype) * 0.5
+            truth = torch.ops.torchvision._deform_conv2d_backward(grad.double(), x.double(), w.double(), off.double(), mm.double(),
+                                                                  b.double(), *geo, use_mask)
+            ours = torch.ops.vision_b200._deform_conv2d_backward(grad, x, w, off, mm, b, *geo, use_mask)
+            tol = 2e-5 if dtype == torch.float32 else 1e-10
+            for name, a, t_ in zip(("input", "weight", "offset", "mask", "bias"), ours, truth):
+                assert a.shape == t_.shape and a.dtype == dtype, name
+                scale = max(1.0, t_.abs().max().item())
+                np.testing.assert_allclose(a.double().cpu().numpy(), t_.cpu().numpy(), rtol=tol, atol=tol * scale, err_msg=name)
+
+
+def test_deform_conv2d_gradcheck_and_installed_autograd(vb):
+    """gradcheck in fp64 as test/test_ops.py:1236-1285 (fast_mode, nondet_tol for the atomics of grad_input); after install()
+    torchvision.ops.deform_conv2d(...).backward() runs on our kernels."""
+    tv = pytest.importorskip("torchvision")
+    from torch.autograd import gradcheck
+
+    assert not vb.installed()
+    x, w, off, m, b, geo = _dcn_args(3, torch.float64, seed=1)
+    sh, sw, ph, pw, dh, dw, ng, og = geo
+    for t_ in (x, w, off, m, b):
+        t_.requires_grad_(True)
+    f = lambda x_, o_, m_, w_, b_: vb.ops.deform_conv2d(x_, o_, w_, b_, stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw), mask=m_)
+    assert gradcheck(f, (x, off, m, w, b), nondet_tol=1e-5, fast_mode=True)
+    f2 = lambda x_, o_, w_, b_: vb.ops.deform_conv2d(x_, o_, w_, b_, stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw), mask=None)
+    assert gradcheck(f2, (x, off, w, b), nondet_tol=1e-5, fast_mode=True)
+    # bf16 at a tensor-core shape: gradients flow and are finite, weight gradient close to an fp32 evaluation of the reference
+    from vision_b200 import workloads
+    xb, offb, wb, bb, mb = workloads.cfg4_deform_conv2d(device=DEV, batch=2, c_in=64, c_out=128, hw=16, dtype=torch.bfloat16)
+    ref_in = [t_.float().requires_grad_(True) for t_ in (xb, offb, wb, bb, mb)]
+    tv.ops.deform_conv2d(ref_in[0], ref_in[1], ref_in[2], ref_in[3], 1, 1, 1, ref_in[4]).square().mean().backward()
+    vb.install()
+    try:
+        ours_in = [t_.clone().requires_grad_(True) for t_ in (xb, offb, wb, bb, mb)]
+        before = vb.launch_count()
+        tv.ops.deform_conv2d(ours_in[0], ours_in[1], ours_in[2], ours_in[3], 1, 1, 1, ours_in[4]).float().square().mean().backward()
+        assert vb.launch_count() >= before + 3                       # forward + the two backward kernels
+    finally:
+        vb.uninstall()
+    for a, r in zip(ours_in, ref_in):
+        assert torch.isfinite(a.grad.float()).all()
+        scale = r.grad.abs().max().item() + 1e-12
+        assert (a.grad.float() - r.grad).abs().max().item() <= 5e-2 * scale

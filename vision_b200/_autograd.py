@@ -170,6 +170,22 @@ def register() -> None:
         return inp.new_empty(tuple(inp.shape[:-2]) + (out_h, out_w))
 
     # ---- deform_conv2d ----
+    def dcn_setup(ctx, inputs, output):
+        inp, weight, offset, mask, bias = inputs[:5]
+        ctx.save_for_backward(inp, weight, offset, mask, bias)
+        ctx.args = tuple(inputs[5:])
+
+    def dcn_backward(ctx, grad):
+        inp, weight, offset, mask, bias = ctx.saved_tensors
+        gi, gw, go, gm, gb = ops._deform_conv2d_backward(grad, inp, weight, offset, mask, bias, *ctx.args)
+        return (gi, gw, go, gm, gb) + (None,) * 9
+
+    lib.register_autograd("vision_b200::deform_conv2d", dcn_backward, setup_context=dcn_setup)
+
+    @lib.register_fake("vision_b200::_deform_conv2d_backward")
+    def _(grad, inp, weight, offset, mask, bias, *args):
+        return (torch.empty_like(inp), torch.empty_like(weight), torch.empty_like(offset), torch.empty_like(mask), torch.empty_like(bias))
+
     @lib.register_fake("vision_b200::deform_conv2d")
     def _(inp, weight, offset, mask, bias, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups, offset_groups, use_mask):
         kh, kw = weight.shape[-2:]

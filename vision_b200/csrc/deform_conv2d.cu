@@ -175,6 +175,50 @@ int launch_simt(const void* input, const void* weight, const void* offset, const
   return check_launch("deform_conv2d_simt_kernel");
 }
 
+// ---- float64 (the reference dispatches FLOATING_TYPES_AND_HALF; its gradcheck tests run in double) --------------------
+// One thread per output element, double accumulation, bilinear_interpolate exactly as deform_conv2d_kernel.cu:97-134.
+// A correctness path for tests, not a performance path.
+__device__ __forceinline__ double dcn_bilinear_f64(const double* __restrict__ in, int H, int W, double h, double w) {
+  if (h <= -1 || H <= h || w <= -1 || W <= w) return 0;
+  const int hl = (int)floor(h), wl = (int)floor(w);
+  const int hh_i = hl + 1, wh_i = wl + 1;
+  const double lh = h - hl, lw = w - wl, hh = 1 - lh, hw = 1 - lw;
+  const double v1 = (hl >= 0 && wl >= 0) ? in[hl * W + wl] : 0;
+  const double v2 = (hl >= 0 && wh_i <= W - 1) ? in[hl * W + wh_i] : 0;
+  const double v3 = (hh_i <= H - 1 && wl >= 0) ? in[hh_i * W + wl] : 0;
+  const double v4 = (hh_i <= H - 1 && wh_i <= W - 1) ? in[hh_i * W + wh_i] : 0;
+  return hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
+}
+
+__global__ void __launch_bounds__(256)
+deform_conv2d_f64_kernel(const double* __restrict__ in, const double* __restrict__ w, const double* __restrict__ off,
+                         const double* __restrict__ mask, const double* __restrict__ bias, double* __restrict__ out, DcnParams p) {
+  const int HWo = p.out_h * p.out_w, HWi = p.in_h * p.in_w, KK = p.kh * p.kw;
+  const int64_t total = (int64_t)p.batch * p.c_out * HWo;
+  const int cin_g = p.c_in / p.groups, cout_g = p.c_out / p.groups, c_per_off = p.c_in / p.offset_groups;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(idx % HWo);
+    const int co = (int)((idx / HWo) % p.c_out);
+    const int b = (int)(idx / HWo / p.c_out);
+    const int oy = pix / p.out_w, ox = pix - oy * p.out_w;
+    const int g = co / cout_g;
+    double sum = 0;
+    for (int ci = 0; ci < cin_g; ++ci) {
+      const int c = g * cin_g + ci, og = c / c_per_off;
+      const double* __restrict__ plane = in + ((int64_t)b * p.c_in + c) * HWi;
+      for (int tap = 0; tap < KK; ++tap) {
+        const int i = tap / p.kw, j = tap - i * p.kw;
+        const int64_t ob = ((int64_t)b * p.offset_groups + og) * 2 * KK;
+        const double y = (double)(oy * p.stride_h - p.pad_h + i * p.dil_h) + off[(ob + 2 * tap) * HWo + pix];
+        const double x = (double)(ox * p.stride_w - p.pad_w + j * p.dil_w) + off[(ob + 2 * tap + 1) * HWo + pix];
+        const double m = p.use_mask ? mask[(((int64_t)b * p.offset_groups + og) * KK + tap) * HWo + pix] : 1.0;
+        sum += w[((int64_t)co * cin_g + ci) * KK + tap] * (m * dcn_bilinear_f64(plane, p.in_h, p.in_w, y, x));
+      }
+    }
+    out[idx] = sum + (bias ? bias[co] : 0.0);
+  }
+}
+
 }  // namespace
 
 // deform_conv2d_tc.cu: returns 1 if handled, 0 if not applicable, other = error
@@ -228,6 +272,13 @@ extern "C" int vb200_deform_conv2d_forward(const void* input, const void* weight
     case VB200_F32: return launch_simt<float>(input, weight, offset, mask, bias, out, p, st);
     case VB200_F16: return launch_simt<__half>(input, weight, offset, mask, bias, out, p, st);
     case VB200_BF16: return launch_simt<__nv_bfloat16>(input, weight, offset, mask, bias, out, p, st);
+    case VB200_F64: {
+      const int64_t total = (int64_t)batch * c_out * p.out_h * p.out_w;
+      const int grid = (int)(ceil_div64(total, 256) < (int64_t)sm_count() * 16 ? ceil_div64(total, 256) : (int64_t)sm_count() * 16);
+      deform_conv2d_f64_kernel<<<grid, 256, 0, st>>>((const double*)input, (const double*)weight, (const double*)offset,
+                                                    (const double*)mask, (const double*)bias, (double*)out, p);
+      return check_launch("deform_conv2d_f64_kernel");
+    }
   }
   set_error("deform_conv2d: unsupported dtype %d", dtype);
   return VB200_EUNSUPPORTED;

@@ -671,8 +671,13 @@ deform_conv2d_tc2_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpack
 // im2col + SGEMM).  Same structure as deform_conv2d_tc_kernel: M = 128 pixels, N = BN couts, K step 32 channels
 // (SWIZZLE_64B); a stage holds A1 A2 A3 (8 KB each) and B1 B2 B3 (BN x 64 B each); the gather reads a channels-last
 // fp32 staging copy (one 128-byte line = 32 channels per pixel corner), blends in fp32 and writes the three splits.
+// ACCUMULATION: the tensor core adds into its fp32 accumulator with truncation (measured: ~one ulp of the accumulator
+// lost per MMA instruction, a bias that grows linearly with the number of MMAs - 8e-5 absolute after 864 MMAs into one
+// accumulator).  So (1) the five correction terms go to their OWN accumulator (its magnitude is 2^-8 of the result, so its
+// truncation is invisible) and (2) the a1 b1 terms rotate over THREE accumulators by K step; the epilogue adds the four
+// TMEM regions in registers with round-to-nearest.  BN = 128: 3 + 1 accumulators x 128 columns = all 512 TMEM columns.
 // =================================================================================================
-constexpr int T3_KB = 32, T3_STAGES = 2;
+constexpr int T3_KB = 32, T3_STAGES = 3, T3_MAIN = 3;
 constexpr int T3_ROW = 2 * T3_KB;                 // 64-byte tile rows
 constexpr int T3_A = TC_BM * T3_ROW;              // 8 KB per A split
 
@@ -736,7 +741,8 @@ deform_conv2d_tc3_kernel(const float* __restrict__ nhwc, const __nv_bfloat16* __
     mbar_init(accum_full, 1);
     mbar_fence_init();
   }
-  if (warp == TC1_GATHER_WARPS + 1) tmem_alloc(tmem_slot, BN);
+  static_assert(BN * (T3_MAIN + 1) <= 512, "3 main + 1 correction accumulator must fit TMEM");
+  if (warp == TC1_GATHER_WARPS + 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -835,13 +841,18 @@ deform_conv2d_tc3_kernel(const float* __restrict__ nhwc, const __nv_bfloat16* __
 #pragma unroll 1
     for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
       const int col = col_q * COLS_PER_WARP + c0;
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
+      uint32_t r0[16], r1[16], r2[16], rs[16];
+      const uint32_t ta = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col;
+      tmem_ld16(ta, r0);
+      tmem_ld16(ta + BN, r1);
+      tmem_ld16(ta + 2 * BN, r2);
+      tmem_ld16(ta + 3 * BN, rs);
       if (pix < HWo) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int co = nt * BN + col + j;
-          out[((int64_t)b * p.c_out + co) * HWo + pix] = __uint_as_float(r[j]) + (bias ? bias[co] : 0.f);
+          const float main = (n_q > 2 ? __uint_as_float(r2[j]) : 0.f) + ((n_q > 1 ? __uint_as_float(r1[j]) : 0.f) + __uint_as_float(r0[j]));
+          out[((int64_t)b * p.c_out + co) * HWo + pix] = (main + __uint_as_float(rs[j])) + (bias ? bias[co] : 0.f);
         }
       }
     }
@@ -868,22 +879,28 @@ deform_conv2d_tc3_kernel(const float* __restrict__ nhwc, const __nv_bfloat16* __
         tc_fence_after();
         const uint32_t a_addr = smem_u32(stages + st * STAGE_BYTES);
         const uint32_t b_addr = a_addr + 3 * T3_A;
-        // small terms first (a3b1, a1b3, a2b2), then the first-order cross terms, then a1b1
-        constexpr int ia[6] = {2, 0, 1, 1, 0, 0}, ib[6] = {0, 2, 1, 0, 1, 0};
+        // correction terms (a3b1, a1b3, a2b2, a2b1, a1b2) -> their own accumulator at column 3 * BN
+        constexpr int ia[5] = {2, 0, 1, 1, 0}, ib[5] = {0, 2, 1, 0, 1};
 #pragma unroll
-        for (int t = 0; t < 6; ++t) {
+        for (int t = 0; t < 5; ++t) {
 #pragma unroll
           for (int k = 0; k < T3_KB / 16; ++k)
-            umma_f16(tmem_base, smem_desc_k<T3_KB>(a_addr + ia[t] * T3_A + k * 32), smem_desc_k<T3_KB>(b_addr + ib[t] * B_BYTES + k * 32),
-                     idesc, (q | t | k) ? 1u : 0u);
+            umma_f16(tmem_base + 3u * BN, smem_desc_k<T3_KB>(a_addr + ia[t] * T3_A + k * 32),
+                     smem_desc_k<T3_KB>(b_addr + ib[t] * B_BYTES + k * 32), idesc, (q | t | k) ? 1u : 0u);
         }
+        // a1 b1 -> main accumulator q mod 3 (first touch of each starts from zero)
+        const uint32_t main_col = (uint32_t)(q % T3_MAIN) * BN;
+#pragma unroll
+        for (int k = 0; k < T3_KB / 16; ++k)
+          umma_f16(tmem_base + main_col, smem_desc_k<T3_KB>(a_addr + k * 32), smem_desc_k<T3_KB>(b_addr + k * 32), idesc,
+                   (q >= T3_MAIN || k) ? 1u : 0u);
         umma_commit(&empty[st]);
       }
       umma_commit(accum_full);
     }
   }
   __syncthreads();
-  if (warp == TC1_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN); }
+  if (warp == TC1_GATHER_WARPS + 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 size_t tc3_smem_bytes(int BN, int KK) {
@@ -891,10 +908,7 @@ size_t tc3_smem_bytes(int BN, int KK) {
 }
 int tc3_pick_bn(const DcnParams& p) {
   const int KK = p.kh * p.kw;
-  const int cands[2] = {256, 128};
-  for (int c = 0; c < 2; ++c)
-    if (p.c_out % cands[c] == 0 && tc3_smem_bytes(cands[c], KK) <= (size_t)max_smem_optin()) return cands[c];
-  return 0;
+  return (p.c_out % 128 == 0 && tc3_smem_bytes(128, KK) <= (size_t)max_smem_optin()) ? 128 : 0;
 }
 bool tc3_eligible(int dtype, const DcnParams& p) {
   if (dtype != VB200_F32 || p.groups != 1) return false;
@@ -1034,15 +1048,9 @@ int launch_tc3(const void* input, const void* weight, const void* offset, const 
   if (rc) return rc;
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
   const size_t smem = tc3_smem_bytes(BN, KK);
-  if (BN == 256) {
-    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc3_kernel<256>>(smem));
-    deform_conv2d_tc3_kernel<256><<<grid, TC1_THREADS, smem, st>>>(nhwc, wpacked, (const float*)offset, (const float*)mask,
-                                                                  (const float*)bias, (float*)out, p);
-  } else {
-    VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc3_kernel<128>>(smem));
-    deform_conv2d_tc3_kernel<128><<<grid, TC1_THREADS, smem, st>>>(nhwc, wpacked, (const float*)offset, (const float*)mask,
-                                                                  (const float*)bias, (float*)out, p);
-  }
+  VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc3_kernel<128>>(smem));
+  deform_conv2d_tc3_kernel<128><<<grid, TC1_THREADS, smem, st>>>(nhwc, wpacked, (const float*)offset, (const float*)mask,
+                                                                (const float*)bias, (float*)out, p);
   rc = check_launch("deform_conv2d_tc3_kernel");
   return rc ? rc : 1;
 }

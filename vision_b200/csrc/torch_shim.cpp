@@ -431,7 +431,7 @@ at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, cons
   at::Tensor out = at::empty({batch, c_out, out_h, out_w}, input_c.options());
   if (batch == 0 || out.numel() == 0) return out;
   const int dt = dtype_code(st, "deform_conv2d");
-  TORCH_CHECK(dt == VB200_F32 || dt == VB200_F16 || dt == VB200_BF16, "deform_conv2d: unsupported dtype ", st);
+  TORCH_CHECK(dt == VB200_F32 || dt == VB200_F16 || dt == VB200_BF16 || dt == VB200_F64, "deform_conv2d: unsupported dtype ", st);
   TORCH_CHECK(bias_c.numel() == c_out, "bias must have one entry per output channel");
   const size_t wsb = vb200_deform_conv2d_workspace_bytes(dt, (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out, (int)kh,
                                                          (int)kw, (int)out_h, (int)out_w, (int)n_weight_grps,
@@ -445,6 +445,73 @@ at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, cons
                                        wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
            "deform_conv2d");
   return out;
+}
+
+// ---- deform_conv2d backward (schema csrc/ops/deform_conv2d.cpp:103-104; reference deform_conv2d_kernel.cu:647-1033) -------
+// Two plain GEMMs (cuBLAS through at::matmul: weight^T x grad_out -> dcol; grad_out x columns^T -> grad_weight) around two
+// kernels of ours: the fused grad_input / grad_offset / grad_mask pass and the column sampler (deform_conv2d_bwd.cu).
+std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor> deform_conv2d_backward(
+    const at::Tensor& grad, const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset, const at::Tensor& mask,
+    const at::Tensor& bias, int64_t stride_h, int64_t stride_w, int64_t pad_h, int64_t pad_w, int64_t dilation_h, int64_t dilation_w,
+    int64_t n_weight_grps, int64_t n_offset_grps, bool use_mask) {
+  TORCH_CHECK(grad.is_cuda() && input.is_cuda(), "deform_conv2d_backward: CUDA tensors expected");
+  at::cuda::CUDAGuard guard(input.device());
+  at::Tensor grad_c = grad.contiguous(), input_c = input.contiguous(), weight_c = weight.contiguous(), offset_c = offset.contiguous();
+  at::Tensor mask_c = mask.contiguous();
+  const int64_t B = input_c.size(0), C_in = input_c.size(1), H = input_c.size(2), W = input_c.size(3);
+  const int64_t C_out = weight_c.size(0), cin_g = weight_c.size(1), kh = weight_c.size(2), kw = weight_c.size(3), KK = kh * kw;
+  TORCH_CHECK(n_weight_grps > 0 && n_offset_grps > 0 && cin_g * n_weight_grps == C_in && C_out % n_weight_grps == 0 && C_in % n_offset_grps == 0,
+              "deform_conv2d_backward: channels not divisible by groups");
+  const auto st = input_c.scalar_type();
+  TORCH_CHECK(grad_c.scalar_type() == st && weight_c.scalar_type() == st && offset_c.scalar_type() == st && (!use_mask || mask_c.scalar_type() == st),
+              "deform_conv2d_backward: all tensors must share one dtype");
+  const int dt = dtype_code(st, "deform_conv2d_backward");
+  TORCH_CHECK(dt == VB200_F32 || dt == VB200_F64 || dt == VB200_F16 || dt == VB200_BF16, "deform_conv2d_backward: unsupported dtype ", st);
+  at::Tensor grad_input = at::zeros_like(input_c), grad_offset = at::empty_like(offset_c), grad_weight = at::zeros_like(weight_c);
+  at::Tensor grad_mask = use_mask ? at::empty_like(mask_c) : at::zeros_like(mask_c);
+  at::Tensor grad_bias = at::ones_like(bias) * (grad_c.numel() ? grad_c.sum({0, 2, 3}) : at::zeros_like(bias));   // deform_conv2d_kernel.cu:1231
+  if (B == 0 || grad_c.numel() == 0) return std::make_tuple(grad_input, grad_weight, grad_offset, grad_mask, grad_bias);
+  const int64_t out_h = grad_c.size(2), out_w = grad_c.size(3), HWo = out_h * out_w, cout_g = C_out / n_weight_grps;
+  TORCH_CHECK(grad_c.size(0) == B && grad_c.size(1) == C_out && offset_c.size(2) == out_h && offset_c.size(3) == out_w,
+              "deform_conv2d_backward: grad / offset shapes do not match the forward geometry");
+  const int64_t per_img = C_in * KK * HWo * (int64_t)input_c.element_size();
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(1ll << 30) / std::max<int64_t>(per_img, 1)));
+  const bool low = st == at::kHalf || st == at::kBFloat16;
+  at::Tensor gw_acc = low ? at::zeros({C_out, cin_g * KK}, input_c.options().dtype(at::kFloat)) : grad_weight.view({C_out, cin_g * KK});
+  at::Tensor w2 = weight_c.view({C_out, cin_g * KK});
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t nb = std::min(chunk, B - b0);
+    at::Tensor g = grad_c.narrow(0, b0, nb).view({nb, C_out, HWo});
+    at::Tensor buf = at::empty({nb, C_in * KK, HWo}, input_c.options());
+    // dcol = weight^T x grad_out, per weight group
+    for (int64_t grp = 0; grp < n_weight_grps; ++grp) {
+      at::Tensor wt = w2.narrow(0, grp * cout_g, cout_g).t();                                  // [cin_g*KK, cout_g]
+      at::Tensor d = at::matmul(wt, g.narrow(1, grp * cout_g, cout_g));                        // [nb, cin_g*KK, HWo]
+      if (n_weight_grps == 1) buf = d; else buf.narrow(1, grp * cin_g * KK, cin_g * KK).copy_(d);
+    }
+    at::Tensor in_b = input_c.narrow(0, b0, nb), off_b = offset_c.narrow(0, b0, nb);
+    at::Tensor gi_b = grad_input.narrow(0, b0, nb), go_b = grad_offset.narrow(0, b0, nb);
+    const void* mk = use_mask ? mask_c.narrow(0, b0, nb).data_ptr() : nullptr;
+    void* gm = use_mask ? grad_mask.narrow(0, b0, nb).data_ptr() : nullptr;
+    check_rc(vb200_deform_conv2d_backward_inputs(buf.data_ptr(), in_b.data_ptr(), off_b.data_ptr(), mk, gi_b.data_ptr(), go_b.data_ptr(), gm,
+                                                 dt, (int)nb, (int)C_in, (int)H, (int)W, (int)kh, (int)kw, (int)stride_h, (int)stride_w,
+                                                 (int)pad_h, (int)pad_w, (int)dilation_h, (int)dilation_w, (int)n_offset_grps,
+                                                 use_mask ? 1 : 0, cur_stream()),
+             "deform_conv2d_backward");
+    // columns for grad_weight (the buffer is reused)
+    check_rc(vb200_deform_conv2d_sample_columns(in_b.data_ptr(), off_b.data_ptr(), mk, buf.data_ptr(), dt, (int)nb, (int)C_in, (int)H, (int)W,
+                                                (int)kh, (int)kw, (int)stride_h, (int)stride_w, (int)pad_h, (int)pad_w, (int)dilation_h,
+                                                (int)dilation_w, (int)n_offset_grps, use_mask ? 1 : 0, cur_stream()),
+             "deform_conv2d_backward");
+    for (int64_t grp = 0; grp < n_weight_grps; ++grp) {
+      at::Tensor cols = buf.narrow(1, grp * cin_g * KK, cin_g * KK);                           // [nb, cin_g*KK, HWo]
+      at::Tensor gw = at::matmul(g.narrow(1, grp * cout_g, cout_g), cols.transpose(1, 2));     // [nb, cout_g, cin_g*KK]
+      at::Tensor acc = gw_acc.narrow(0, grp * cout_g, cout_g);
+      acc.add_(low ? gw.to(at::kFloat).sum(0) : gw.sum(0));
+    }
+  }
+  if (low) grad_weight.view({C_out, cin_g * KK}).copy_(gw_acc);
+  return std::make_tuple(grad_input, grad_weight, grad_offset, grad_mask, grad_bias);
 }
 
 // ---- resize ----------------------------------------------------------------
@@ -506,6 +573,7 @@ void install(bool on) {
   lib->impl("deform_conv2d", TORCH_FN(deform_conv2d));
   lib->impl("ps_roi_pool", TORCH_FN(ps_roi_pool));
   lib->impl("_ps_roi_pool_backward", TORCH_FN(ps_roi_pool_backward));
+  lib->impl("_deform_conv2d_backward", TORCH_FN(deform_conv2d_backward));
   lib->impl("_roi_align_backward", TORCH_FN(roi_align_backward));
   lib->impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   lib->impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
@@ -532,6 +600,7 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("deform_conv2d(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> Tensor");
   m.def("ps_roi_pool(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width) -> (Tensor, Tensor)");
   m.def("_ps_roi_pool_backward(Tensor grad, Tensor rois, Tensor channel_mapping, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
+  m.def("_deform_conv2d_backward(Tensor grad, Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> (Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
   m.def("resize_crop_normalize(Tensor input, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w, int mode, bool antialias, float[] mean, float[] std) -> Tensor");
   m.def("detection_postprocess(Tensor boxes, Tensor scores, Tensor labels, float img_h, float img_w, float score_thresh, bool score_inclusive, float min_size, float nms_thresh, int topk) -> (Tensor, Tensor, Tensor)");
