@@ -633,4 +633,5 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("_ps_roi_pool_backward", TORCH_FN(ps_roi_pool_backward));
   m.impl("detection_postprocess", TORCH_FN(detection_postprocess));
   m.impl("resize_crop_normalize", TORCH_FN(resize_crop_normalize));
+  m.impl("_deform_conv2d_backward", TORCH_FN(deform_conv2d_backward));
 }
