@@ -233,6 +233,20 @@ VB200_API int vb200_deform_conv2d_forward(const void* input, const void* weight,
                                 int use_mask, void* workspace, size_t workspace_bytes,
                                 vb200_stream stream);
 
+/* Weights are constant across inference calls and a channels-last producer can hand the input over without the
+ * NCHW -> NHWC staging pass: vb200_deform_conv2d_pack_weight() writes the swizzled K-major image the tensor-core
+ * kernels read (vb200_deform_conv2d_packed_weight_bytes() bytes; 0 = this shape takes the SIMT kernel), and
+ * vb200_deform_conv2d_forward_ex() takes it (packed_weight may be NULL) plus `input_is_nhwc` (input laid out
+ * [batch, in_h, in_w, c_in], 16-byte aligned).  The torch shim caches the packed image per weight tensor / version. */
+VB200_API size_t vb200_deform_conv2d_packed_weight_bytes(int dtype, int c_in, int c_out, int kh, int kw, int groups, int offset_groups);
+VB200_API int vb200_deform_conv2d_pack_weight(const void* weight, void* packed, int dtype, int c_in, int c_out, int kh, int kw,
+                                    int groups, int offset_groups, vb200_stream stream);
+VB200_API int vb200_deform_conv2d_forward_ex(const void* input, const void* weight, const void* packed_weight, int input_is_nhwc,
+                                   const void* offset, const void* mask, const void* bias, void* out, int dtype, int batch,
+                                   int c_in, int in_h, int in_w, int c_out, int kh, int kw, int stride_h, int stride_w,
+                                   int pad_h, int pad_w, int dil_h, int dil_w, int groups, int offset_groups, int use_mask,
+                                   void* workspace, size_t workspace_bytes, vb200_stream stream);
+
 /* ---- deform_conv2d backward ----------------------------------------------
  * Replace the kernels of deform_conv2d_backward_kernel, csrc/ops/cuda/deform_conv2d_kernel.cu:319-1033 (schema
  * csrc/ops/deform_conv2d.cpp:103-104).  The two dense contractions (weight^T x grad_out, grad_out x columns^T) are plain

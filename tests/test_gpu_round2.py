@@ -624,3 +624,28 @@ def test_deform_conv2d_gradcheck_and_installed_autograd(vb):
         assert torch.isfinite(a.grad.float()).all()
         scale = r.grad.abs().max().item() + 1e-12
         assert (a.grad.float() - r.grad).abs().max().item() <= 5e-2 * scale
+
+
+def test_deform_conv2d_packed_weight_cache_and_channels_last(vb):
+    """The shim packs the weights once per (tensor, version) and hands a channels-last input to the tensor-core kernel
+    without the staging pass: same bits as the plain call, fewer launches; an in-place weight update re-packs."""
+    from vision_b200 import workloads
+
+    for dtype in (torch.bfloat16, torch.float32):
+        x, off, w, b, m = workloads.cfg4_deform_conv2d(device=DEV, batch=2, c_in=128, c_out=256, hw=24, dtype=dtype)
+        base = vb.launch_count()
+        first = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, m)
+        n_first = vb.launch_count() - base
+        base = vb.launch_count()
+        second = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, m)
+        n_second = vb.launch_count() - base
+        assert torch.equal(first, second) and n_second == n_first - 1            # no pack_weights launch the second time
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        base = vb.launch_count()
+        third = vb.ops.deform_conv2d(xcl, off, w, b, 1, 1, 1, m)
+        assert torch.equal(first, third) and vb.launch_count() - base == n_second - 1   # and no NCHW -> NHWC staging launch
+        with torch.no_grad():
+            w.mul_(0.5)                                                          # version bump: the cached image is stale
+        fourth = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, m)
+        w2 = w.clone()
+        assert torch.equal(fourth, vb.ops.deform_conv2d(x, off, w2, b, 1, 1, 1, m)) and not torch.equal(fourth, first)

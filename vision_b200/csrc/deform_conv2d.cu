@@ -222,9 +222,13 @@ deform_conv2d_f64_kernel(const double* __restrict__ in, const double* __restrict
 }  // namespace
 
 // deform_conv2d_tc.cu: returns 1 if handled, 0 if not applicable, other = error
+struct DcnHints { const void* packed_weight; int input_is_nhwc; };   // optional: pre-packed weights / channels-last input (no staging pass)
 int deform_conv2d_tc_try(const void* input, const void* weight, const void* offset, const void* mask, const void* bias,
-                         void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                         void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                         const DcnHints& hints);
 size_t deform_conv2d_tc_workspace(int dtype, const DcnParams& p);
+size_t deform_conv2d_tc_packed_bytes(int dtype, const DcnParams& p);
+int deform_conv2d_tc_pack(const void* weight, void* packed, int dtype, const DcnParams& p, cudaStream_t st);
 
 }  // namespace vb200
 
@@ -241,12 +245,50 @@ extern "C" size_t vb200_deform_conv2d_workspace_bytes(int dtype, int batch, int 
   return deform_conv2d_tc_workspace(dtype, p);
 }
 
+static int dcn_forward_impl(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
+                            int dtype, int batch, int c_in, int in_h, int in_w, int c_out, int kh, int kw, int stride_h, int stride_w,
+                            int pad_h, int pad_w, int dil_h, int dil_w, int groups, int offset_groups, int use_mask, void* workspace,
+                            size_t workspace_bytes, vb200_stream stream, const DcnHints& hints);
+
 extern "C" int vb200_deform_conv2d_forward(const void* input, const void* weight, const void* offset,
                                            const void* mask, const void* bias, void* out, int dtype, int batch,
                                            int c_in, int in_h, int in_w, int c_out, int kh, int kw, int stride_h,
                                            int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
                                            int offset_groups, int use_mask, void* workspace,
                                            size_t workspace_bytes, vb200_stream stream) {
+  return dcn_forward_impl(input, weight, offset, mask, bias, out, dtype, batch, c_in, in_h, in_w, c_out, kh, kw, stride_h, stride_w, pad_h,
+                          pad_w, dil_h, dil_w, groups, offset_groups, use_mask, workspace, workspace_bytes, stream, DcnHints{nullptr, 0});
+}
+
+extern "C" size_t vb200_deform_conv2d_packed_weight_bytes(int dtype, int c_in, int c_out, int kh, int kw, int groups, int offset_groups) {
+  DcnParams p{};
+  p.batch = 1; p.c_in = c_in; p.in_h = 8; p.in_w = 8; p.c_out = c_out; p.kh = kh; p.kw = kw; p.groups = groups; p.offset_groups = offset_groups;
+  return deform_conv2d_tc_packed_bytes(dtype, p);
+}
+
+extern "C" int vb200_deform_conv2d_pack_weight(const void* weight, void* packed, int dtype, int c_in, int c_out, int kh, int kw, int groups,
+                                               int offset_groups, vb200_stream stream) {
+  DcnParams p{};
+  p.batch = 1; p.c_in = c_in; p.in_h = 8; p.in_w = 8; p.c_out = c_out; p.kh = kh; p.kw = kw; p.groups = groups; p.offset_groups = offset_groups;
+  VB200_REQUIRE(weight && packed, "deform_conv2d_pack_weight: null pointer");
+  VB200_REQUIRE(deform_conv2d_tc_packed_bytes(dtype, p) > 0, "deform_conv2d_pack_weight: this shape does not take the tensor-core path");
+  return deform_conv2d_tc_pack(weight, packed, dtype, p, (cudaStream_t)stream);
+}
+
+extern "C" int vb200_deform_conv2d_forward_ex(const void* input, const void* weight, const void* packed_weight, int input_is_nhwc,
+                                              const void* offset, const void* mask, const void* bias, void* out, int dtype, int batch,
+                                              int c_in, int in_h, int in_w, int c_out, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                              int pad_w, int dil_h, int dil_w, int groups, int offset_groups, int use_mask, void* workspace,
+                                              size_t workspace_bytes, vb200_stream stream) {
+  return dcn_forward_impl(input, weight, offset, mask, bias, out, dtype, batch, c_in, in_h, in_w, c_out, kh, kw, stride_h, stride_w, pad_h,
+                          pad_w, dil_h, dil_w, groups, offset_groups, use_mask, workspace, workspace_bytes, stream,
+                          DcnHints{packed_weight, input_is_nhwc});
+}
+
+static int dcn_forward_impl(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
+                            int dtype, int batch, int c_in, int in_h, int in_w, int c_out, int kh, int kw, int stride_h, int stride_w,
+                            int pad_h, int pad_w, int dil_h, int dil_w, int groups, int offset_groups, int use_mask, void* workspace,
+                            size_t workspace_bytes, vb200_stream stream, const DcnHints& hints) {
   // argument checks mirror deform_conv2d_kernel.cu:1056-1150
   VB200_REQUIRE(kh > 0 && kw > 0, "weight_h: %d weight_w: %d", kh, kw);
   VB200_REQUIRE(stride_h > 0 && stride_w > 0, "stride_h: %d stride_w: %d", stride_h, stride_w);
@@ -265,9 +307,10 @@ extern "C" int vb200_deform_conv2d_forward(const void* input, const void* weight
   cudaStream_t st = (cudaStream_t)stream;
   const char* force = env_override(ENV_DCN_PATH);   // "simt" forces the SIMT kernel
   if (!(force && force[0] == 's')) {
-    const int rc = deform_conv2d_tc_try(input, weight, offset, mask, bias, out, dtype, p, workspace, workspace_bytes, st);
+    const int rc = deform_conv2d_tc_try(input, weight, offset, mask, bias, out, dtype, p, workspace, workspace_bytes, st, hints);
     if (rc != 0) return rc == 1 ? 0 : rc;
   }
+  VB200_REQUIRE(!hints.input_is_nhwc, "deform_conv2d: a channels-last input is only accepted by the tensor-core path (this shape / dtype takes the SIMT kernel)");
   switch (dtype) {
     case VB200_F32: return launch_simt<float>(input, weight, offset, mask, bias, out, p, st);
     case VB200_F16: return launch_simt<__half>(input, weight, offset, mask, bias, out, p, st);

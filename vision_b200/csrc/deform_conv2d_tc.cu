@@ -23,6 +23,7 @@
 
 namespace vb200 {
 
+struct DcnHints { const void* packed_weight; int input_is_nhwc; };
 
 namespace {
 
@@ -973,28 +974,46 @@ bool tc_eligible(int dtype, const DcnParams& p) {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 template <typename T>
+int pack_tc_weights(const void* weight, T* wpacked, const DcnParams& p, cudaStream_t st) {
+  const int KK = p.kh * p.kw;
+  if (tc2_enabled(p)) {
+    pack_weights2_kernel<T><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK);
+    return check_launch("pack_weights2_kernel");
+  }
+  const int BN = tc_pick_bn(p);
+  if (tc_kb(512) == 32 && BN == 512)
+    pack_weights_kernel<T, 32><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+  else
+    pack_weights_kernel<T, 64><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+  return check_launch("pack_weights_kernel");
+}
+
+template <typename T>
 int launch_tc(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
-              const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+              const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st, const DcnHints& hints) {
   const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
-  const size_t nhwc_bytes = align256((size_t)p.batch * HWi * p.c_in * sizeof(T));
-  const size_t w_bytes = align256((size_t)p.c_out * p.c_in * KK * sizeof(T));
-  if (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0)
+  const size_t nhwc_bytes = hints.input_is_nhwc ? 0 : align256((size_t)p.batch * HWi * p.c_in * sizeof(T));
+  const size_t w_bytes = hints.packed_weight ? 0 : align256((size_t)p.c_out * p.c_in * KK * sizeof(T));
+  if (nhwc_bytes + w_bytes > 0 && (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0))
     return 0;       // no usable workspace: the SIMT kernel serves the call (a C-ABI caller may pass none)
-  T* nhwc = (T*)workspace;
-  T* wpacked = (T*)((char*)workspace + nhwc_bytes);
-  if (HWi % 2 == 0 && p.c_in % 64 == 0 && ((uintptr_t)input % 4) == 0) {
+  T* nhwc = hints.input_is_nhwc ? (T*)const_cast<void*>(input) : (T*)workspace;
+  T* wpacked = hints.packed_weight ? (T*)const_cast<void*>(hints.packed_weight) : (T*)((char*)workspace + nhwc_bytes);
+  if (hints.input_is_nhwc) {
+    if (((uintptr_t)input % 16) != 0) { set_error("deform_conv2d: channels-last input must be 16-byte aligned"); return VB200_EINVAL; }
+  } else if (HWi % 2 == 0 && p.c_in % 64 == 0 && ((uintptr_t)input % 4) == 0) {
     dim3 tg((unsigned)ceil_div(HWi, 64), (unsigned)(p.c_in / 64), (unsigned)p.batch);
     nchw_to_nhwc64_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
   } else {
     dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
     nchw_to_nhwc_kernel<T><<<tg, 256, 0, st>>>((const T*)input, nhwc, p.c_in, HWi);
   }
-  int rc = check_launch("nchw_to_nhwc_kernel");
+  int rc = hints.input_is_nhwc ? 0 : check_launch("nchw_to_nhwc_kernel");
   if (rc) return rc;
-  if (tc2_enabled(p)) {
-    pack_weights2_kernel<T><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK);
-    rc = check_launch("pack_weights2_kernel");
+  if (!hints.packed_weight) {
+    rc = pack_tc_weights<T>(weight, wpacked, p, st);
     if (rc) return rc;
+  }
+  if (tc2_enabled(p)) {
     const int total_tiles = p.batch * ceil_div(HWo, TC_BM);
     dim3 grid2((unsigned)((total_tiles + 1) & ~1), (unsigned)(p.c_out / 512));
     const size_t smem2 = tc2_smem_bytes(KK);
@@ -1005,12 +1024,6 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
     return rc ? rc : 1;
   }
   const int BN = tc_pick_bn(p);
-  if (tc_kb(512) == 32 && BN == 512)
-    pack_weights_kernel<T, 32><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
-  else
-    pack_weights_kernel<T, 64><<<sm_count() * 4, 256, 0, st>>>((const T*)weight, wpacked, p.c_out, p.c_in, KK, BN);
-  rc = check_launch("pack_weights_kernel");
-  if (rc) return rc;
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
   const size_t smem = tc_smem_bytes(BN, KK);
 #define VB200_TC_LAUNCH(BN_, ST_)                                                                                         \
@@ -1031,21 +1044,27 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
 }  // namespace
 
 int launch_tc3(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
-               const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st, const DcnHints& hints) {
   const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
-  const size_t nhwc_bytes = align256((size_t)p.batch * HWi * p.c_in * 4);
-  const size_t w_bytes = align256((size_t)p.c_out * p.c_in * KK * 3 * 2);
-  if (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0) return 0;   // SIMT kernel serves the call
-  float* nhwc = (float*)workspace;
-  __nv_bfloat16* wpacked = (__nv_bfloat16*)((char*)workspace + nhwc_bytes);
-  dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
-  nchw_to_nhwc_kernel<float><<<tg, 256, 0, st>>>((const float*)input, nhwc, p.c_in, HWi);
-  int rc = check_launch("nchw_to_nhwc_kernel");
-  if (rc) return rc;
+  const size_t nhwc_bytes = hints.input_is_nhwc ? 0 : align256((size_t)p.batch * HWi * p.c_in * 4);
+  const size_t w_bytes = hints.packed_weight ? 0 : align256((size_t)p.c_out * p.c_in * KK * 3 * 2);
+  if (nhwc_bytes + w_bytes > 0 && (workspace == nullptr || workspace_bytes < nhwc_bytes + w_bytes || ((uintptr_t)workspace % 256) != 0))
+    return 0;   // SIMT kernel serves the call
+  float* nhwc = hints.input_is_nhwc ? (float*)const_cast<void*>(input) : (float*)workspace;
+  __nv_bfloat16* wpacked = hints.packed_weight ? (__nv_bfloat16*)const_cast<void*>(hints.packed_weight) : (__nv_bfloat16*)((char*)workspace + nhwc_bytes);
+  int rc = 0;
+  if (!hints.input_is_nhwc) {
+    dim3 tg((unsigned)ceil_div(HWi, 32), (unsigned)ceil_div(p.c_in, 32), (unsigned)p.batch);
+    nchw_to_nhwc_kernel<float><<<tg, 256, 0, st>>>((const float*)input, nhwc, p.c_in, HWi);
+    rc = check_launch("nchw_to_nhwc_kernel");
+    if (rc) return rc;
+  } else if (((uintptr_t)input % 16) != 0) { set_error("deform_conv2d: channels-last input must be 16-byte aligned"); return VB200_EINVAL; }
   const int BN = tc3_pick_bn(p);
-  pack_weights3_kernel<<<sm_count() * 4, 256, 0, st>>>((const float*)weight, wpacked, p.c_out, p.c_in, KK, BN);
-  rc = check_launch("pack_weights3_kernel");
-  if (rc) return rc;
+  if (!hints.packed_weight) {
+    pack_weights3_kernel<<<sm_count() * 4, 256, 0, st>>>((const float*)weight, wpacked, p.c_out, p.c_in, KK, BN);
+    rc = check_launch("pack_weights3_kernel");
+    if (rc) return rc;
+  }
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
   const size_t smem = tc3_smem_bytes(BN, KK);
   VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc3_kernel<128>>(smem));
@@ -1065,12 +1084,28 @@ size_t deform_conv2d_tc_workspace(int dtype, const DcnParams& p) {
 }
 
 int deform_conv2d_tc_try(const void* input, const void* weight, const void* offset, const void* mask, const void* bias,
-                         void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (tc3_eligible(dtype, p)) return launch_tc3(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);
+                         void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                         const DcnHints& hints) {
+  if (tc3_eligible(dtype, p)) return launch_tc3(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st, hints);
   if (!tc_eligible(dtype, p)) return 0;
   if (dtype == VB200_BF16)
-    return launch_tc<__nv_bfloat16>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);
-  return launch_tc<__half>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st);
+    return launch_tc<__nv_bfloat16>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st, hints);
+  return launch_tc<__half>(input, weight, offset, mask, bias, out, p, workspace, workspace_bytes, st, hints);
+}
+
+// Packed-weight image for the tensor-core path of this shape (0: the shape does not take that path).
+size_t deform_conv2d_tc_packed_bytes(int dtype, const DcnParams& p) {
+  if (tc3_eligible(dtype, p)) return align256((size_t)p.c_out * p.c_in * p.kh * p.kw * 6);
+  if (tc_eligible(dtype, p)) return align256((size_t)p.c_out * p.c_in * p.kh * p.kw * 2);
+  return 0;
+}
+int deform_conv2d_tc_pack(const void* weight, void* packed, int dtype, const DcnParams& p, cudaStream_t st) {
+  if (tc3_eligible(dtype, p)) {
+    pack_weights3_kernel<<<sm_count() * 4, 256, 0, st>>>((const float*)weight, (__nv_bfloat16*)packed, p.c_out, p.c_in, p.kh * p.kw, tc3_pick_bn(p));
+    return check_launch("pack_weights3_kernel");
+  }
+  if (dtype == VB200_BF16) return pack_tc_weights<__nv_bfloat16>(weight, (__nv_bfloat16*)packed, p, st);
+  return pack_tc_weights<__half>(weight, (__half*)packed, p, st);
 }
 
 }  // namespace vb200

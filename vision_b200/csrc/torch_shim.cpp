@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <atomic>
 #include <memory>
+#include <mutex>
+#include <vector>
 
 #include "../../include/vision_b200.h"
 
@@ -386,11 +388,49 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> detection_postprocess(const at::T
 }
 
 // ---- deform_conv2d ---------------------------------------------------------
+// Packed weights are cached per weight tensor: the key is the TensorImpl (held weakly, so a recycled address cannot
+// alias) plus its version counter (an in-place update of the parameter invalidates the entry).
+struct PackedWeight {
+  c10::weak_intrusive_ptr<c10::TensorImpl> impl;
+  uint32_t version;
+  int dtype;
+  at::Tensor packed;
+};
+std::mutex g_pack_mu;
+std::vector<PackedWeight> g_pack_cache;
+
+at::Tensor packed_weight_for(const at::Tensor& weight_c, int dt, int c_in, int c_out, int kh, int kw, int groups, int offset_groups) {
+  const size_t bytes = vb200_deform_conv2d_packed_weight_bytes(dt, c_in, c_out, kh, kw, groups, offset_groups);
+  if (bytes == 0 || weight_c.is_inference()) return at::Tensor();
+  c10::TensorImpl* impl = weight_c.unsafeGetTensorImpl();
+  const uint32_t version = (uint32_t)weight_c._version();
+  std::lock_guard<std::mutex> lk(g_pack_mu);
+  for (size_t i = 0; i < g_pack_cache.size(); ++i) {
+    auto locked = g_pack_cache[i].impl.lock();
+    if (!locked) { g_pack_cache.erase(g_pack_cache.begin() + i); --i; continue; }      // the weight died
+    if (locked.get() == impl && g_pack_cache[i].dtype == dt) {
+      if (g_pack_cache[i].version == version) return g_pack_cache[i].packed;
+      g_pack_cache.erase(g_pack_cache.begin() + i);                                     // updated in place: re-pack
+      break;
+    }
+  }
+  at::Tensor packed = at::empty({(int64_t)bytes}, weight_c.options().dtype(at::kByte));
+  check_rc(vb200_deform_conv2d_pack_weight(weight_c.data_ptr(), packed.data_ptr(), dt, c_in, c_out, kh, kw, groups, offset_groups,
+                                           (vb200_stream)at::cuda::getCurrentCUDAStream().stream()),
+           "deform_conv2d");
+  if (g_pack_cache.size() >= 32) g_pack_cache.erase(g_pack_cache.begin());
+  g_pack_cache.push_back(PackedWeight{c10::weak_intrusive_ptr<c10::TensorImpl>(c10::intrusive_ptr<c10::TensorImpl>::reclaim_copy(impl)),
+                                      version, dt, packed});
+  return packed;
+}
+
 at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset,
                          const at::Tensor& mask, const at::Tensor& bias, int64_t stride_h, int64_t stride_w,
                          int64_t pad_h, int64_t pad_w, int64_t dilation_h, int64_t dilation_w, int64_t n_weight_grps,
                          int64_t n_offset_grps, bool use_mask) {
-  at::Tensor input_c = input.contiguous(), offset_c = offset.contiguous(), weight_c = weight.contiguous();
+  // a channels-last input is handed to the tensor-core path as it is (no NCHW -> NHWC staging pass)
+  const bool nhwc_in = input.dim() == 4 && !input.is_contiguous() && input.is_contiguous(at::MemoryFormat::ChannelsLast);
+  at::Tensor input_c = nhwc_in ? input : input.contiguous(), offset_c = offset.contiguous(), weight_c = weight.contiguous();
   at::Tensor mask_c = mask.contiguous(), bias_c = bias.contiguous();
   TORCH_CHECK(input_c.ndimension() == 4);
   TORCH_CHECK(offset_c.ndimension() == 4);
@@ -437,12 +477,16 @@ at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, cons
                                                          (int)kw, (int)out_h, (int)out_w, (int)n_weight_grps,
                                                          (int)n_offset_grps);
   at::Tensor ws = workspace(wsb, input_c);
-  check_rc(vb200_deform_conv2d_forward(input_c.data_ptr(), weight_c.data_ptr(), offset_c.data_ptr(),
-                                       use_mask ? mask_c.data_ptr() : nullptr, bias_c.data_ptr(), out.data_ptr(), dt,
-                                       (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out, (int)kh, (int)kw,
-                                       (int)stride_h, (int)stride_w, (int)pad_h, (int)pad_w, (int)dilation_h,
-                                       (int)dilation_w, (int)n_weight_grps, (int)n_offset_grps, use_mask ? 1 : 0,
-                                       wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+  at::Tensor packed = wsb ? packed_weight_for(weight_c, dt, (int)c_in, (int)c_out, (int)kh, (int)kw, (int)n_weight_grps, (int)n_offset_grps)
+                          : at::Tensor();
+  const bool nhwc_ok = nhwc_in && wsb > 0 && ((uintptr_t)input_c.data_ptr() % 16) == 0;      // wsb > 0 <=> tensor-core path
+  if (nhwc_in && !nhwc_ok) input_c = input.contiguous();
+  check_rc(vb200_deform_conv2d_forward_ex(input_c.data_ptr(), weight_c.data_ptr(), packed.defined() ? packed.data_ptr() : nullptr,
+                                          nhwc_ok ? 1 : 0, offset_c.data_ptr(), use_mask ? mask_c.data_ptr() : nullptr, bias_c.data_ptr(),
+                                          out.data_ptr(), dt, (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out, (int)kh, (int)kw,
+                                          (int)stride_h, (int)stride_w, (int)pad_h, (int)pad_w, (int)dilation_h, (int)dilation_w,
+                                          (int)n_weight_grps, (int)n_offset_grps, use_mask ? 1 : 0, wsb ? ws.data_ptr() : nullptr, wsb,
+                                          cur_stream()),
            "deform_conv2d");
   return out;
 }
