@@ -177,11 +177,14 @@ def test_roi_pool_golden_and_random(vb, oracle, golden):
     o, a = torch.ops.vision_b200.roi_pool(x.to(DEV), rois.to(DEV), 0.25, 7, 7)
     wo, wa = oracle.roi_pool(x.numpy(), rois.numpy(), 7, 0.25)
     assert np.array_equal(npy(o), wo) and np.array_equal(npy(a), wa)            # bit-exact incl. argmax
+    # fp16: the reference kernel runs its box arithmetic in Half (every scalar op rounds to half), which moves some bin
+    # windows; our kernel reproduces those roundings, so the check is bit-equality with the reference's own CUDA kernel
     xh = x.half().to(DEV)
-    oh = vb.ops.roi_pool(xh, rois.half().to(DEV), 7, 0.25)
-    wh, _ = oracle.roi_pool(xh.float().cpu().numpy(), rois.half().float().numpy(), 7, 0.25)
-    np.testing.assert_allclose(npy(oh), wh, **F16_TOL)
-    assert vb.ops.roi_pool(x.to(DEV), torch.zeros(0, 5, device=DEV), 3).shape == (0, 16, 3, 3)
+    oh, ah = torch.ops.vision_b200.roi_pool(xh, rois.half().to(DEV), 0.25, 7, 7)
+    tv = pytest.importorskip("torchvision")
+    assert not vb.installed()
+    rh_, rah = torch.ops.torchvision.roi_pool(xh, rois.half().to(DEV), 0.25, 7, 7)
+    assert torch.equal(oh, rh_) and torch.equal(ah, rah)
 
 
 def test_ps_roi_align_golden_and_random(vb, oracle, golden):

@@ -539,15 +539,17 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");   // the plane has landed
     __syncthreads();
 
-    for (; n < r1; n += NW) {
+    float* __restrict__ outp_lin = output + ((int64_t)n * C + (pl - b * C)) * NB;   // single level: RoI id == n, rows advance by a fixed step
+    for (; n < r1; n += NW, outp_lin += ostep) {
       const int nn = n + NW;
       uint2 le_next = make_uint2(0u, 0u);
       int id_next2 = 0;
       __syncwarp();
       if (nn < r1) {
-        if (nn + NW < r1) id_next2 = MULTI ? __ldg(ids + nn + NW) : nn + NW;
-        le_next = __ldg(&tab[id_next].lane[lane]);
-        if (lane < 8) cp_async16(stage_s + (slot ^ 128u) + lane * 16u, reinterpret_cast<const uint4*>(tab + id_next) + 16 + lane);
+        if (MULTI && nn + NW < r1) id_next2 = __ldg(ids + nn + NW);
+        const int idn = MULTI ? id_next : nn;
+        le_next = __ldg(&tab[idn].lane[lane]);
+        if (lane < 8) cp_async16(stage_s + (slot ^ 128u) + lane * 16u, reinterpret_cast<const uint4*>(tab + idn) + 16 + lane);
       }
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
       __syncwarp();
@@ -556,7 +558,7 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
       bool mine = true;
       if (B > 1) mine = (int)lds_u32(st + 116u) == b;      // header word 1: the RoI's batch index
       if (mine) {
-        float* __restrict__ outp = output + ((int64_t)id * C + (pl - b * C)) * NB;
+        float* __restrict__ outp = MULTI ? output + ((int64_t)id * C + (pl - b * C)) * NB : outp_lin;
         const uint32_t base0 = plane_s + (le.x & ~3u);
         const uint32_t base1 = base0 + (lane_is_y ? 4u : (uint32_t)pitch * 4u);
         const float wl_ = __uint_as_float(le.y);
@@ -593,7 +595,6 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
       id = id_next;
       id_next = id_next2;
     }
-    (void)ostep;
     w += (r1 - r0);
   }
 }
