@@ -127,3 +127,75 @@ def test_sharded_gather_gloo_world2():
         p.join(timeout=60)
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] and r[2] for r in results)
+
+
+# ---- round 2: fake (meta) kernels, autograd registration, fused-caller gating - all without a GPU ----
+def test_fake_kernels_give_reference_shapes():
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    vision_b200._lib.load_ops()
+    ops = torch.ops.vision_b200
+    with FakeTensorMode():
+        x = torch.empty(2, 50, 20, 30, device="cuda")
+        r = torch.empty(7, 5, device="cuda")
+        assert ops.roi_align(x, r, 0.5, 7, 5, 2, False).shape == (7, 50, 7, 5)
+        o, a = ops.roi_pool(x, r, 0.5, 3, 3)
+        assert o.shape == (7, 50, 3, 3) and a.dtype == torch.int32
+        o, m = ops.ps_roi_align(x, r, 0.5, 5, 5, 2)
+        assert o.shape == (7, 2, 5, 5) and m.dtype == torch.int32
+        o, m = ops.ps_roi_pool(x, r, 0.5, 5, 5)
+        assert o.shape == (7, 2, 5, 5)
+        assert ops._roi_align_backward(torch.empty(7, 50, 7, 5, device="cuda"), r, 0.5, 7, 5, 2, 50, 20, 30, 2, False).shape == (2, 50, 20, 30)
+        assert ops.resize(x, 9, 11, 0, True).shape == (2, 50, 9, 11)
+        w = torch.empty(8, 50, 3, 3, device="cuda")
+        off = torch.empty(2, 18, 20, 30, device="cuda")
+        msk = torch.empty(2, 9, 20, 30, device="cuda")
+        out = ops.deform_conv2d(x, w, off, msk, torch.empty(8, device="cuda"), 1, 1, 1, 1, 1, 1, 1, 1, True)
+        assert out.shape == (2, 8, 20, 30)
+        feats = [torch.empty(2, 16, 40 // s, 48 // s, device="cuda") for s in (1, 2, 4)]
+        o, lv = ops.multiscale_roi_align(feats, r, [0.25, 0.125, 0.0625], 7, 7, 2, 2, 4, 224.0, 4.0, 1e-6)
+        assert o.shape == (7, 16, 7, 7) and lv.shape == (7,) and lv.dtype == torch.int32
+
+
+def test_fused_caller_gating_and_crop_arithmetic():
+    import torch
+    from vision_b200 import ops as vops, transforms as vtf
+    from torchvision.transforms import InterpolationMode
+
+    # CPU tensors never take the fused paths (install() then calls the reference body)
+    feats = [torch.rand(1, 4, 32 // s, 32 // s) for s in (1, 2)]
+    assert not vops.multiscale_roi_align_supported(feats, [torch.rand(3, 4)], (7, 7), 2)
+    assert not vtf.classification_preprocess_supported(torch.zeros(3, 300, 400, dtype=torch.uint8), [224], [256], InterpolationMode.BILINEAR, True)
+    # output-size rule of the preset: shorter edge to resize_size, then the centred crop (transforms/functional.py:353-384, center_crop)
+    assert vtf.compute_resized_output_size((375, 500), size=[256]) == [256, 341]
+    assert vtf._crop_hw([224]) == (224, 224) and vtf._crop_hw((200, 210)) == (200, 210)
+    with pytest.raises(RuntimeError, match="unsupported input"):
+        vtf.classification_preprocess(torch.zeros(3, 300, 400), [224], [256], (0.5,) * 3, (0.5,) * 3)
+    from vision_b200 import detection
+    assert not detection._fusable(torch.rand(4, 4))
+
+
+def test_install_rebinds_and_restores_python_entry_points():
+    import torchvision
+    from torchvision.models.detection import roi_heads, rpn
+    from torchvision.ops import poolers
+    from torchvision.transforms import _presets
+
+    before = (torchvision.ops.boxes.batched_nms, poolers._multiscale_roi_align, roi_heads.RoIHeads.postprocess_detections,
+              rpn.RegionProposalNetwork.filter_proposals, _presets.ImageClassification.forward)
+    vision_b200.install()
+    try:
+        during = (torchvision.ops.boxes.batched_nms, poolers._multiscale_roi_align, roi_heads.RoIHeads.postprocess_detections,
+                  rpn.RegionProposalNetwork.filter_proposals, _presets.ImageClassification.forward)
+        assert all(a is not b for a, b in zip(before, during))
+        # CPU inputs still run the reference bodies through the rebinding
+        import torch
+        b = torch.tensor([[0.0, 0, 10, 10], [1, 1, 11, 11], [50, 50, 60, 60]])
+        keep = torchvision.ops.batched_nms(b, torch.tensor([0.9, 0.8, 0.7]), torch.tensor([0, 0, 1]), 0.5)
+        assert keep.tolist() == [0, 2]
+    finally:
+        vision_b200.uninstall()
+    after = (torchvision.ops.boxes.batched_nms, poolers._multiscale_roi_align, roi_heads.RoIHeads.postprocess_detections,
+             rpn.RegionProposalNetwork.filter_proposals, _presets.ImageClassification.forward)
+    assert all(a is b for a, b in zip(before, after))
