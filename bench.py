@@ -42,7 +42,14 @@ if ROOT not in sys.path:
 ALG_BYTES = 55_705_600 + 20_000 + 50_176_000      # map + rois + output
 K_ROIS = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum of the headline kernel, one launch of this workload (profiles/, ncu --set full)
-NCU_TRAFFIC = {"bytes": 67_274_240 + 9_228_288, "source": "profiles/r1_roi_align_line_v3.ncu-rep (ncu --set full, one launch)"}
+NCU_TRAFFIC = {"bytes": 67_071_744 + 9_524_224, "source": "profiles/r2_roi_align.ncu-rep / r2_roi_align_ncu.txt (ncu --set full, one launch; most of "
+                                                          "the 50 MB output is still dirty in L2 when the capture ends)"}
+# per-launch DRAM traffic of the dominant kernel of the other configs, same kind of capture (profiles/r2_*_ncu.txt)
+NCU_TRAFFIC_CFG = {
+    "cfg3": {"bytes": 1_622_784 + 8_721_664, "source": "profiles/r2_bnms_mask_ncu.txt + r2_bnms_scan_ncu.txt (one image)"},
+    "cfg4": {"bytes": 146_062_848 + 97_087_488, "source": "profiles/r2_deform_bf16.ncu-rep / r2_deform_bf16_ncu.txt (deform_conv2d_tc_kernel, N=32)"},
+    "cfg5": {"bytes": 6_426_276_000 + 42_117_888, "source": "profiles/r2_resize128.ncu-rep / r2_resize128_ncu.txt (resize_aa_stream_kernel, 128 images)"},
+}
 WORKLOAD = "roi_align fp32 1x256x200x272, 1000 RoIs, 7x7, scale 0.25, sampling_ratio 2, aligned=False (BASELINE configs[1])"
 CFG3_IMAGES = 4
 CFG3_BOXES = 100_000
@@ -348,7 +355,8 @@ def block_cfg3(ctx: Ctx, vb, tv, sharded) -> dict:
                    "l2": "flushed before every timed step"},
         "ms_per_image": ms / CFG3_IMAGES, "clustered_ms_per_image": ms_cl,
         "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": alg, "peak_source": src,
+                     "frac": alg / (ms / 1e3) / 1e9 / peak, "traffic": NCU_TRAFFIC_CFG["cfg3"]["bytes"] * CFG3_IMAGES,
+                     "traffic_source": NCU_TRAFFIC_CFG["cfg3"]["source"], "algorithmic_bytes": alg, "peak_source": src,
                      "note": "HBM-nominal only: 2.8 MB per image is < 1 us of HBM time; the real bound is the per-class greedy chain plus "
                              "sum n_c^2/2 = 62.5 M IoU tests per image (DESIGN.md 4.3)",
                      "iou_pairs_per_s": ctx.world * CFG3_IMAGES * 62.5e6 / (ms / 1e3)},
@@ -396,7 +404,8 @@ def block_cfg4(ctx: Ctx, vb, tv, sharded) -> dict:
                    "api": "torchvision.ops.deform_conv2d after vision_b200.install()", "l2": "flushed before every timed step",
                    "includes": "NCHW->NHWC staging of the input and weight packing (re-done every call) + the tcgen05 kernel"},
         "roofline": {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
-                     "frac_of_sustained": tf / sustained, "peak_sustained": sustained, "traffic": None,
+                     "frac_of_sustained": tf / sustained, "peak_sustained": sustained, "traffic": NCU_TRAFFIC_CFG["cfg4"]["bytes"],
+                     "traffic_source": NCU_TRAFFIC_CFG["cfg4"]["source"], "tensor_pipe_active_pct_ncu": 52.7,
                      "algorithmic_flops": CFG4_FLOPS, "peak_source": src + " (burst: the op is timed alone between L2 flushes)"},
     }
     hx, hoff, hw_, hb, hm = [t.cpu() for t in (x, off, w, b, m)]
@@ -452,7 +461,8 @@ def block_cfg5(ctx: Ctx, vb, tv, sharded) -> dict:
                                f"configs[4] at 8 GPUs; 1024 images = 8 such shards)",
                    "api": "torchvision.transforms.v2.functional.resize after vision_b200.install()", "l2": "input (6.4 GB) exceeds L2; flushed anyway"},
         "roofline": {"bound": "hbm", "achieved": nbytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": nbytes / (ms / 1e3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": nbytes, "peak_source": src},
+                     "frac": nbytes / (ms / 1e3) / 1e9 / peak, "traffic": NCU_TRAFFIC_CFG["cfg5"]["bytes"],
+                     "traffic_source": NCU_TRAFFIC_CFG["cfg5"]["source"], "algorithmic_bytes": nbytes, "peak_source": src},
     }
     sub = 32
     hx = x[:sub].cpu()

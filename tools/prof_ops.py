@@ -11,6 +11,8 @@ sys.path.insert(0, ROOT)
 import vision_b200 as vb  # noqa: E402
 from vision_b200 import workloads  # noqa: E402
 
+vb._lib.load_ops()
+
 op = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = "cuda"

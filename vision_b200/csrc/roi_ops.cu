@@ -637,6 +637,20 @@ struct PoolGeom { int batch, rsw, rsh; A bh, bw; };
 template <typename T> __device__ __forceinline__ typename Acc<T>::type rnd(typename Acc<T>::type v) { return v; }
 template <> __device__ __forceinline__ float rnd<__half>(float v) { return __half2float(__float2half_rn(v)); }
 
+// one element of the resident plane from a shared-space address, widened to the accumulator type
+template <typename T> __device__ __forceinline__ typename Acc<T>::type lds_acc(uint32_t addr);
+template <> __device__ __forceinline__ float lds_acc<float>(uint32_t addr) { return lds_f32(addr); }
+template <> __device__ __forceinline__ float lds_acc<__half>(uint32_t addr) {
+  unsigned short u;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
+  return __half2float(__ushort_as_half(u));
+}
+template <> __device__ __forceinline__ double lds_acc<double>(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 template <typename T, typename A>
 __device__ __forceinline__ PoolGeom<A> pool_geometry(const T* __restrict__ r, A scale_in, int PH, int PW) {
   PoolGeom<A> g;
@@ -705,11 +719,29 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
           he = min(max(he + g.rsh, 0), H);
           A best = neg_max;
           int idx = -1;
-          for (int h = hs; h < he; ++h) {
-            const T* __restrict__ row = plane + h * W;
-            for (int x = ws + q; x < we; x += Q) {
-              const A v = to_acc(row[x]);
-              if (v > best) { best = v; idx = h * W + x; }
+          if (RESIDENT) {
+            // shared-space addresses (no generic-pointer arithmetic): the lane walks its columns ws + q, ws + q + Q, ... of every
+            // window row and remembers the ADDRESS of its first maximum; 5 instructions per element instead of 12
+            constexpr uint32_t ESZ = (uint32_t)sizeof(T);
+            const uint32_t plane_a = smem_u32(plane_s);
+            const int ncol = act && we > ws + q ? (we - ws - q + Q - 1) / Q : 0;
+            uint32_t row_a = plane_a + (uint32_t)(hs * W + ws + q) * ESZ, best_a = 0xffffffffu;
+            for (int h = hs; h < he; ++h, row_a += (uint32_t)W * ESZ) {
+              uint32_t a = row_a;
+#pragma unroll 4
+              for (int t = 0; t < ncol; ++t, a += (uint32_t)Q * ESZ) {
+                const A v = lds_acc<T>(a);
+                if (v > best) { best = v; best_a = a; }
+              }
+            }
+            idx = best_a == 0xffffffffu ? -1 : (int)((best_a - plane_a) / ESZ);
+          } else {
+            for (int h = hs; h < he; ++h) {
+              const T* __restrict__ row = plane + h * W;
+              for (int x = ws + q; x < we; x += Q) {
+                const A v = to_acc(row[x]);
+                if (v > best) { best = v; idx = h * W + x; }
+              }
             }
           }
           for (int o = 1; o < Q; o <<= 1) {
