@@ -277,6 +277,14 @@ VB200_API int vb200_deform_conv2d_backward_inputs(const void* dcol, const void* 
 VB200_API int vb200_resize(const void* input, void* output, int dtype, int64_t planes, int in_h, int in_w,
                  int out_h, int out_w, int mode, int antialias, vb200_stream stream);
 
+/* ---- box_iou_rotated (API completeness) ------------------
+ * Replaces box_iou_rotated_cuda, csrc/ops/cuda/box_iou_rotated_kernel.cu:92-160 (schema torchvision::box_iou_rotated,
+ * csrc/ops/box_iou_rotated.cpp).  boxes1 [n1, 5], boxes2 [n2, 5] as (x_ctr, y_ctr, w, h, angle in degrees), F32;
+ * ious [n1, n2] F32.  The intersection area is found by clipping (Sutherland-Hodgman) instead of the reference's
+ * intersection points + convex hull: same area up to fp32 rounding. */
+VB200_API int vb200_box_iou_rotated(const void* boxes1, const void* boxes2, float* ious, int dtype, int64_t n1, int64_t n2,
+                          vb200_stream stream);
+
 /* ---- fused inference preprocessing --------------------------------------
  * Replaces ImageClassification.forward, torchvision/transforms/_presets.py:57-64 (resize -> center_crop ->
  * convert_image_dtype(float) -> normalize) with one launch: only the crop window [crop_top, +crop_h) x [crop_left, +crop_w)

@@ -134,6 +134,26 @@ def ps_roi_pool(inp, rois, output_size, spatial_scale=1.0):
     return out, cm
 
 
+def box_iou_rotated(boxes1, boxes2) -> np.ndarray:
+    """[n1, 5] x [n2, 5] boxes (x_ctr, y_ctr, w, h, angle in degrees) -> [n1, n2] IoU."""
+    b1, b2 = _f32(boxes1).reshape(-1, 5), _f32(boxes2).reshape(-1, 5)
+    out = np.zeros((b1.shape[0], b2.shape[0]), dtype=np.float32)
+    lib().orc_box_iou_rotated_f32(_p(b1), b1.shape[0], _p(b2), b2.shape[0], _p(out))
+    return out
+
+
+def box_iou_rotated_ref(boxes1, boxes2):
+    """The reference's own arithmetic (oracle/_ref, compiled from /root/reference's header); None when it was not built."""
+    path = os.path.join(_HERE, "_ref", "libbox_iou_rotated_ref.so")
+    if not os.path.exists(path):
+        return None
+    ref = ctypes.CDLL(path)
+    b1, b2 = _f32(boxes1).reshape(-1, 5), _f32(boxes2).reshape(-1, 5)
+    out = np.zeros((b1.shape[0], b2.shape[0]), dtype=np.float32)
+    ref.ref_box_iou_rotated_f32(_p(b1), b1.shape[0], _p(b2), b2.shape[0], _p(out))
+    return out
+
+
 def deform_conv2d(inp, offset, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
                   mask=None) -> np.ndarray:
     inp, offset, weight = _f32(inp), _f32(offset), _f32(weight)

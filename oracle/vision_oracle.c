@@ -767,3 +767,133 @@ ORC_API void orc_ps_roi_pool_f32(const float* input, const float* rois, int chan
         }
   }
 }
+
+/* ------------------------------------------------------------------------ */
+/* box_iou_rotated — torchvision/csrc/ops/box_iou_rotated_utils.h:67-383     */
+/* (rotated-rectangle IoU: vertices, edge/edge intersections + contained     */
+/* vertices, Graham scan, fan area; CPU variant of the hull's sort) driven   */
+/* as csrc/ops/cpu/box_iou_rotated_kernel.cpp:28-55 does.  Boxes are          */
+/* (x_ctr, y_ctr, w, h, angle in degrees).  The float / double promotions of  */
+/* the header are kept (EPS and the literal thresholds are doubles, the       */
+/* centre shift and the final /2.0 go through double).  Pinned bit for bit    */
+/* against oracle/_ref/libbox_iou_rotated_ref.so (the header itself compiled  */
+/* from /root/reference) in tests/test_oracle.py and through                  */
+/* tests/golden/box_iou_rotated.npz.                                          */
+/* ------------------------------------------------------------------------ */
+typedef struct { float x, y; } RPt;
+static inline float rdot(RPt a, RPt b) { return a.x * b.x + a.y * b.y; }
+static inline float rcross(RPt a, RPt b) { return a.x * b.y - b.x * a.y; }
+static inline RPt rsub(RPt a, RPt b) { RPt r = {a.x - b.x, a.y - b.y}; return r; }
+
+static void rot_vertices(float xc, float yc, float w, float h, float a, RPt* pts) {
+  double theta = a * 0.01745329251;
+  float c2 = (float)cos(theta) * 0.5f, s2 = (float)sin(theta) * 0.5f;
+  pts[0].x = xc + s2 * h + c2 * w;
+  pts[0].y = yc + c2 * h - s2 * w;
+  pts[1].x = xc - s2 * h + c2 * w;
+  pts[1].y = yc - c2 * h - s2 * w;
+  pts[2].x = 2 * xc - pts[0].x;
+  pts[2].y = 2 * yc - pts[0].y;
+  pts[3].x = 2 * xc - pts[1].x;
+  pts[3].y = 2 * yc - pts[1].y;
+}
+
+static int rot_intersections(const RPt* p1, const RPt* p2, RPt* out) {
+  RPt v1[4], v2[4];
+  for (int i = 0; i < 4; ++i) { v1[i] = rsub(p1[(i + 1) % 4], p1[i]); v2[i] = rsub(p2[(i + 1) % 4], p2[i]); }
+  const double EPS = 1e-5;
+  int num = 0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float det = rcross(v2[j], v1[i]);
+      if (fabs((double)det) <= 1e-14) continue;
+      RPt v12 = rsub(p2[j], p1[i]);
+      float t1 = rcross(v2[j], v12) / det;
+      float t2 = rcross(v1[i], v12) / det;
+      if (t1 > -EPS && t1 < 1.0f + EPS && t2 > -EPS && t2 < 1.0f + EPS) {
+        out[num].x = p1[i].x + v1[i].x * t1;
+        out[num].y = p1[i].y + v1[i].y * t1;
+        ++num;
+      }
+    }
+  {
+    RPt AB = v2[0], DA = v2[3];
+    float ABdotAB = rdot(AB, AB), ADdotAD = rdot(DA, DA);
+    for (int i = 0; i < 4; ++i) {
+      RPt AP = rsub(p1[i], p2[0]);
+      float APdotAB = rdot(AP, AB), APdotAD = -rdot(AP, DA);
+      if ((APdotAB > -EPS) && (APdotAD > -EPS) && (APdotAB < ABdotAB + EPS) && (APdotAD < ADdotAD + EPS)) out[num++] = p1[i];
+    }
+  }
+  {
+    RPt AB = v1[0], DA = v1[3];
+    float ABdotAB = rdot(AB, AB), ADdotAD = rdot(DA, DA);
+    for (int i = 0; i < 4; ++i) {
+      RPt AP = rsub(p2[i], p1[0]);
+      float APdotAB = rdot(AP, AB), APdotAD = -rdot(AP, DA);
+      if ((APdotAB > -EPS) && (APdotAD > -EPS) && (APdotAB < ABdotAB + EPS) && (APdotAD < ADdotAD + EPS)) out[num++] = p2[i];
+    }
+  }
+  return num;
+}
+
+static int rot_hull(const RPt* p, int n, RPt* q) {
+  int t = 0;
+  for (int i = 1; i < n; ++i)
+    if (p[i].y < p[t].y || (p[i].y == p[t].y && p[i].x < p[t].x)) t = i;
+  RPt start = p[t];
+  for (int i = 0; i < n; ++i) q[i] = rsub(p[i], start);
+  RPt tmp = q[0]; q[0] = q[t]; q[t] = tmp;
+  float dist[24];
+  for (int i = 0; i < n; ++i) dist[i] = rdot(q[i], q[i]);
+  for (int i = 1; i < n - 1; ++i)
+    for (int j = i + 1; j < n; ++j) {
+      float cp = rcross(q[i], q[j]);
+      if ((cp < -1e-6) || (fabs((double)cp) < 1e-6 && dist[i] > dist[j])) {
+        RPt qt = q[i]; q[i] = q[j]; q[j] = qt;
+        float dt = dist[i]; dist[i] = dist[j]; dist[j] = dt;
+      }
+    }
+  for (int i = 0; i < n; ++i) dist[i] = rdot(q[i], q[i]);
+  int k;
+  for (k = 1; k < n; ++k)
+    if (dist[k] > 1e-8) break;
+  if (k == n) { q[0] = p[t]; return 1; }
+  q[1] = q[k];
+  int m = 2;
+  for (int i = k + 1; i < n; ++i) {
+    while (m > 1) {
+      RPt q1 = rsub(q[i], q[m - 2]), q2 = rsub(q[m - 1], q[m - 2]);
+      if (q1.x * q2.y >= q2.x * q1.y) m--; else break;
+    }
+    q[m++] = q[i];
+  }
+  return m;       /* shift_to_zero = true: the area does not need the original coordinates */
+}
+
+static float rot_iou_one(const float* b1, const float* b2) {
+  double csx = (b1[0] + b2[0]) / 2.0, csy = (b1[1] + b2[1]) / 2.0;
+  float x1 = (float)(b1[0] - csx), y1 = (float)(b1[1] - csy), x2 = (float)(b2[0] - csx), y2 = (float)(b2[1] - csy);
+  float area1 = b1[2] * b1[3], area2 = b2[2] * b2[3];
+  if (area1 < 1e-14 || area2 < 1e-14) return 0.f;
+  RPt p1[4], p2[4], inter[24], ordered[24];
+  rot_vertices(x1, y1, b1[2], b1[3], b1[4], p1);
+  rot_vertices(x2, y2, b2[2], b2[3], b2[4], p2);
+  int num = rot_intersections(p1, p2, inter);
+  float intersection = 0.f;
+  if (num > 2) {
+    int m = rot_hull(inter, num, ordered);
+    if (m > 2) {
+      float area = 0.f;
+      for (int i = 1; i < m - 1; ++i) area += (float)fabs((double)rcross(rsub(ordered[i], ordered[0]), rsub(ordered[i + 1], ordered[0])));
+      intersection = (float)(area / 2.0);
+    }
+  }
+  float iou = intersection / (area1 + area2 - intersection);
+  return (iou < 0) ? 0 : (iou > 1 ? 1 : iou);
+}
+
+ORC_API void orc_box_iou_rotated_f32(const float* boxes1, int n1, const float* boxes2, int n2, float* ious) {
+  for (int i = 0; i < n1; ++i)
+    for (int j = 0; j < n2; ++j) ious[(int64_t)i * n2 + j] = rot_iou_one(boxes1 + 5 * i, boxes2 + 5 * j);
+}

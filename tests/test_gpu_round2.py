@@ -6,6 +6,8 @@
 * deform_conv2d at BASELINE configs[3] FULL size (N=32, 512->512, 64x64, bf16) against the reference CUDA op run in
   fp32 on the bf16-rounded inputs, tolerance 1e-2 as north_star states.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -648,3 +650,28 @@ def test_deform_conv2d_packed_weight_cache_and_channels_last(vb):
         fourth = vb.ops.deform_conv2d(x, off, w, b, 1, 1, 1, m)
         w2 = w.clone()
         assert torch.equal(fourth, vb.ops.deform_conv2d(x, off, w2, b, 1, 1, 1, m)) and not torch.equal(fourth, first)
+
+
+def test_box_iou_rotated_vs_oracle_and_golden(vb, oracle):
+    """Clipping-based kernel vs the oracle (itself bit-identical to the reference header, tests/test_oracle.py) and the fixture
+    generated by the reference's own code.  The algorithms differ (clipping vs intersection points + hull), so the bound is a
+    tolerance: 1e-5 absolute on the IoU, except pairs whose intersection is a sliver below the reference's own epsilons."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "box_iou_rotated.npz"))
+    b1, b2 = torch.from_numpy(g["boxes1"]).to(DEV), torch.from_numpy(g["boxes2"]).to(DEV)
+    before = vb.launch_count()
+    got = vb.ops.box_iou_rotated(b1, b2)
+    assert vb.launch_count() == before + 1 and got.shape == (257, 193) and got.dtype == torch.float32
+    err = np.abs(npy(got) - g["ious"])
+    assert err.max() <= 2e-5, (err.max(), np.unravel_index(err.argmax(), err.shape))
+    np.testing.assert_allclose(npy(vb.ops.box_iou_rotated(torch.from_numpy(g["unit1"]).to(DEV), torch.from_numpy(g["unit2"]).to(DEV))),
+                               g["unit_ious"], atol=1e-6)
+    rng = np.random.default_rng(11)
+    for n1, n2, span in ((1, 1, 10.0), (33, 65, 50.0), (1000, 777, 400.0)):
+        c = rng.uniform(0, span, (n1 + n2, 2)); wh = np.exp(rng.uniform(0, 4.5, (n1 + n2, 2))); a = rng.uniform(-720, 720, (n1 + n2, 1))
+        b = np.concatenate([c, wh, a], 1).astype(np.float32)
+        want = oracle.box_iou_rotated(b[:n1], b[n1:])
+        got = npy(vb.ops.box_iou_rotated(torch.from_numpy(b[:n1]).to(DEV), torch.from_numpy(b[n1:]).to(DEV)))
+        assert np.abs(got - want).max() <= 2e-5
+    assert vb.ops.box_iou_rotated(torch.zeros(0, 5, device=DEV), b2).shape == (0, 193)
+    with pytest.raises(RuntimeError, match="Tensor\\[N, 5\\]"):
+        vb.ops.box_iou_rotated(torch.zeros(3, 4, device=DEV), b2)

@@ -1,6 +1,8 @@
 """CPU suite, part 1: the oracle is pinned — against the committed golden vectors (produced by the
 reference's own CPU kernels, tests/golden/gen_golden.py) and, when torchvision is importable here,
 against the reference live on fresh seeds."""
+import os
+
 import numpy as np
 import pytest
 
@@ -253,3 +255,21 @@ def test_resize_random_sizes_live(oracle, seed):
         for aa in (False, True):
             want = F.interpolate(x, size=[oh, ow], mode=mode, align_corners=False, antialias=aa).numpy()
             np.testing.assert_allclose(oracle.resize(x.numpy(), (oh, ow), code, aa), want, rtol=0, atol=5e-6)   # ATen vectorises the sums
+
+
+# ---- box_iou_rotated: the oracle against the reference header itself (oracle/_ref) and the fixture made from it ----
+def test_box_iou_rotated_golden_and_ref(oracle):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "box_iou_rotated.npz"))
+    assert np.array_equal(oracle.box_iou_rotated(g["boxes1"], g["boxes2"]), g["ious"])          # bit for bit
+    u = oracle.box_iou_rotated(g["unit1"], g["unit2"])
+    assert np.array_equal(u, g["unit_ious"])
+    assert abs(u[0, 0] - 1.0) < 1e-6 and abs(u[0, 1] - 1.0 / 3.0) < 1e-6 and abs(u[0, 2] - 1.0) < 1e-6   # unit squares: 1, 1/3, 1 (90 degrees)
+    rng = np.random.default_rng(7)
+    c = rng.uniform(0, 100, (150, 2)); wh = np.exp(rng.uniform(0, 4, (150, 2))); a = rng.uniform(-360, 360, (150, 1))
+    b = np.concatenate([c, wh, a], 1).astype(np.float32)
+    ref = oracle.box_iou_rotated_ref(b, b[::-1].copy())
+    if ref is not None:                                     # build container: the reference's own code, live
+        assert np.array_equal(oracle.box_iou_rotated(b, b[::-1].copy()), ref)
+    iou = oracle.box_iou_rotated(b, b)
+    assert np.allclose(np.diag(iou), 1.0, atol=1e-5) and np.all(iou >= 0) and np.all(iou <= 1)
+    np.testing.assert_allclose(iou, iou.T, atol=2e-5)       # symmetric up to the order of operations

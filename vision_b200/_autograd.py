@@ -164,6 +164,10 @@ def register() -> None:
         n = ctx.new_dynamic_size()
         return boxes.new_empty((n,), dtype=torch.int64)
 
+    @lib.register_fake("vision_b200::box_iou_rotated")
+    def _(boxes1, boxes2):
+        return boxes1.new_empty((boxes1.size(0), boxes2.size(0)))
+
     # ---- resize ----
     @lib.register_fake("vision_b200::resize")
     def _(inp, out_h, out_w, mode, antialias):

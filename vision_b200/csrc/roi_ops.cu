@@ -679,9 +679,10 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
   const int64_t per = (total + gridDim.x - 1) / gridDim.x;
   const int64_t w0 = (int64_t)blockIdx.x * per, w1 = min(total, w0 + per);
   // lane -> (bin column, sub-lane): Q = largest power of two with PW * Q <= 32 (1 when PW >= 17)
-  int Q = 1;
-  while (PW * Q * 2 <= 32) Q *= 2;
-  const int pw_l = lane / Q, q = lane - pw_l * Q;
+  int qshift = 0;
+  while ((PW << (qshift + 1)) <= 32) ++qshift;
+  const int Q = 1 << qshift, bins_per_pass = 32 >> qshift;
+  const int pw_l = lane >> qshift, q = lane & (Q - 1);
   const A neg_max = (A)-3.402823466e+38F;   // -FLT_MAX for every dtype, as the reference initialises it
 
   int64_t w = w0;
@@ -702,9 +703,9 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
       if (g.batch != b) continue;
       T* __restrict__ outp = output + ((int64_t)n * C + c) * PH * PW;
       int32_t* __restrict__ argp = argmax + ((int64_t)n * C + c) * PH * PW;
-      for (int pw0 = 0; pw0 < PW; pw0 += 32 / Q) {
+      for (int pw0 = 0; pw0 < PW; pw0 += bins_per_pass) {
         const int pw = pw0 + pw_l;
-        const bool act = pw < PW && pw_l < 32 / Q;
+        const bool act = pw < PW;
         int ws = 0, we = 0;
         if (act) {
           ws = (int)floor(rnd<T>(mul_rn(rnd<T>((A)pw), g.bw)));
@@ -712,6 +713,9 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
           ws = min(max(ws + g.rsw, 0), W);
           we = min(max(we + g.rsw, 0), W);
         }
+        // columns this lane scans in every window row: ws + q, ws + q + Q, ...; the warp loops to the widest lane's count
+        const int ncol = act && we > ws + q ? (we - ws - q + Q - 1) >> qshift : 0;
+        const int ncol_max = __reduce_max_sync(0xffffffffu, ncol);
         for (int ph = 0; ph < PH; ++ph) {
           int hs = (int)floor(rnd<T>(mul_rn(rnd<T>((A)ph), g.bh)));
           int he = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(ph + 1)), g.bh)));
@@ -724,14 +728,14 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
             // window row and remembers the ADDRESS of its first maximum; 5 instructions per element instead of 12
             constexpr uint32_t ESZ = (uint32_t)sizeof(T);
             const uint32_t plane_a = smem_u32(plane_s);
-            const int ncol = act && we > ws + q ? (we - ws - q + Q - 1) / Q : 0;
             uint32_t row_a = plane_a + (uint32_t)(hs * W + ws + q) * ESZ, best_a = 0xffffffffu;
             for (int h = hs; h < he; ++h, row_a += (uint32_t)W * ESZ) {
               uint32_t a = row_a;
-#pragma unroll 4
-              for (int t = 0; t < ncol; ++t, a += (uint32_t)Q * ESZ) {
-                const A v = lds_acc<T>(a);
-                if (v > best) { best = v; best_a = a; }
+              for (int t = 0; t < ncol_max; ++t, a += (uint32_t)Q * ESZ) {     // warp-uniform trip count, lanes past their window idle
+                if (t < ncol) {
+                  const A v = lds_acc<T>(a);
+                  if (v > best) { best = v; best_a = a; }
+                }
               }
             }
             idx = best_a == 0xffffffffu ? -1 : (int)((best_a - plane_a) / ESZ);

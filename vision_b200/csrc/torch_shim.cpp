@@ -602,6 +602,20 @@ at::Tensor resize_crop_normalize(const at::Tensor& input, int64_t resize_h, int6
   return out;
 }
 
+// ---- box_iou_rotated (csrc/ops/box_iou_rotated.cpp; checks as cuda/box_iou_rotated_kernel.cu:92-118) ----------------
+at::Tensor box_iou_rotated(const at::Tensor& boxes1, const at::Tensor& boxes2) {
+  TORCH_CHECK(boxes1.is_cuda() && boxes2.is_cuda(), "boxes1 and boxes2 must be CUDA tensors");
+  TORCH_CHECK(boxes1.dim() == 2 && boxes1.size(1) == 5 && boxes2.dim() == 2 && boxes2.size(1) == 5, "boxes must have shape as Tensor[N, 5]");
+  TORCH_CHECK(boxes1.scalar_type() == at::kFloat && boxes2.scalar_type() == at::kFloat, "box_iou_rotated: float32 boxes");
+  at::cuda::CUDAGuard guard(boxes1.device());
+  at::Tensor b1 = boxes1.contiguous(), b2 = boxes2.contiguous();
+  at::Tensor out = at::empty({b1.size(0), b2.size(0)}, b1.options());
+  if (out.numel() == 0) return out;
+  check_rc(vb200_box_iou_rotated(b1.data_ptr(), b2.data_ptr(), out.data_ptr<float>(), VB200_F32, b1.size(0), b2.size(0), cur_stream()),
+           "box_iou_rotated");
+  return out;
+}
+
 // ---- install / uninstall -----------------------------------------------------
 std::unique_ptr<torch::Library> g_override;
 
@@ -647,6 +661,7 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("_deform_conv2d_backward(Tensor grad, Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> (Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
   m.def("resize_crop_normalize(Tensor input, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w, int mode, bool antialias, float[] mean, float[] std) -> Tensor");
+  m.def("box_iou_rotated(Tensor boxes1, Tensor boxes2) -> Tensor");
   m.def("detection_postprocess(Tensor boxes, Tensor scores, Tensor labels, float img_h, float img_w, float score_thresh, bool score_inclusive, float min_size, float nms_thresh, int topk) -> (Tensor, Tensor, Tensor)");
   m.def("multiscale_roi_align(Tensor[] features, Tensor rois, float[] scales, int pooled_height, int pooled_width, int sampling_ratio, int k_min, int k_max, float canonical_scale, float canonical_level, float eps) -> (Tensor, Tensor)");
   m.def("_roi_align_backward(Tensor grad, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width, int sampling_ratio, bool aligned) -> Tensor");
@@ -677,5 +692,6 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("_ps_roi_pool_backward", TORCH_FN(ps_roi_pool_backward));
   m.impl("detection_postprocess", TORCH_FN(detection_postprocess));
   m.impl("resize_crop_normalize", TORCH_FN(resize_crop_normalize));
+  m.impl("box_iou_rotated", TORCH_FN(box_iou_rotated));
   m.impl("_deform_conv2d_backward", TORCH_FN(deform_conv2d_backward));
 }

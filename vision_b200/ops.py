@@ -45,6 +45,13 @@ def batched_nms(boxes: Tensor, scores: Tensor, idxs: Tensor, iou_threshold: floa
     return _ops().batched_nms(boxes, scores, idxs, float(iou_threshold))
 
 
+def box_iou_rotated(boxes1: Tensor, boxes2: Tensor) -> Tensor:
+    """IoU of rotated boxes in cxcywhr format (torchvision.ops.box_iou(..., fmt="cxcywhr") -> torch.ops.torchvision.box_iou_rotated,
+    torchvision/ops/boxes.py:386-399).  The installed 0.26 wheel has no such op, so this is only reachable as vision_b200.ops."""
+    _require_cuda(boxes1, "boxes1")
+    return _ops().box_iou_rotated(boxes1, boxes2)
+
+
 # ---- RoI ops ------------------------------------------------------------------
 def convert_boxes_to_roi_format(boxes: list[Tensor]) -> Tensor:
     """torchvision/ops/_utils.py:18-25"""
