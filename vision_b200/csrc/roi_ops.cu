@@ -470,15 +470,20 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
   const int off_x = 2 * q * P + grp, off_y = 2 * q + grp * P;       // lane axis x: bin = k * P + grp; y: the transpose
   const bool st0 = grp < P && 2 * q < P, st1 = grp < P && 2 * q + 1 < P;
 
+  // Work is split evenly in COST units.  Single level: cost = (plane, RoI) pairs.  MULTI: a plane of level l costs
+  // K_l + O_l, O_l = the fixed price of switching to it (two barriers, the load latency, its bytes) expressed in pairs -
+  // without it a level that holds a dozen RoIs hands one CTA ~150 plane switches and the whole launch waits for it
+  // (measured: 362 us instead of ~100 us for 1000 boxes over four levels).
   int64_t total = (int64_t)B * C * K;
-  int Kl[kMaxLevels];
+  int Kl[kMaxLevels], Ol[kMaxLevels];
   if (MULTI) {
     asm volatile("griddepcontrol.wait;" ::: "memory");      // the level counts come from the geometry kernel
     total = 0;
 #pragma unroll
     for (int l = 0; l < kMaxLevels; ++l) {
       Kl[l] = l < L.num_levels ? __ldg(lvl_count + l) : 0;
-      total += (int64_t)B * C * Kl[l];
+      Ol[l] = Kl[l] > 0 ? 48 + ((L.lv[l].H * L.lv[l].W) >> 9) : 0;
+      total += (int64_t)B * C * (Kl[l] + Ol[l]);
     }
   }
   const int64_t per = (total + gridDim.x - 1) / gridDim.x;
@@ -492,20 +497,24 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
     int lvl = 0, Kc = K;
     int64_t wl = w;
     const int* __restrict__ ids = nullptr;
+    int cost_c = K, ovh = 0;
     if (MULTI) {
 #pragma unroll
       for (int l = 0; l < kMaxLevels; ++l) {
-        const int64_t pl_ = (int64_t)B * C * Kl[l];
+        const int64_t pl_ = (int64_t)B * C * (Kl[l] + Ol[l]);
         if (lvl == l && wl >= pl_) { wl -= pl_; lvl = l + 1; }
       }
-      Kc = Kl[lvl];
+      Kc = Kl[lvl]; ovh = Ol[lvl]; cost_c = Kc + ovh;
       H = L.lv[lvl].H; W = L.lv[lvl].W; pitch = L.lv[lvl].pitch; input = L.lv[lvl].base;
       ids = bucket + (int64_t)lvl * K;
     }
-    const int pl = (int)(wl / Kc);              // plane index = b * C + c
-    const int r0 = (int)(wl - (int64_t)pl * Kc);
-    const int r1 = (int)min((int64_t)Kc, r0 + (w1 - w));
+    const int pl = (int)(wl / cost_c);              // plane index = b * C + c
+    const int f = (int)(wl - (int64_t)pl * cost_c);  // position inside the plane's cost span: [0, ovh) switch, [ovh, ovh + Kc) RoIs
+    const int span = (int)min((int64_t)(cost_c - f), w1 - w);
+    const int r0 = max(0, f - ovh);
+    const int r1 = min(Kc, f + span - ovh);
     const int b = pl / C;
+    if (r1 <= r0) { w += span; continue; }          // this CTA's share of the plane is switch cost only
     const int64_t ostep = (int64_t)NW * C * NB;
     __syncthreads();                           // everyone is done with the previous plane
     if (H != cur_H || pitch != cur_pitch) {    // (re)zero the pads: columns [W, pitch) of every row and the two zero rows
@@ -595,7 +604,7 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
       id = id_next;
       id_next = id_next2;
     }
-    w += (r1 - r0);
+    w += span;
   }
 }
 
