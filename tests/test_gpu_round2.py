@@ -164,12 +164,15 @@ def test_roi_pool_plane_major_shapes_bit_exact_vs_reference_cuda(vb, oracle, dty
     assert not vb.installed()
     cases = [((2, 5, 40, 52), 300, (7, 7), 0.25), ((1, 3, 30, 30), 1200, (5, 5), 0.5), ((3, 4, 25, 33), 200, (3, 17), 1.0),
              ((1, 2, 64, 48), 2000, (2, 40), 0.5), ((2, 6, 20, 20), 40, (1, 1), 1.0), ((1, 8, 200, 272), 600, (7, 7), 0.25),
+             ((1, 2, 64, 480), 300, (2, 20), 1.0),                        # Q = 1 and bins wider than 8 columns: the plain-loop branch
              ((1, 2, 300, 400), 100, (4, 2), 0.25)]                      # last: fp32 plane 480 KB > shared memory
     for shape, k, (ph, pw), scale in cases:
         b, c, h, w = shape
         g = torch.Generator().manual_seed(k + pw)
         x = torch.randn(*shape, generator=g)
         x[:, :, ::3, ::4] = 0.75                                          # exact ties: the first maximum in row-major order wins
+        x[:, :, 1::5, 2::7] = float("nan")                                 # NaN is never selected (v > best is false)
+        x[:, 0, :4, :] = -0.0                                              # signed zeros: the first one's sign is what comes out
         rois = _rois(k, b, h, w, scale, seed=k)
         xd, rd = x.to(dtype).to(DEV), rois.to(dtype).to(DEV)
         o1, a1 = torch.ops.torchvision.roi_pool(xd, rd, scale, ph, pw)

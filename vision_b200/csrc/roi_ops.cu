@@ -675,6 +675,26 @@ __device__ __forceinline__ PoolGeom<A> pool_geometry(const T* __restrict__ r, A 
   return g;
 }
 
+__device__ __forceinline__ float acc_max(float a, float b) { return fmaxf(a, b); }     // NaN operands are dropped, as `v > best` drops them
+__device__ __forceinline__ double acc_max(double a, double b) { return fmax(a, b); }
+
+// One lane's share of one bin window on the resident plane: rows [hs, he), NC columns at byte offsets off[0..NC) from the row
+// address (entries past the lane's own count repeat its last column: re-reading cannot change a maximum).  The inner loop is
+// LDS + FMNMX per element; the arg-max is kept at ROW granularity (first row whose maximum beats the best so far), the column
+// is recovered afterwards by re-reading that single row left to right - the reference's "first maximum in row-major order".
+template <typename T, int NC>
+__device__ __forceinline__ void pool_scan(uint32_t row_a, uint32_t row_step, const uint32_t (&off)[8], int hs, int he,
+                                          typename Acc<T>::type neg_max, typename Acc<T>::type& best, uint32_t& best_row_a) {
+  using A = typename Acc<T>::type;
+  for (int h = hs; h < he; ++h, row_a += row_step) {
+    A rm = lds_acc<T>(row_a + off[0]);
+#pragma unroll
+    for (int t = 1; t < NC; ++t) rm = acc_max(rm, lds_acc<T>(row_a + off[t]));
+    if (rm > best) { best = rm; best_row_a = row_a; }
+  }
+  (void)neg_max;
+}
+
 template <typename T, bool RESIDENT>
 __global__ void __launch_bounds__(RESIDENT ? 1024 : 256, RESIDENT ? 1 : 4)
 roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T* __restrict__ output,
@@ -725,6 +745,12 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
         // columns this lane scans in every window row: ws + q, ws + q + Q, ...; the warp loops to the widest lane's count
         const int ncol = act && we > ws + q ? (we - ws - q + Q - 1) >> qshift : 0;
         const int ncol_max = __reduce_max_sync(0xffffffffu, ncol);
+        // byte offsets of this lane's columns inside a window row, relative to column col0; a lane with no column of its own
+        // reads column 0 of the plane row range (valid memory) and is ignored afterwards
+        const int col0 = ncol > 0 ? ws + q : 0;
+        uint32_t off[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) off[t] = (uint32_t)(min(t, max(ncol - 1, 0)) << qshift) * (uint32_t)sizeof(T);
         for (int ph = 0; ph < PH; ++ph) {
           int hs = (int)floor(rnd<T>(mul_rn(rnd<T>((A)ph), g.bh)));
           int he = (int)ceil(rnd<T>(mul_rn(rnd<T>((A)(ph + 1)), g.bh)));
@@ -733,21 +759,45 @@ roi_pool_plane_kernel(const T* __restrict__ input, const T* __restrict__ rois, T
           A best = neg_max;
           int idx = -1;
           if (RESIDENT) {
-            // shared-space addresses (no generic-pointer arithmetic): the lane walks its columns ws + q, ws + q + Q, ... of every
-            // window row and remembers the ADDRESS of its first maximum; 5 instructions per element instead of 12
             constexpr uint32_t ESZ = (uint32_t)sizeof(T);
             const uint32_t plane_a = smem_u32(plane_s);
-            uint32_t row_a = plane_a + (uint32_t)(hs * W + ws + q) * ESZ, best_a = 0xffffffffu;
-            for (int h = hs; h < he; ++h, row_a += (uint32_t)W * ESZ) {
-              uint32_t a = row_a;
-              for (int t = 0; t < ncol_max; ++t, a += (uint32_t)Q * ESZ) {     // warp-uniform trip count, lanes past their window idle
-                if (t < ncol) {
+            const uint32_t row_a0 = plane_a + (uint32_t)(hs * W + col0) * ESZ, row_step = (uint32_t)W * ESZ;
+            if (ncol_max <= 8) {
+              uint32_t best_row_a = 0xffffffffu;
+              switch (ncol_max) {          // warp-uniform
+                case 1: pool_scan<T, 1>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 2: pool_scan<T, 2>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 3: pool_scan<T, 3>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 4: pool_scan<T, 4>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 5: pool_scan<T, 5>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 6: pool_scan<T, 6>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 7: pool_scan<T, 7>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                case 8: pool_scan<T, 8>(row_a0, row_step, off, hs, he, neg_max, best, best_row_a); break;
+                default: break;
+              }
+              if (ncol > 0 && best_row_a != 0xffffffffu) {
+                // column of the first maximum inside the winning row; the VALUE is re-read there (keeps the sign of a zero)
+                uint32_t a = best_row_a + off[0];
+                for (int t = 0; t < ncol; ++t, a += (uint32_t)Q * ESZ) {
                   const A v = lds_acc<T>(a);
-                  if (v > best) { best = v; best_a = a; }
+                  if (v == best) { best = v; idx = (int)((a - plane_a) / ESZ); break; }
+                }
+              } else {
+                best = neg_max;             // lanes without a column of their own only repeated a neighbour's reads
+              }
+            } else {                        // very wide bins: plain loop, a warp-uniform trip count with idle lanes
+              uint32_t row_a = row_a0 + off[0], best_a = 0xffffffffu;
+              for (int h = hs; h < he; ++h, row_a += row_step) {
+                uint32_t a = row_a;
+                for (int t = 0; t < ncol_max; ++t, a += (uint32_t)Q * ESZ) {
+                  if (t < ncol) {
+                    const A v = lds_acc<T>(a);
+                    if (v > best) { best = v; best_a = a; }
+                  }
                 }
               }
+              idx = best_a == 0xffffffffu ? -1 : (int)((best_a - plane_a) / ESZ);
             }
-            idx = best_a == 0xffffffffu ? -1 : (int)((best_a - plane_a) / ESZ);
           } else {
             for (int h = hs; h < he; ++h) {
               const T* __restrict__ row = plane + h * W;
