@@ -43,7 +43,8 @@ DevAttr& attr() {
 namespace {
 const char* const kEnvNames[ENV_COUNT] = {"VB200_ROI_ALIGN_PATH", "VB200_ROI_LINE_AXIS", "VB200_NMS_PATH", "VB200_BNMS_PATH",
                                           "VB200_BNMS_WARPS", "VB200_RESIZE_PATH", "VB200_DCN_PATH", "VB200_DCN_CTA2",
-                                          "VB200_DCN_STAGES", "VB200_DCN_BN", "VB200_ROI_BWD_PATH"};
+                                          "VB200_DCN_STAGES", "VB200_DCN_BN", "VB200_ROI_BWD_PATH", "VB200_BNMS_GRAPH"};
+std::atomic<int> g_env_gen{0};
 char g_env_val[ENV_COUNT][32];
 std::atomic<int> g_env_set[ENV_COUNT];
 std::atomic<int> g_env_loaded{0};
@@ -55,6 +56,7 @@ void load_env_locked() {
     g_env_set[k].store(v ? 1 : 0, std::memory_order_release);
   }
   g_env_loaded.store(1, std::memory_order_release);
+  g_env_gen.fetch_add(1, std::memory_order_relaxed);
 }
 }  // namespace
 
@@ -64,6 +66,11 @@ const char* env_override(EnvKey k) {
     if (!g_env_loaded.load(std::memory_order_relaxed)) load_env_locked();
   }
   return g_env_set[k].load(std::memory_order_acquire) ? g_env_val[k] : nullptr;
+}
+
+int env_generation() {
+  env_override(ENV_BNMS_GRAPH);      // make sure the overrides are loaded
+  return g_env_gen.load(std::memory_order_relaxed);
 }
 
 int sm_count() { return attr().sms; }
