@@ -678,3 +678,26 @@ def test_box_iou_rotated_vs_oracle_and_golden(vb, oracle):
     assert vb.ops.box_iou_rotated(torch.zeros(0, 5, device=DEV), b2).shape == (0, 193)
     with pytest.raises(RuntimeError, match="Tensor\\[N, 5\\]"):
         vb.ops.box_iou_rotated(torch.zeros(3, 4, device=DEV), b2)
+
+
+def test_batched_nms_graph_replay_matches_plain_launches(vb, oracle):
+    """A repeating argument set is replayed as a CUDA graph from the third call on: same indices as the plain launches, also
+    after the CONTENTS of the (same) buffers change; one launch is counted per replay."""
+    from vision_b200 import workloads
+    from test_gpu_parity import force_env
+
+    b, s, i = [t_.to(DEV) for t_ in workloads.cfg3_batched_nms(n=60_000, seed=3)]
+    with force_env("VB200_BNMS_GRAPH", "0"):
+        plain = vb.ops.batched_nms(b, s, i, 0.5).clone()
+    outs, counts = [], []
+    for _ in range(4):
+        before = vb.launch_count()
+        outs.append(vb.ops.batched_nms(b, s, i, 0.5).clone())
+        counts.append(vb.launch_count() - before)
+    assert all(torch.equal(o, plain) for o in outs)
+    assert counts[-1] <= 2 < counts[0]                   # graph replay: one graph launch instead of ~25 kernel launches
+    b2, s2, i2 = workloads.cfg3_batched_nms(n=60_000, seed=4, clustered=True)
+    b.copy_(b2.to(DEV)); s.copy_(s2.to(DEV)); i.copy_(i2.to(DEV))            # same addresses, new contents
+    got = vb.ops.batched_nms(b, s, i, 0.5)
+    want = oracle.batched_nms(b2.numpy(), s2.numpy(), i2.numpy(), 0.5, mode=oracle.NMS_MODE_CUDA, device_is_cuda=True)
+    assert np.array_equal(npy(got), want)

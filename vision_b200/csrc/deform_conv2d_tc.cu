@@ -154,11 +154,24 @@ __device__ __forceinline__ uint64_t smem_desc_k(uint32_t smem_addr) {
 template <typename T> struct Elem;
 template <> struct Elem<__nv_bfloat16> {
   static constexpr uint32_t kFmt = 1;
+  // packed 16-bit blend (HFMA2.BF16): weight pair x value pair + accumulator pair, one rounding to bf16 per step
+  static __device__ __forceinline__ uint32_t dup(float w) { __nv_bfloat162 v = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t*>(&v); }
+  static __device__ __forceinline__ uint32_t mul2(uint32_t w, uint32_t a) {
+    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&w), *reinterpret_cast<__nv_bfloat162*>(&a)); return *reinterpret_cast<uint32_t*>(&r); }
+  static __device__ __forceinline__ uint32_t fma2p(uint32_t w, uint32_t a, uint32_t c) {
+    __nv_bfloat162 r = __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w), *reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&c));
+    return *reinterpret_cast<uint32_t*>(&r); }
   static __device__ __forceinline__ float2 up(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
   static __device__ __forceinline__ uint32_t pk(float a, float b) { __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
 };
 template <> struct Elem<__half> {
   static constexpr uint32_t kFmt = 0;
+  static __device__ __forceinline__ uint32_t dup(float w) { __half2 v = __float2half2_rn(w); return *reinterpret_cast<uint32_t*>(&v); }
+  static __device__ __forceinline__ uint32_t mul2(uint32_t w, uint32_t a) {
+    __half2 r = __hmul2(*reinterpret_cast<__half2*>(&w), *reinterpret_cast<__half2*>(&a)); return *reinterpret_cast<uint32_t*>(&r); }
+  static __device__ __forceinline__ uint32_t fma2p(uint32_t w, uint32_t a, uint32_t c) {
+    __half2 r = __hfma2(*reinterpret_cast<__half2*>(&w), *reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&c));
+    return *reinterpret_cast<uint32_t*>(&r); }
   static __device__ __forceinline__ float2 up(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
   static __device__ __forceinline__ uint32_t pk(float a, float b) { __half2 v = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&v); }
 };
@@ -287,6 +300,16 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float wv[4] = {wq[i].x, wq[i].y, wq[i].z, wq[i].w};
+          uint4 o;
+          if (p.blend16) {
+            // blend in the storage format (HFMA2): 16 instructions per 8 channels instead of 52 (unpack + FFMA2 + pack).  Every
+            // step rounds to 16 bits - the A operand is rounded to that format anyway; the whole op stays inside its 1e-2 bound.
+            const uint32_t w0 = Elem<T>::dup(wv[0]), w1 = Elem<T>::dup(wv[1]), w2_ = Elem<T>::dup(wv[2]), w3 = Elem<T>::dup(wv[3]);
+            o.x = Elem<T>::fma2p(w3, v[i][3].x, Elem<T>::fma2p(w2_, v[i][2].x, Elem<T>::fma2p(w1, v[i][1].x, Elem<T>::mul2(w0, v[i][0].x))));
+            o.y = Elem<T>::fma2p(w3, v[i][3].y, Elem<T>::fma2p(w2_, v[i][2].y, Elem<T>::fma2p(w1, v[i][1].y, Elem<T>::mul2(w0, v[i][0].y))));
+            o.z = Elem<T>::fma2p(w3, v[i][3].z, Elem<T>::fma2p(w2_, v[i][2].z, Elem<T>::fma2p(w1, v[i][1].z, Elem<T>::mul2(w0, v[i][0].z))));
+            o.w = Elem<T>::fma2p(w3, v[i][3].w, Elem<T>::fma2p(w2_, v[i][2].w, Elem<T>::fma2p(w1, v[i][1].w, Elem<T>::mul2(w0, v[i][0].w))));
+          } else {
           unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};   // 8 channels as 4 packed fp32 pairs (FFMA2)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -298,9 +321,9 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
               acc[k] = fma2(w2, pack2(f.x, f.y), acc[k]);
             }
           }
-          uint4 o;
           o.x = Elem<T>::pk(lo32(acc[0]), hi32(acc[0])); o.y = Elem<T>::pk(lo32(acc[1]), hi32(acc[1]));
           o.z = Elem<T>::pk(lo32(acc[2]), hi32(acc[2])); o.w = Elem<T>::pk(lo32(acc[3]), hi32(acc[3]));
+          }
           const int prow = prow0 + 4 * i;
           *reinterpret_cast<uint4*>(a_tile + prow * ROW_BYTES + ((my_chunk ^ tc_swz<KB>(prow)) << 4)) = o;
         }
@@ -990,7 +1013,12 @@ int pack_tc_weights(const void* weight, T* wpacked, const DcnParams& p, cudaStre
 
 template <typename T>
 int launch_tc(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,
-              const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st, const DcnHints& hints) {
+              const DcnParams& p_in, void* workspace, size_t workspace_bytes, cudaStream_t st, const DcnHints& hints) {
+  DcnParams p = p_in;
+  {
+    const char* env = env_override(ENV_DCN_BLEND);      // VB200_DCN_BLEND=16: blend the corners in the storage format
+    p.blend16 = env && env[0] == '1' && env[1] == '6';
+  }
   const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
   const size_t nhwc_bytes = hints.input_is_nhwc ? 0 : align256((size_t)p.batch * HWi * p.c_in * sizeof(T));
   const size_t w_bytes = hints.packed_weight ? 0 : align256((size_t)p.c_out * p.c_in * KK * sizeof(T));
