@@ -139,6 +139,46 @@ def test_roi_align_line_path(vb, oracle):
                     np.testing.assert_allclose(npy(got), want, **F32_TOL)
 
 
+def test_roi_align_band_path(vb, oracle):
+    """7x7 / sampling_ratio 2 / channels % 8 == 0 takes the band-resident channel-interleaved kernel: several bands per
+    map (bin rows straddling two bands are summed with RED into rows the geometry kernel zeroed), batched maps, RoIs
+    hanging outside the map, degenerate / inverted / border-hugging RoIs, out-of-range batch indices (zeros)."""
+    from vision_b200 import workloads
+
+    for seed, (b, c, h, w), k in ((1, (2, 8, 80, 200), 300), (2, (1, 16, 200, 272), 200), (3, (1, 8, 300, 100), 400),
+                                  (4, (3, 24, 40, 53), 500), (5, (1, 64, 33, 31), 70)):
+        x, rois, kw = workloads.cfg2_roi_align(seed=seed, k=k, batch=b, channels=c, height=h, width=w)
+        rois = rois.clone()
+        rois[::7, 1:3] -= 90.0                      # start outside the map
+        rois[1::11, 3:] += 400.0                    # end far outside
+        rois[2::13, 3:] = rois[2::13, 1:3]          # zero-size
+        rois[3::17, 1:] = torch.tensor([w * 4 - 6.0, h * 4 - 6.0, w * 4 + 0.0, h * 4 + 0.0])   # bottom-right corner
+        rois[4::19, 3] = rois[4::19, 1] + 700.0     # very wide, short
+        rois[5::23, 4] = rois[5::23, 2] + 2000.0    # taller than the map
+        rois[6::29, 2] = h * 4 + 50.0               # entirely below the map: every sample row is outside
+        rois[6::29, 4] = h * 4 + 90.0
+        rois[8::31, 3:] = rois[8::31, 1:3] - 40.0   # inverted (aligned=True keeps the negative size)
+        for aligned in (False, True):
+            want = oracle.roi_align(x.numpy(), rois.numpy(), 7, 0.25, 2, aligned)
+            with force_env("VB200_ROI_ALIGN_PATH", "band"):
+                before = vb.launch_count()
+                got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2, aligned)
+                assert vb.launch_count() - before == 2      # geometry + gather
+                again = vb.ops.roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2, aligned)
+            np.testing.assert_allclose(npy(got), want, **F32_TOL)
+            assert torch.equal(got, again), "band kernel must be bit-reproducible (split bin rows add two partials)"
+    # batch indices outside [0, B): zeros, like the line kernel
+    x, rois, kw = workloads.cfg2_roi_align(seed=9, k=64, batch=2, channels=8, height=60, width=80)
+    rois[::5, 0] = 7.0
+    rois[1::5, 0] = -1.0
+    with force_env("VB200_ROI_ALIGN_PATH", "band"):
+        got = vb.ops.roi_align(x.to(DEV), rois.to(DEV), 7, 0.25, 2, False)
+    ok = (rois[:, 0] >= 0) & (rois[:, 0] < 2)
+    want = oracle.roi_align(x.numpy(), rois[ok].numpy(), 7, 0.25, 2, False)
+    np.testing.assert_allclose(npy(got)[ok.numpy()], want, **F32_TOL)
+    assert float(got[~ok.to(DEV)].abs().max()) == 0.0
+
+
 def test_roi_align_cfg2_thread_per_bin_plane_path(vb, oracle):
     from vision_b200 import workloads
 
