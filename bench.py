@@ -473,9 +473,28 @@ def block_cfg5(ctx: Ctx, vb, tv, sharded) -> dict:
     if ctx.world > 1:
         g = sharded.OverlappedGather()
         gms = ctx.device_ms(lambda: sharded.sharded_apply_overlapped(lambda t: TF.resize(t, [224, 224]), x, chunks=4, gather=g), steps)
-        out["with_allgather"] = {"ms_per_step": gms, "value": ctx.world * CFG5_BATCH / (gms / 1e3), "unit": "images/s",
-                                 "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2,
-                                 "note": "4 chunks of 32 images, each chunk's all_gather_into_tensor on a side stream under the next chunk's kernel"}
+        nccl = {"ms_per_step": gms, "value": ctx.world * CFG5_BATCH / (gms / 1e3), "unit": "images/s",
+                "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2,
+                "note": "4 chunks of 32 images, each chunk's all_gather_into_tensor on a side stream under the next chunk's kernel"}
+        out["with_allgather"] = nccl
+        # the exchange fused into the kernel: every output pixel is stored to all ranks' gathered buffers (peer-mapped memory)
+        peer = sharded.PeerGather.create((CFG5_BATCH, 3, 224, 224), x.dtype, ctx.dev)
+        ok = ctx.max_over_ranks(0.0 if peer is not None else 1.0) == 0.0      # every rank must have it
+        if ok:
+            want = sharded.sharded_apply_overlapped(lambda t: TF.resize(t, [224, 224]), x, chunks=4, gather=g).materialize()
+            got = sharded.resize_gather(x, [224, 224], peer)
+            same = bool(torch.equal(got, want))
+            fms = ctx.device_ms(lambda: sharded.resize_gather(x, [224, 224], peer), steps)
+            out["with_allgather"] = {"ms_per_step": fms, "value": ctx.world * CFG5_BATCH / (fms / 1e3), "unit": "images/s",
+                                     "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2,
+                                     "identical_to_nccl_gather": same,
+                                     "note": "all-gather fused into the resize kernel: each finished pixel is stored to every rank's gathered buffer "
+                                             "(torch symmetric memory, NVLink peer stores), one device-side barrier before and after; no NCCL call",
+                                     "nccl_overlapped": nccl}
+            del want, got
+        else:
+            out["with_allgather"]["peer_stores"] = "unavailable on this box (symmetric memory rendezvous failed); NCCL exchange reported"
+        del peer
     if ctx.rank == 0 and ctx.world == 1:
         xs = x[:sub]
         g = gpu_reference_ms(ctx, vb, lambda: TF.resize(xs, [224, 224]), 3, 1)

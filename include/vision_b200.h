@@ -74,6 +74,9 @@ VB200_API uint64_t vb200_launch_count(void);
 /* The VB200_* path overrides (testing / profiling only) are read from the environment once, the first
  * time a launcher needs them; this re-reads them (tests switch paths inside one process). */
 VB200_API void vb200_reload_env(void);
+/* Generation counter of those overrides (bumped by every (re)load): callers that cache layout-dependent artefacts, e.g.
+ * packed deform_conv2d weights, key them on it. */
+VB200_API int vb200_env_generation(void);
 
 /* ---- roi_align ---------------------------------------------------------
  * Replaces roi_align_forward_kernel, csrc/ops/cuda/roi_align_kernel.cu:334-394
@@ -276,6 +279,14 @@ VB200_API int vb200_deform_conv2d_backward_inputs(const void* dcol, const void* 
  * align_corners=False semantics.  dtype: F32, F16, BF16, U8. */
 VB200_API int vb200_resize(const void* input, void* output, int dtype, int64_t planes, int in_h, int in_w,
                  int out_h, int out_w, int mode, int antialias, vb200_stream stream);
+/* resize fused with the all-gather of its output (the batch shards over the GPUs of one box and the only
+ * exchange is an all-gather of the per-shard outputs - here done by the kernel's own stores).  outputs[0] is the caller's
+ * slot of its gathered buffer, outputs[1..n) the SAME slot of every peer's buffer (peer-mapped device pointers, e.g. from
+ * torch.distributed._symmetric_memory or cudaIpcOpenMemHandle); each finished pixel is stored to all of them.  The caller
+ * synchronises the ranks before peers read (and before the buffers are rewritten).  1 <= n_outputs <= 8.  Replaces the
+ * `dist.all_gather` a data-parallel caller of resize_image (_geometry.py:283-362) issues after the op. */
+VB200_API int vb200_resize_gather(const void* input, void* const* outputs, int n_outputs, int dtype, int64_t planes, int in_h,
+                        int in_w, int out_h, int out_w, int mode, int antialias, vb200_stream stream);
 
 /* ---- box_iou_rotated (API completeness) ------------------
  * Replaces box_iou_rotated_cuda, csrc/ops/cuda/box_iou_rotated_kernel.cu:92-160 (schema torchvision::box_iou_rotated,

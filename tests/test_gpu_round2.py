@@ -701,3 +701,27 @@ def test_batched_nms_graph_replay_matches_plain_launches(vb, oracle):
     got = vb.ops.batched_nms(b, s, i, 0.5)
     want = oracle.batched_nms(b2.numpy(), s2.numpy(), i2.numpy(), 0.5, mode=oracle.NMS_MODE_CUDA, device_is_cuda=True)
     assert np.array_equal(npy(got), want)
+
+
+# ---- resize fused with the all-gather of its output (peer stores): several destinations on ONE GPU --------------------------
+@pytest.mark.gpu
+def test_resize_gather_writes_every_destination(vb):
+    """vision_b200::resize_gather stores each output pixel to all destinations (on a multi-GPU box: the same slot of every
+    rank's gathered buffer).  Here the destinations are three slots of local buffers; each must equal the plain resize, and
+    the bytes around the slots must stay untouched.  Streaming kernel (fp16 / uint8 bilinear-AA) and the copy fallback (bicubic)."""
+    torch.manual_seed(0)
+    for dtype, mode, aa, shape, size in ((torch.float16, 0, True, (5, 3, 270, 480), (64, 56)),
+                                         (torch.uint8, 0, True, (2, 3, 300, 400), (40, 48)),
+                                         (torch.float16, 1, True, (2, 3, 90, 120), (30, 40)),
+                                         (torch.float32, 0, False, (2, 1, 33, 47), (20, 21))):
+        x = (torch.rand(shape, device=DEV) * 255).to(dtype) if dtype == torch.uint8 else torch.rand(shape, device=DEV).to(dtype)
+        want = torch.ops.vision_b200.resize(x, size[0], size[1], mode, aa)
+        n = want.numel()
+        bufs = [torch.full((n + 64,), 7, dtype=dtype, device=DEV) for _ in range(3)]
+        ptrs = [b.data_ptr() + 32 * b.element_size() for b in bufs]
+        torch.ops.vision_b200.resize_gather(x, ptrs, size[0], size[1], mode, aa)
+        for b in bufs:
+            assert torch.equal(b[32:32 + n].view(want.shape), want)
+            assert bool((b[:32] == 7).all()) and bool((b[32 + n:] == 7).all())
+    with pytest.raises(RuntimeError, match="1..8 destinations"):
+        torch.ops.vision_b200.resize_gather(x, [], 4, 4, 0, True)

@@ -108,6 +108,8 @@ def _worker(rank, world, port, q):
             torch.equal(lazy.rank(1 - rank).flatten(0, 1), (imgs * 2)[(1 - rank) * 3:(2 - rank) * 3])
         one = sh.sharded_apply_overlapped(lambda t: t + 1, mine, chunks=1, gather=og)
         ok3 = ok3 and torch.equal(one, imgs + 1)
+        # the peer-store transport needs CUDA + NCCL: under gloo the factory reports "unavailable" and callers keep the collective
+        ok3 = ok3 and sh.PeerGather.create((3, 3, 4, 4), torch.float32, "cpu") is None
         q.put((rank, ok1, ok2 and ok3))
     finally:
         dist.destroy_process_group()

@@ -271,7 +271,7 @@ int launch_resize(const void* in, void* out, int64_t planes, int in_h, int in_w,
 }  // namespace
 
 // implemented in resize_stream.cu; returns 1 if it handled the request, 0 if not applicable, <0 / >1 on error
-int resize_aa_stream_try(const void* in, void* out, int dtype, int64_t planes, int in_h, int in_w, int out_h,
+int resize_aa_stream_try(const void* in, void* const* outs, int ndst, int dtype, int64_t planes, int in_h, int in_w, int out_h,
                          int out_w, int mode, cudaStream_t st);
 
 }  // namespace vb200
@@ -341,7 +341,8 @@ extern "C" int vb200_resize(const void* input, void* output, int dtype, int64_t 
   VB200_REQUIRE(input && output, "resize: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (antialias) {
-    const int rc = resize_aa_stream_try(input, output, dtype, planes, in_h, in_w, out_h, out_w, mode, st);
+    void* outs[1] = {output};
+    const int rc = resize_aa_stream_try(input, outs, 1, dtype, planes, in_h, in_w, out_h, out_w, mode, st);
     if (rc != 0) return rc == 1 ? 0 : rc;
   }
   switch (dtype) {
@@ -352,4 +353,27 @@ extern "C" int vb200_resize(const void* input, void* output, int dtype, int64_t 
   }
   set_error("resize: unsupported dtype %d", dtype);
   return VB200_EUNSUPPORTED;
+}
+
+// resize fused with the all-gather of its output: every finished pixel is stored to outputs[0] (the caller's own slot) and to
+// the same slot of outputs[1..n) - peer-mapped buffers of the other ranks - so the exchange rides under the input stream.
+extern "C" int vb200_resize_gather(const void* input, void* const* outputs, int n_outputs, int dtype, int64_t planes, int in_h,
+                                   int in_w, int out_h, int out_w, int mode, int antialias, vb200_stream stream) {
+  VB200_REQUIRE(n_outputs >= 1 && n_outputs <= 8 && outputs, "resize_gather: 1..8 destinations");
+  for (int d = 0; d < n_outputs; ++d) VB200_REQUIRE(outputs[d] != nullptr, "resize_gather: null destination");
+  VB200_REQUIRE(planes >= 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, "resize: bad sizes");
+  if (planes == 0) return 0;
+  VB200_REQUIRE(input, "resize: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (antialias) {
+    const int rc = resize_aa_stream_try(input, outputs, n_outputs, dtype, planes, in_h, in_w, out_h, out_w, mode, st);
+    if (rc != 0) return rc == 1 ? 0 : rc;
+  }
+  // other modes: the plain kernel into the caller's slot, then one copy per peer on the same stream
+  const int rc = vb200_resize(input, outputs[0], dtype, planes, in_h, in_w, out_h, out_w, mode, antialias, stream);
+  if (rc) return rc;
+  const size_t esize = dtype == VB200_F32 ? 4 : dtype == VB200_U8 ? 1 : 2;
+  const size_t bytes = (size_t)planes * out_h * out_w * esize;
+  for (int d = 1; d < n_outputs; ++d) VB200_CUDA_TRY(cudaMemcpyAsync(outputs[d], outputs[0], bytes, cudaMemcpyDefault, st));
+  return 0;
 }

@@ -26,11 +26,17 @@ namespace {
 constexpr int kMaxConsumerWarps = 16;
 constexpr int kMaxBandRows = 1024;   // upper bound on band_cap (keeps the per-row tables at 12 KB)
 
+constexpr int kMaxResizeDst = 8;
+
 struct StreamParams {
   int in_h, in_w, out_h, out_w;
   float scale_w, scale_h;
   int rows_out_per_cta, n_stages, row_pitch;   // row_pitch: bytes per stage (row + zeroed pad)
   int band_cap;                                // capacity of the per-row vertical tables
+  // destinations: the caller's own output and, for the fused all-gather (vb200_resize_gather), the same slot of every
+  // peer's gathered buffer (peer-mapped device memory: the stores travel over NVLink while the input streams from HBM)
+  void* dst[kMaxResizeDst];
+  int ndst;
 };
 
 __device__ __forceinline__ float centre(float scale, int m) { return scale * ((float)m + 0.5f); }
@@ -116,7 +122,7 @@ template <> __device__ __forceinline__ uint8_t store_px<uint8_t>(float v) { retu
 // NW: consumer warps the kernel is compiled for (block = (n_cwarps + 1) * 32 <= (NW + 1) * 32).
 template <typename T, int NP, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, (NW <= 8 && NP <= 12) ? 3 : 1)
-resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamParams p, int n_cwarps) {
+resize_aa_stream_kernel(const T* __restrict__ in, StreamParams p, int n_cwarps) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [stages][row_pitch] | full[S] empty[S] | totx[OW] xmcx[OW] xminx[OW] xendx[OW] | toty.. | rowA[band] rowB[band] rowK[band]
   unsigned char* stages = smem;
@@ -214,7 +220,12 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   }
   const int word0 = min((int)((e * (int)sizeof(T)) >> 2), (int)(row_bytes >> 2));     // beyond the row: the zeroed pad
   const bool writer = have && lane < 31 && i < p.out_w;     // lane 31 only supplies B to lane 30
-  T* __restrict__ dst = out + plane * (int64_t)p.out_h * p.out_w + i;
+  const int64_t doff = plane * (int64_t)p.out_h * p.out_w + i;
+  auto put = [&](int row, float v) {              // one finished output pixel -> every destination
+    const T q = store_px<T>(v);
+    const int64_t o = doff + (int64_t)row * p.out_w;
+    for (int d = 0; d < p.ndst; ++d) reinterpret_cast<T*>(p.dst[d])[o] = q;
+  };
 
   float acc_lo = 0.f, acc_hi = 0.f;
   int k_cur = oy0;
@@ -241,7 +252,7 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
     const float h = A + __shfl_down_sync(0xffffffffu, B, 1);
     const int k = rowK[rl];
     if (k != k_cur) {                              // CTA-uniform: output row k_cur - 1 is complete
-      if (writer && k_cur - 1 >= oy0) dst[(int64_t)(k_cur - 1) * p.out_w] = store_px<T>(acc_lo);
+      if (writer && k_cur - 1 >= oy0) put(k_cur - 1, acc_lo);
       acc_lo = acc_hi; acc_hi = 0.f; k_cur = k;
     }
     acc_hi = fmaf(rowA[rl], h, acc_hi);
@@ -249,12 +260,12 @@ resize_aa_stream_kernel(const T* __restrict__ in, T* __restrict__ out, StreamPar
   }
   // rows of the band are exhausted: acc_lo holds output row k_cur - 1; a band that ended exactly on an
   // interval boundary (k_cur == oy1 - 1 cannot happen: the band includes interval oy1) -> k_cur == oy1
-  if (writer && k_cur - 1 >= oy0 && k_cur - 1 < oy1) dst[(int64_t)(k_cur - 1) * p.out_w] = store_px<T>(acc_lo);
-  if (writer && k_cur < oy1 && k_cur >= oy0) dst[(int64_t)k_cur * p.out_w] = store_px<T>(acc_hi);
+  if (writer && k_cur - 1 >= oy0 && k_cur - 1 < oy1) put(k_cur - 1, acc_lo);
+  if (writer && k_cur < oy1 && k_cur >= oy0) put(k_cur, acc_hi);
 }
 
 template <typename T, int NP, int NW>
-int launch_stream(const void* in, void* out, int64_t planes, const StreamParams& p0, cudaStream_t st) {
+int launch_stream(const void* in, int64_t planes, const StreamParams& p0, cudaStream_t st) {
   constexpr int LW = (NP * 2 * (int)sizeof(T) + 3) / 4;       // 32-bit words a thread reads per row
   StreamParams p = p0;
   const int n_cwarps = ceil_div(p.out_w + 1, 31);
@@ -289,8 +300,9 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
   while (done < planes) {
     const int64_t chunk = planes - done < 65535 ? planes - done : 65535;
     dim3 grid((unsigned)splits, (unsigned)chunk);
-    resize_aa_stream_kernel<T, NP, NW><<<grid, (n_cwarps + 1) * 32, smem, st>>>(
-        (const T*)in + done * (int64_t)p.in_h * p.in_w, (T*)out + done * (int64_t)p.out_h * p.out_w, p, n_cwarps);
+    StreamParams pc = p;
+    for (int d = 0; d < p.ndst; ++d) pc.dst[d] = (T*)p.dst[d] + done * (int64_t)p.out_h * p.out_w;
+    resize_aa_stream_kernel<T, NP, NW><<<grid, (n_cwarps + 1) * 32, smem, st>>>((const T*)in + done * (int64_t)p.in_h * p.in_w, pc, n_cwarps);
     int rc = check_launch("resize_aa_stream_kernel");
     if (rc) return rc;
     done += chunk;
@@ -299,29 +311,29 @@ int launch_stream(const void* in, void* out, int64_t planes, const StreamParams&
 }
 
 template <typename T>
-int dispatch_lw(const void* in, void* out, int64_t planes, const StreamParams& p, cudaStream_t st) {
+int dispatch_lw(const void* in, int64_t planes, const StreamParams& p, cudaStream_t st) {
   // a thread owns at most floor(scale)+1 pixels, + the slot alignment slack
   constexpr int ALIGN = Px<T>::PPW > 2 ? Px<T>::PPW : 2;
   const int need = ((int)floorf(p.scale_w) + 1 + (ALIGN - 1) + 1) / 2;     // pixel pairs
   const bool small = ceil_div(p.out_w + 1, 31) <= 8;
   if (small) {
-    if (need <= 4) return launch_stream<T, 4, 8>(in, out, planes, p, st);
-    if (need <= 6) return launch_stream<T, 6, 8>(in, out, planes, p, st);
-    if (need <= 10) return launch_stream<T, 10, 8>(in, out, planes, p, st);
-    if (need <= 12) return launch_stream<T, 12, 8>(in, out, planes, p, st);
-    if (need <= 16) return launch_stream<T, 16, 8>(in, out, planes, p, st);
+    if (need <= 4) return launch_stream<T, 4, 8>(in, planes, p, st);
+    if (need <= 6) return launch_stream<T, 6, 8>(in, planes, p, st);
+    if (need <= 10) return launch_stream<T, 10, 8>(in, planes, p, st);
+    if (need <= 12) return launch_stream<T, 12, 8>(in, planes, p, st);
+    if (need <= 16) return launch_stream<T, 16, 8>(in, planes, p, st);
     return 0;
   }
-  if (need <= 4) return launch_stream<T, 4, kMaxConsumerWarps>(in, out, planes, p, st);
-  if (need <= 6) return launch_stream<T, 6, kMaxConsumerWarps>(in, out, planes, p, st);
-  if (need <= 10) return launch_stream<T, 10, kMaxConsumerWarps>(in, out, planes, p, st);
-  if (need <= 16) return launch_stream<T, 16, kMaxConsumerWarps>(in, out, planes, p, st);
+  if (need <= 4) return launch_stream<T, 4, kMaxConsumerWarps>(in, planes, p, st);
+  if (need <= 6) return launch_stream<T, 6, kMaxConsumerWarps>(in, planes, p, st);
+  if (need <= 10) return launch_stream<T, 10, kMaxConsumerWarps>(in, planes, p, st);
+  if (need <= 16) return launch_stream<T, 16, kMaxConsumerWarps>(in, planes, p, st);
   return 0;
 }
 
 }  // namespace
 
-int resize_aa_stream_try(const void* in, void* out, int dtype, int64_t planes, int in_h, int in_w, int out_h,
+int resize_aa_stream_try(const void* in, void* const* outs, int ndst, int dtype, int64_t planes, int in_h, int in_w, int out_h,
                          int out_w, int mode, cudaStream_t st) {
   const char* force = env_override(ENV_RESIZE_PATH);            // "generic" disables the fast path
   if (force && force[0] == 'g') return 0;
@@ -331,15 +343,18 @@ int resize_aa_stream_try(const void* in, void* out, int dtype, int64_t planes, i
   if (in_w <= out_w || in_h < out_h) return 0;                 // horizontal downscale, vertical scale >= 1
   if (out_w + 1 > 31 * kMaxConsumerWarps) return 0;
   if (((size_t)in_w * esize) % 16 != 0 || ((uintptr_t)in % 16) != 0) return 0;
+  if (ndst < 1 || ndst > kMaxResizeDst) return 0;
   StreamParams p{};
+  p.ndst = ndst;
+  for (int d = 0; d < ndst; ++d) p.dst[d] = outs[d];
   p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
   p.scale_w = (float)in_w / (float)out_w;
   p.scale_h = (float)in_h / (float)out_h;
   if (p.scale_w < 2.0f) return 0;
-  if (dtype == VB200_F16) return dispatch_lw<__half>(in, out, planes, p, st);
-  if (dtype == VB200_U8) return dispatch_lw<uint8_t>(in, out, planes, p, st);
-  if (dtype == VB200_F32) return dispatch_lw<float>(in, out, planes, p, st);
-  return dispatch_lw<__nv_bfloat16>(in, out, planes, p, st);
+  if (dtype == VB200_F16) return dispatch_lw<__half>(in, planes, p, st);
+  if (dtype == VB200_U8) return dispatch_lw<uint8_t>(in, planes, p, st);
+  if (dtype == VB200_F32) return dispatch_lw<float>(in, planes, p, st);
+  return dispatch_lw<__nv_bfloat16>(in, planes, p, st);
 }
 
 }  // namespace vb200

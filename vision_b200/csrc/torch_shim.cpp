@@ -389,11 +389,13 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor> detection_postprocess(const at::T
 
 // ---- deform_conv2d ---------------------------------------------------------
 // Packed weights are cached per weight tensor: the key is the TensorImpl (held weakly, so a recycled address cannot
-// alias) plus its version counter (an in-place update of the parameter invalidates the entry).
+// alias) plus its version counter (an in-place update of the parameter invalidates the entry) plus the generation of the
+// VB200_* overrides (VB200_DCN_CTA2 / VB200_DCN_BN change the packed layout).
 struct PackedWeight {
   c10::weak_intrusive_ptr<c10::TensorImpl> impl;
   uint32_t version;
   int dtype;
+  int env_gen;
   at::Tensor packed;
 };
 std::mutex g_pack_mu;
@@ -404,12 +406,13 @@ at::Tensor packed_weight_for(const at::Tensor& weight_c, int dt, int c_in, int c
   if (bytes == 0 || weight_c.is_inference()) return at::Tensor();
   c10::TensorImpl* impl = weight_c.unsafeGetTensorImpl();
   const uint32_t version = (uint32_t)weight_c._version();
+  const int env_gen = vb200_env_generation();
   std::lock_guard<std::mutex> lk(g_pack_mu);
   for (size_t i = 0; i < g_pack_cache.size(); ++i) {
     auto locked = g_pack_cache[i].impl.lock();
     if (!locked) { g_pack_cache.erase(g_pack_cache.begin() + i); --i; continue; }      // the weight died
     if (locked.get() == impl && g_pack_cache[i].dtype == dt) {
-      if (g_pack_cache[i].version == version) return g_pack_cache[i].packed;
+      if (g_pack_cache[i].version == version && g_pack_cache[i].env_gen == env_gen) return g_pack_cache[i].packed;
       g_pack_cache.erase(g_pack_cache.begin() + i);                                     // updated in place: re-pack
       break;
     }
@@ -420,7 +423,7 @@ at::Tensor packed_weight_for(const at::Tensor& weight_c, int dt, int c_in, int c
            "deform_conv2d");
   if (g_pack_cache.size() >= 32) g_pack_cache.erase(g_pack_cache.begin());
   g_pack_cache.push_back(PackedWeight{c10::weak_intrusive_ptr<c10::TensorImpl>(c10::intrusive_ptr<c10::TensorImpl>::reclaim_copy(impl)),
-                                      version, dt, packed});
+                                      version, dt, env_gen, packed});
   return packed;
 }
 
@@ -581,6 +584,26 @@ at::Tensor resize(const at::Tensor& input, int64_t out_h, int64_t out_w, int64_t
   return out;
 }
 
+// resize + all-gather by peer stores: dst_ptrs[0] = this rank's slot of its own gathered buffer, dst_ptrs[1..] = the same slot
+// of the peers' buffers (device pointers as integers, e.g. _SymmetricMemory.buffer_ptrs[r] + slot offset).
+void resize_gather(const at::Tensor& input, at::IntArrayRef dst_ptrs, int64_t out_h, int64_t out_w, int64_t mode, bool antialias) {
+  TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+  TORCH_CHECK(input.dim() >= 2, "resize: input must have at least 2 dimensions");
+  TORCH_CHECK(out_h > 0 && out_w > 0, "resize: output size must be positive");
+  TORCH_CHECK(dst_ptrs.size() >= 1 && dst_ptrs.size() <= 8, "resize_gather: 1..8 destinations");
+  at::cuda::CUDAGuard guard(input.device());
+  at::Tensor in_c = input.contiguous();
+  const int64_t in_h = in_c.size(-2), in_w = in_c.size(-1);
+  TORCH_CHECK(in_h > 0 && in_w > 0, "resize: empty spatial dimensions");
+  if (in_c.numel() == 0) return;
+  const int64_t planes = in_c.numel() / (in_h * in_w);
+  void* outs[8];
+  for (size_t d = 0; d < dst_ptrs.size(); ++d) outs[d] = reinterpret_cast<void*>(static_cast<uintptr_t>(dst_ptrs[d]));
+  check_rc(vb200_resize_gather(in_c.data_ptr(), outs, (int)dst_ptrs.size(), dtype_code(in_c.scalar_type(), "resize"), planes, (int)in_h,
+                               (int)in_w, (int)out_h, (int)out_w, (int)mode, antialias ? 1 : 0, cur_stream()),
+           "resize_gather");
+}
+
 // ---- fused inference preprocessing (transforms/_presets.py:57-64) -------------------------------------------------
 at::Tensor resize_crop_normalize(const at::Tensor& input, int64_t resize_h, int64_t resize_w, int64_t crop_top, int64_t crop_left,
                                  int64_t crop_h, int64_t crop_w, int64_t mode, bool antialias, at::ArrayRef<double> mean,
@@ -660,6 +683,7 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("_ps_roi_pool_backward(Tensor grad, Tensor rois, Tensor channel_mapping, float spatial_scale, SymInt pooled_height, SymInt pooled_width, SymInt batch_size, SymInt channels, SymInt height, SymInt width) -> Tensor");
   m.def("_deform_conv2d_backward(Tensor grad, Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> (Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
+  m.def("resize_gather(Tensor input, int[] dst_ptrs, int out_h, int out_w, int mode, bool antialias) -> ()");
   m.def("resize_crop_normalize(Tensor input, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w, int mode, bool antialias, float[] mean, float[] std) -> Tensor");
   m.def("box_iou_rotated(Tensor boxes1, Tensor boxes2) -> Tensor");
   m.def("detection_postprocess(Tensor boxes, Tensor scores, Tensor labels, float img_h, float img_w, float score_thresh, bool score_inclusive, float min_size, float nms_thresh, int topk) -> (Tensor, Tensor, Tensor)");
@@ -684,6 +708,7 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("ps_roi_align", TORCH_FN(ps_roi_align));
   m.impl("deform_conv2d", TORCH_FN(deform_conv2d));
   m.impl("resize", TORCH_FN(resize));
+  m.impl("resize_gather", TORCH_FN(resize_gather));
   m.impl("_roi_align_backward", TORCH_FN(roi_align_backward));
   m.impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   m.impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));
