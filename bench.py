@@ -417,9 +417,28 @@ def block_cfg4(ctx: Ctx, vb, tv, sharded) -> dict:
         g = sharded.OverlappedGather()
         part = lambda i: tv.ops.deform_conv2d(x[i * 8:(i + 1) * 8], off[i * 8:(i + 1) * 8], w, b, 1, 1, 1, m[i * 8:(i + 1) * 8])
         gms = ctx.device_ms(lambda: g.run(part, 4), steps)
-        out["with_allgather"] = {"ms_per_step": gms, "value": ctx.world * CFG4_FLOPS / (gms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                 "bytes_gathered_per_rank": ctx.world * x.numel() * 2,
-                                 "note": "4 batch chunks, each chunk's all_gather_into_tensor on a side stream under the next chunk's kernel"}
+        nccl = {"ms_per_step": gms, "value": ctx.world * CFG4_FLOPS / (gms / 1e3) / 1e12, "unit": "TFLOP/s",
+                "bytes_gathered_per_rank": ctx.world * x.numel() * 2,
+                "note": "4 batch chunks, each chunk's all_gather_into_tensor on a side stream under the next chunk's kernel"}
+        out["with_allgather"] = nccl
+        peer = sharded.PeerGather.create(tuple(x.shape), x.dtype, ctx.dev)      # C_out = C_in, same spatial size: output shard = input shape
+        if ctx.max_over_ranks(0.0 if peer is not None else 1.0) == 0.0:
+            want = sharded.all_gather_equal(op())
+            got = sharded.deform_conv2d_gather(x, off, w, b, peer, 1, 1, 1, m)
+            same = bool(torch.equal(got, want))
+            fms = ctx.device_ms(lambda: sharded.deform_conv2d_gather(x, off, w, b, peer, 1, 1, 1, m), steps)
+            ingress = (ctx.world - 1) * x.numel() * 2
+            out["with_allgather"] = {"ms_per_step": fms, "value": ctx.world * CFG4_FLOPS / (fms / 1e3) / 1e12, "unit": "TFLOP/s",
+                                     "bytes_gathered_per_rank": ctx.world * x.numel() * 2, "identical_to_nccl_gather": same,
+                                     "nvlink_ingress_floor_ms": ingress / 900e9 * 1e3,
+                                     "note": "all-gather fused into the tcgen05 kernel's epilogue: each output element is stored to every rank's gathered "
+                                             "buffer (torch symmetric memory, NVLink peer stores), one device-side barrier before and after; no NCCL "
+                                             "call.  nvlink_ingress_floor_ms = (world-1) x 134 MB received per rank per step at 900 GB/s",
+                                     "nccl_overlapped": nccl}
+            del want, got
+        else:
+            out["with_allgather"]["peer_stores"] = "unavailable on this box (symmetric memory rendezvous failed); NCCL exchange reported"
+        del peer
     if ctx.rank == 0 and ctx.world == 1:
         xf, of, wf, bf, mf = x.float(), off.float(), w.float(), b.float(), m.float()
         old = torch.backends.cuda.matmul.allow_tf32
@@ -610,6 +629,41 @@ def main():
                   "note": "op + all-gather of the per-shard outputs (NCCL).  overlapped = 4 channel chunks, chunk i's all_gather_into_tensor on a "
                           "side stream under chunk i+1's kernel; serial = one un-overlapped collective after the full op; ms_per_step = the better "
                           "of the two; L2 flushed before every step"}
+
+        # the exchange fused into the kernel (vision_b200.sharded.PeerGather): every finished bin goes to all ranks' buffers, by one
+        # NVSwitch multicast store where the box offers it, else by one NVLink peer store per rank
+        peer = sharded.PeerGather.create((K_ROIS, 256, 7, 7), torch.float32, dev)
+        if ctx.max_over_ranks(0.0 if peer is not None else 1.0) == 0.0:
+            ref = sharded.all_gather_equal(torchvision.ops.roi_align(xd, rd, **kw))
+            fused = {}
+            for name, mc in (("multicast", True), ("peer_stores", False)):
+                if mc and ctx.max_over_ranks(0.0 if peer.mc_ptr else 1.0) != 0.0:
+                    continue
+                try:
+                    got = sharded.roi_align_gather(xd, rd, peer, multicast=mc, **kw)
+                    same = bool(torch.equal(got, ref))
+                    fms = ctx.device_ms(lambda: sharded.roi_align_gather(xd, rd, peer, multicast=mc, **kw), g_steps)
+                    fused[name] = {"ms_per_step": fms, "value": world * K_ROIS / (fms / 1e3), "identical_to_nccl_gather": same}
+                except Exception as ex:      # noqa: BLE001 - an unsupported transport must not take the line down
+                    fused[name] = {"error": repr(ex)[:200]}
+            ok = {k_: v for k_, v in fused.items() if v.get("identical_to_nccl_gather")}
+            if ok:
+                bname = min(ok, key=lambda k_: ok[k_]["ms_per_step"])
+                ingress = (world - 1) * K_ROIS * 256 * 49 * 4
+                gather = {"ms_per_step": ok[bname]["ms_per_step"], "value": ok[bname]["value"], "unit": "RoIs/s",
+                          "bytes_gathered_per_rank": world * K_ROIS * 256 * 49 * 4, "transport": bname, "identical_to_nccl_gather": True,
+                          "nvlink_ingress_floor_ms": ingress / 900e9 * 1e3,
+                          "note": "all-gather fused into the roi_align kernel (no NCCL call): each finished bin is stored into every rank's gathered "
+                                  "buffer (torch symmetric memory; multicast = one multimem.st replicated by the NVSwitch, peer_stores = one NVLink "
+                                  "store per rank), one device-side barrier before and after.  Every rank RECEIVES (world-1) x 50 MB per step: "
+                                  "nvlink_ingress_floor_ms is that volume at 900 GB/s, the bound of this exchange whatever the transport",
+                          "fused_variants": fused, "nccl": gather}
+            else:
+                gather["fused_variants"] = fused
+            del ref
+        else:
+            gather["peer_stores"] = "unavailable on this box (symmetric memory rendezvous failed); NCCL exchange reported"
+        del peer
 
     configs = {}
     want = set(args.configs.split(",")) if not args.no_secondary else set()

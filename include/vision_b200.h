@@ -94,6 +94,15 @@ VB200_API int vb200_roi_align_forward(const void* input, const void* rois, void*
                             int pooled_h, int pooled_w, double spatial_scale,
                             int sampling_ratio, int aligned, void* workspace,
                             size_t workspace_bytes, vb200_stream stream);
+/* roi_align fused with the all-gather of its output over the GPUs of one box: outputs[0] is the caller's slot
+ * of its own gathered buffer, outputs[1..n_outputs) the SAME slot of every peer's buffer (peer-mapped device pointers);
+ * multicast_output, when not NULL, is ONE NVSwitch multicast address of that slot and replaces the per-peer stores
+ * (multimem.st: the switch replicates each store to every rank, the local one included; fp32 only).  Same arguments and
+ * workspace as vb200_roi_align_forward otherwise.  The caller synchronises the ranks before anyone reads the buffers. */
+VB200_API int vb200_roi_align_forward_gather(const void* input, const void* rois, void* const* outputs, int n_outputs,
+                                   void* multicast_output, int dtype, int batch, int channels, int height, int width,
+                                   int num_rois, int pooled_h, int pooled_w, double spatial_scale, int sampling_ratio,
+                                   int aligned, void* workspace, size_t workspace_bytes, vb200_stream stream);
 
 /* ---- MultiScaleRoIAlign, fused -----------------------------------------
  * Replaces _multiscale_roi_align, torchvision/ops/poolers.py:147-228: per level {where, gather rois, roi_align,
@@ -249,6 +258,16 @@ VB200_API int vb200_deform_conv2d_forward_ex(const void* input, const void* weig
                                    int c_in, int in_h, int in_w, int c_out, int kh, int kw, int stride_h, int stride_w,
                                    int pad_h, int pad_w, int dil_h, int dil_w, int groups, int offset_groups, int use_mask,
                                    void* workspace, size_t workspace_bytes, vb200_stream stream);
+/* deform_conv2d fused with the all-gather of its output over the GPUs of one box (the batch shards, one
+ * all-gather of the per-shard outputs): outs[0] is the caller's slot of its own gathered buffer, outs[1..n_outs) the SAME slot
+ * of every peer's buffer (peer-mapped device pointers); the tcgen05 kernel's epilogue stores each output element to all of
+ * them.  Other arguments as vb200_deform_conv2d_forward_ex.  The caller synchronises the ranks before anyone reads. */
+VB200_API int vb200_deform_conv2d_forward_gather(const void* input, const void* weight, const void* packed_weight, int input_is_nhwc,
+                                       const void* offset, const void* mask, const void* bias, void* const* outs, int n_outs,
+                                       int dtype, int batch, int c_in, int in_h, int in_w, int c_out, int kh, int kw,
+                                       int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                                       int offset_groups, int use_mask, void* workspace, size_t workspace_bytes,
+                                       vb200_stream stream);
 
 /* ---- deform_conv2d backward ----------------------------------------------
  * Replace the kernels of deform_conv2d_backward_kernel, csrc/ops/cuda/deform_conv2d_kernel.cu:319-1033 (schema

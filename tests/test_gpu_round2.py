@@ -725,3 +725,41 @@ def test_resize_gather_writes_every_destination(vb):
             assert bool((b[:32] == 7).all()) and bool((b[32 + n:] == 7).all())
     with pytest.raises(RuntimeError, match="1..8 destinations"):
         torch.ops.vision_b200.resize_gather(x, [], 4, 4, 0, True)
+
+
+@pytest.mark.gpu
+def test_roi_align_gather_writes_every_destination(vb):
+    """vision_b200::roi_align_gather: the line kernel stores every bin to all destinations (peer slots on a multi-GPU box; three
+    local buffers here); configurations the line kernel does not cover are computed once and copied."""
+    from vision_b200 import workloads
+
+    for (c, k, pool, dtype) in ((16, 300, 7, torch.float32), (8, 40, 5, torch.float32), (4, 30, 7, torch.float64)):
+        x, rois, kw = workloads.cfg2_roi_align(seed=3, k=k, batch=2, channels=c, height=48, width=64)
+        x, rois = x.to(DEV, dtype), rois.to(DEV, dtype)
+        want = torch.ops.vision_b200.roi_align(x, rois, 0.25, pool, pool, 2, False)
+        n = want.numel()
+        bufs = [torch.full((n + 32,), -3.0, dtype=dtype, device=DEV) for _ in range(3)]
+        ptrs = [b.data_ptr() + 16 * b.element_size() for b in bufs]
+        torch.ops.vision_b200.roi_align_gather(x, rois, ptrs, 0, 0.25, pool, pool, 2, False)
+        for b in bufs:
+            assert torch.equal(b[16:16 + n].view(want.shape), want)
+            assert bool((b[:16] == -3).all()) and bool((b[16 + n:] == -3).all())
+
+
+@pytest.mark.gpu
+def test_deform_conv2d_gather_writes_every_destination(vb):
+    """vision_b200::deform_conv2d_gather: the tcgen05 epilogue stores each output element to all destinations (peer slots on a
+    multi-GPU box; three local buffers here); shapes on the SIMT kernel are computed once and copied."""
+    from vision_b200 import workloads
+
+    for (cin, cout, hw, dtype) in ((64, 128, 16, torch.bfloat16), (8, 8, 9, torch.float32)):
+        x, off, w, b, m = workloads.cfg4_deform_conv2d(seed=2, batch=2, c_in=cin, c_out=cout, hw=hw, dtype=dtype)
+        x, off, w, b, m = [t.to(DEV) for t in (x, off, w, b, m)]
+        want = torch.ops.vision_b200.deform_conv2d(x, w, off, m, b, 1, 1, 1, 1, 1, 1, 1, 1, True)
+        n = want.numel()
+        bufs = [torch.full((n + 128,), 5.0, dtype=dtype, device=DEV) for _ in range(3)]
+        ptrs = [t.data_ptr() + 64 * t.element_size() for t in bufs]
+        torch.ops.vision_b200.deform_conv2d_gather(x, w, off, m, b, ptrs, 1, 1, 1, 1, 1, 1, 1, 1, True)
+        for t in bufs:
+            assert torch.equal(t[64:64 + n].view(want.shape), want)
+            assert bool((t[:64] == 5).all()) and bool((t[64 + n:] == 5).all())

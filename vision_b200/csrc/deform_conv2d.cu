@@ -222,7 +222,6 @@ deform_conv2d_f64_kernel(const double* __restrict__ in, const double* __restrict
 }  // namespace
 
 // deform_conv2d_tc.cu: returns 1 if handled, 0 if not applicable, other = error
-struct DcnHints { const void* packed_weight; int input_is_nhwc; };   // optional: pre-packed weights / channels-last input (no staging pass)
 int deform_conv2d_tc_try(const void* input, const void* weight, const void* offset, const void* mask, const void* bias,
                          void* out, int dtype, const DcnParams& p, void* workspace, size_t workspace_bytes, cudaStream_t st,
                          const DcnHints& hints);
@@ -257,7 +256,7 @@ extern "C" int vb200_deform_conv2d_forward(const void* input, const void* weight
                                            int offset_groups, int use_mask, void* workspace,
                                            size_t workspace_bytes, vb200_stream stream) {
   return dcn_forward_impl(input, weight, offset, mask, bias, out, dtype, batch, c_in, in_h, in_w, c_out, kh, kw, stride_h, stride_w, pad_h,
-                          pad_w, dil_h, dil_w, groups, offset_groups, use_mask, workspace, workspace_bytes, stream, DcnHints{nullptr, 0});
+                          pad_w, dil_h, dil_w, groups, offset_groups, use_mask, workspace, workspace_bytes, stream, DcnHints{nullptr, 0, nullptr, 0, nullptr});
 }
 
 extern "C" size_t vb200_deform_conv2d_packed_weight_bytes(int dtype, int c_in, int c_out, int kh, int kw, int groups, int offset_groups) {
@@ -282,7 +281,29 @@ extern "C" int vb200_deform_conv2d_forward_ex(const void* input, const void* wei
                                               size_t workspace_bytes, vb200_stream stream) {
   return dcn_forward_impl(input, weight, offset, mask, bias, out, dtype, batch, c_in, in_h, in_w, c_out, kh, kw, stride_h, stride_w, pad_h,
                           pad_w, dil_h, dil_w, groups, offset_groups, use_mask, workspace, workspace_bytes, stream,
-                          DcnHints{packed_weight, input_is_nhwc});
+                          DcnHints{packed_weight, input_is_nhwc, nullptr, 0, nullptr});
+}
+
+// deform_conv2d fused with the all-gather of its output: outs[0] is the caller's slot of its own gathered buffer, outs[1..n) the
+// same slot of the peers' buffers (peer-mapped).  The tcgen05 kernel's epilogue stores each element to all of them; shapes that
+// take another kernel are computed into outs[0] and copied to the peers on the same stream.
+extern "C" int vb200_deform_conv2d_forward_gather(const void* input, const void* weight, const void* packed_weight, int input_is_nhwc,
+                                                  const void* offset, const void* mask, const void* bias, void* const* outs, int n_outs,
+                                                  int dtype, int batch, int c_in, int in_h, int in_w, int c_out, int kh, int kw,
+                                                  int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                                                  int offset_groups, int use_mask, void* workspace, size_t workspace_bytes,
+                                                  vb200_stream stream) {
+  VB200_REQUIRE(outs && n_outs >= 1 && n_outs <= 8, "deform_conv2d_gather: 1..8 destinations");
+  for (int d = 0; d < n_outs; ++d) VB200_REQUIRE(outs[d] != nullptr, "deform_conv2d_gather: null destination");
+  bool done = false;
+  const int rc = dcn_forward_impl(input, weight, offset, mask, bias, outs[0], dtype, batch, c_in, in_h, in_w, c_out, kh, kw, stride_h,
+                                  stride_w, pad_h, pad_w, dil_h, dil_w, groups, offset_groups, use_mask, workspace, workspace_bytes, stream,
+                                  DcnHints{packed_weight, input_is_nhwc, outs + 1, n_outs - 1, &done});
+  if (rc || done || n_outs == 1 || batch == 0 || c_out == 0) return rc;
+  const size_t esize = dtype == VB200_F64 ? 8 : dtype == VB200_F32 ? 4 : 2;
+  const size_t bytes = (size_t)batch * c_out * dcn_out_dim(in_h, pad_h, dil_h, kh, stride_h) * dcn_out_dim(in_w, pad_w, dil_w, kw, stride_w) * esize;
+  for (int d = 1; d < n_outs; ++d) VB200_CUDA_TRY(cudaMemcpyAsync(outs[d], outs[0], bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
 }
 
 static int dcn_forward_impl(const void* input, const void* weight, const void* offset, const void* mask, const void* bias, void* out,

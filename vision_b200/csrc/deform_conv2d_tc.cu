@@ -23,7 +23,6 @@
 
 namespace vb200 {
 
-struct DcnHints { const void* packed_weight; int input_is_nhwc; };
 
 namespace {
 
@@ -352,7 +351,10 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
         for (int j = 0; j < 16; ++j) {
           const int co = nt * BN + col + j;
           const float bv = bias ? to_acc(bias[co]) : 0.f;
-          out[((int64_t)b * p.c_out + co) * HWo + pix] = from_acc<T, float>(__uint_as_float(r[j]) + bv);
+          const T v = from_acc<T, float>(__uint_as_float(r[j]) + bv);
+          const int64_t idx = ((int64_t)b * p.c_out + co) * HWo + pix;
+          out[idx] = v;
+          for (int d = 0; d < p.n_peer; ++d) reinterpret_cast<T*>(p.peer_out[d])[idx] = v;     // fused all-gather: peer slots
         }
       }
     }
@@ -1054,6 +1056,9 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
   const int BN = tc_pick_bn(p);
   dim3 grid((unsigned)(p.batch * ceil_div(HWo, TC_BM)), (unsigned)(p.c_out / BN));
   const size_t smem = tc_smem_bytes(BN, KK);
+  p.n_peer = hints.peer_out ? hints.n_peer : 0;
+  for (int d = 0; d < p.n_peer; ++d) p.peer_out[d] = hints.peer_out[d];
+  if (hints.peers_done) *hints.peers_done = true;
 #define VB200_TC_LAUNCH(BN_, ST_)                                                                                         \
   {                                                                                                                       \
     VB200_CUDA_TRY(ensure_dyn_smem<deform_conv2d_tc_kernel<T, BN_, ST_, tc_kb(BN_)>>(smem));                         \

@@ -432,6 +432,11 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
   return v;
 }
 
+// Destinations of the fused all-gather (vb200_roi_align_forward_gather): besides `output` (the caller's slot of its own gathered
+// buffer) every finished bin is stored to the same slot of the peers' buffers - `n` peer-mapped pointers, or ONE NVSwitch
+// multicast address `mc` (multimem.st: the switch replicates the store to every rank, the local one included).
+struct PeerDst { float* dst[7]; float* mc; int n; };
+
 constexpr int kLineThreads = 1024;
 constexpr int kLineStageBytes = (kLineThreads / 32) * 2 * 128;   // per warp: two 128-byte slots (loop entries + header)
 
@@ -444,7 +449,7 @@ template <int P, int SR, bool MULTI>
 __global__ void __launch_bounds__(kLineThreads, 1)
 roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict__ tab, float* __restrict__ output,
                       int B, int C, int H, int W, int K, int pitch, LevelSet L, const int* __restrict__ lvl_count,
-                      const int* __restrict__ bucket) {
+                      const int* __restrict__ bucket, PeerDst pd) {
   constexpr int NS = P * SR, NL = NS * 2, NB = P * P;
   static_assert(NL <= 32 && SR == 2 && P <= 8 && NS == 14, "lane mapping: 4 lanes per bin column, two finished bins per lane");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -596,8 +601,19 @@ roi_align_line_kernel(const float* __restrict__ input, const LineTab* __restrict
           s2[m] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
         }
         float* __restrict__ o = outp + (lane_is_y ? off_y : off_x);
-        if (st0) o[0] = s2[0] * inv_count;
-        if (st1) o[lane_is_y ? 1 : P] = s2[1] * inv_count;
+        float* __restrict__ o1 = o + (lane_is_y ? 1 : P);
+        const float v0 = s2[0] * inv_count, v1 = s2[1] * inv_count;
+        if (pd.mc != nullptr) {              // one store each, replicated by the switch into every rank's buffer
+          if (st0) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(pd.mc + (o - output)), "f"(v0) : "memory");
+          if (st1) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(pd.mc + (o1 - output)), "f"(v1) : "memory");
+        } else {
+          if (st0) o[0] = v0;
+          if (st1) o1[0] = v1;
+          for (int d = 0; d < pd.n; ++d) {   // peer-mapped copies of the same slot (NVLink stores)
+            if (st0) pd.dst[d][o - output] = v0;
+            if (st1) pd.dst[d][o1 - output] = v1;
+          }
+        }
       }
       slot ^= 128u;
       le = le_next;
@@ -1400,11 +1416,11 @@ extern "C" size_t vb200_roi_align_workspace_bytes(int dtype, int batch, int chan
   return roi_align_path(dtype, nullptr, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio) ? a : 0;
 }
 
-extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void* output, int dtype,
-                                       int batch, int channels, int height, int width, int num_rois,
-                                       int pooled_h, int pooled_w, double spatial_scale,
-                                       int sampling_ratio, int aligned, void* workspace,
-                                       size_t workspace_bytes, vb200_stream stream) {
+static int roi_align_forward_impl(const void* input, const void* rois, void* output, int dtype,
+                                  int batch, int channels, int height, int width, int num_rois,
+                                  int pooled_h, int pooled_w, double spatial_scale,
+                                  int sampling_ratio, int aligned, void* workspace,
+                                  size_t workspace_bytes, vb200_stream stream, const PeerDst& peers, bool* peers_done) {
   VB200_REQUIRE(batch >= 0 && channels >= 0 && height >= 0 && width >= 0 && num_rois >= 0, "roi_align: negative size");
   VB200_REQUIRE(pooled_h > 0 && pooled_w > 0, "roi_align: pooled size must be positive");
   if (num_rois == 0 || channels == 0) return 0;
@@ -1415,6 +1431,8 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
   if (dtype == VB200_F32) {
     const size_t geo_pad = roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio);
     int path = roi_align_path(dtype, input, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio);
+    const bool want_peers = peers.n > 0 || peers.mc != nullptr;
+    if (want_peers && path == 3) path = 2;       // the band kernel's RED protocol is local-only; same applicability as the line kernel
     if (path && (workspace == nullptr || ((uintptr_t)workspace % 16) != 0 ||
                  workspace_bytes < roi_align_ws_bytes(path, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio)))
       path = 0;
@@ -1458,6 +1476,7 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       const int64_t pairs = (int64_t)batch * channels * num_rois;
       const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
       VB200_CUDA_TRY(ensure_dyn_smem<roi_align_line_kernel<7, 2, false>>(smem));
+      if (peers_done) *peers_done = true;        // this kernel writes the peer destinations itself
       // programmatic dependent launch: the gather kernel zeroes its pads and stages its first plane while
       // the geometry kernel is still running, and waits (griddepcontrol.wait) before it reads the table
       cudaLaunchConfig_t cfg = {};
@@ -1468,7 +1487,7 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
       cfg.attrs = attr; cfg.numAttrs = 1;
       VB200_CUDA_TRY(cudaLaunchKernelEx(&cfg, roi_align_line_kernel<7, 2, false>, (const float*)input, (const LineTab*)tab,
                                         (float*)output, batch, channels, height, width, num_rois, pitch, none,
-                                        (const int*)nullptr, (const int*)nullptr));
+                                        (const int*)nullptr, (const int*)nullptr, peers));
       return check_launch("roi_align_line_kernel");
     }
     const bool use_plane = path == 1;
@@ -1516,6 +1535,40 @@ extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void
                                             pooled_w, spatial_scale, sampling_ratio, aligned, st);
   set_error("roi_align: unsupported dtype %d (float, double, half as the reference)", dtype);
   return VB200_EUNSUPPORTED;
+}
+
+extern "C" int vb200_roi_align_forward(const void* input, const void* rois, void* output, int dtype,
+                                       int batch, int channels, int height, int width, int num_rois,
+                                       int pooled_h, int pooled_w, double spatial_scale,
+                                       int sampling_ratio, int aligned, void* workspace,
+                                       size_t workspace_bytes, vb200_stream stream) {
+  return roi_align_forward_impl(input, rois, output, dtype, batch, channels, height, width, num_rois, pooled_h, pooled_w, spatial_scale,
+                                sampling_ratio, aligned, workspace, workspace_bytes, stream, PeerDst{}, nullptr);
+}
+
+// roi_align fused with the all-gather of its output: outputs[0] is the caller's slot of its gathered buffer, outputs[1..n) the
+// same slot of the peers' buffers (peer-mapped), or - when `multicast_output` is not NULL - one NVSwitch multicast address of
+// that slot that reaches every rank.  The line kernel stores every finished bin to all of them; configurations it does not
+// cover are computed into outputs[0] and copied to the peers on the same stream.
+extern "C" int vb200_roi_align_forward_gather(const void* input, const void* rois, void* const* outputs, int n_outputs,
+                                              void* multicast_output, int dtype, int batch, int channels, int height, int width,
+                                              int num_rois, int pooled_h, int pooled_w, double spatial_scale, int sampling_ratio,
+                                              int aligned, void* workspace, size_t workspace_bytes, vb200_stream stream) {
+  VB200_REQUIRE(outputs && n_outputs >= 1 && n_outputs <= 8, "roi_align_gather: 1..8 destinations");
+  for (int d = 0; d < n_outputs; ++d) VB200_REQUIRE(outputs[d] != nullptr, "roi_align_gather: null destination");
+  PeerDst pd = {};
+  pd.mc = dtype == VB200_F32 ? (float*)multicast_output : nullptr;
+  pd.n = pd.mc ? 0 : n_outputs - 1;
+  for (int d = 0; d < pd.n; ++d) pd.dst[d] = (float*)outputs[d + 1];
+  bool done = false;
+  const int rc = roi_align_forward_impl(input, rois, outputs[0], dtype, batch, channels, height, width, num_rois, pooled_h, pooled_w,
+                                        spatial_scale, sampling_ratio, aligned, workspace, workspace_bytes, stream, pd, &done);
+  if (rc || done || n_outputs == 1 || num_rois == 0 || channels == 0) return rc;
+  const size_t esize = dtype == VB200_F64 ? 8 : dtype == VB200_F32 ? 4 : 2;
+  const size_t bytes = (size_t)num_rois * channels * pooled_h * pooled_w * esize;
+  for (int d = 1; d < n_outputs; ++d)
+    VB200_CUDA_TRY(cudaMemcpyAsync(outputs[d], outputs[0], bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
 }
 
 // ---- fused MultiScaleRoIAlign ------------------------------------------------------------------------------------
@@ -1588,7 +1641,7 @@ extern "C" int vb200_multiscale_roi_align_forward(const void* const* level_ptrs,
   const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
   VB200_CUDA_TRY(ensure_dyn_smem<roi_align_line_kernel<7, 2, true>>(smem));
   roi_align_line_kernel<7, 2, true><<<grid, kLineThreads, smem, st>>>(nullptr, ws.tab, (float*)output, batch, channels, 0, 0, num_rois, 0,
-                                                                     L, ws.lvl_count, ws.bucket);
+                                                                     L, ws.lvl_count, ws.bucket, PeerDst{});
   return check_launch("roi_align_line_kernel");
 }
 

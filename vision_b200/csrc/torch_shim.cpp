@@ -80,6 +80,29 @@ at::Tensor roi_align(const at::Tensor& input, const at::Tensor& rois, double spa
   return out;
 }
 
+// roi_align + all-gather by peer stores: dst_ptrs[0] = this rank's slot of its own gathered buffer, dst_ptrs[1..] = the same
+// slot of the peers' buffers; mc_ptr != 0: one NVSwitch multicast address of the slot instead (device pointers as integers).
+void roi_align_gather(const at::Tensor& input, const at::Tensor& rois, at::IntArrayRef dst_ptrs, int64_t mc_ptr, double spatial_scale,
+                      int64_t pooled_height, int64_t pooled_width, int64_t sampling_ratio, bool aligned) {
+  check_roi_inputs(input, rois);
+  TORCH_CHECK(dst_ptrs.size() >= 1 && dst_ptrs.size() <= 8, "roi_align_gather: 1..8 destinations");
+  at::cuda::CUDAGuard guard(input.device());
+  const int64_t K = rois.size(0), N = input.size(0), C = input.size(1), H = input.size(2), W = input.size(3);
+  if (K * C * pooled_height * pooled_width == 0) return;
+  const int dt = dtype_code(input.scalar_type(), "roi_align");
+  at::Tensor in_c = input.contiguous(), rois_c = rois.contiguous();
+  const size_t wsb = vb200_roi_align_workspace_bytes(dt, (int)N, (int)C, (int)H, (int)W, (int)K, (int)pooled_height,
+                                                     (int)pooled_width, (int)sampling_ratio);
+  at::Tensor ws = workspace(wsb, input);
+  void* outs[8];
+  for (size_t d = 0; d < dst_ptrs.size(); ++d) outs[d] = reinterpret_cast<void*>(static_cast<uintptr_t>(dst_ptrs[d]));
+  check_rc(vb200_roi_align_forward_gather(in_c.data_ptr(), rois_c.data_ptr(), outs, (int)dst_ptrs.size(),
+                                          reinterpret_cast<void*>(static_cast<uintptr_t>(mc_ptr)), dt, (int)N, (int)C, (int)H, (int)W, (int)K,
+                                          (int)pooled_height, (int)pooled_width, spatial_scale, (int)sampling_ratio, aligned ? 1 : 0,
+                                          wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
+           "roi_align_gather");
+}
+
 std::tuple<at::Tensor, at::Tensor> roi_pool(const at::Tensor& input, const at::Tensor& rois, double spatial_scale,
                                             int64_t pooled_height, int64_t pooled_width) {
   check_roi_inputs(input, rois);
@@ -427,10 +450,12 @@ at::Tensor packed_weight_for(const at::Tensor& weight_c, int dt, int c_in, int c
   return packed;
 }
 
-at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset,
-                         const at::Tensor& mask, const at::Tensor& bias, int64_t stride_h, int64_t stride_w,
-                         int64_t pad_h, int64_t pad_w, int64_t dilation_h, int64_t dilation_w, int64_t n_weight_grps,
-                         int64_t n_offset_grps, bool use_mask) {
+// dst_ptrs == nullptr: allocate and return the output.  Otherwise (fused all-gather): write to dst_ptrs[0] (this rank's slot of its
+// own gathered buffer) and dst_ptrs[1..] (the same slot of the peers' buffers); returns an undefined tensor.
+at::Tensor deform_conv2d_impl(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset,
+                              const at::Tensor& mask, const at::Tensor& bias, int64_t stride_h, int64_t stride_w,
+                              int64_t pad_h, int64_t pad_w, int64_t dilation_h, int64_t dilation_w, int64_t n_weight_grps,
+                              int64_t n_offset_grps, bool use_mask, const at::IntArrayRef* dst_ptrs) {
   // a channels-last input is handed to the tensor-core path as it is (no NCHW -> NHWC staging pass)
   const bool nhwc_in = input.dim() == 4 && !input.is_contiguous() && input.is_contiguous(at::MemoryFormat::ChannelsLast);
   at::Tensor input_c = nhwc_in ? input : input.contiguous(), offset_c = offset.contiguous(), weight_c = weight.contiguous();
@@ -471,8 +496,8 @@ at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, cons
                   bias_c.scalar_type() == st,
               "deform_conv2d: all tensors must share one dtype");
 
-  at::Tensor out = at::empty({batch, c_out, out_h, out_w}, input_c.options());
-  if (batch == 0 || out.numel() == 0) return out;
+  at::Tensor out = dst_ptrs ? at::Tensor() : at::empty({batch, c_out, out_h, out_w}, input_c.options());
+  if (batch == 0 || batch * c_out * out_h * out_w == 0) return out;
   const int dt = dtype_code(st, "deform_conv2d");
   TORCH_CHECK(dt == VB200_F32 || dt == VB200_F16 || dt == VB200_BF16 || dt == VB200_F64, "deform_conv2d: unsupported dtype ", st);
   TORCH_CHECK(bias_c.numel() == c_out, "bias must have one entry per output channel");
@@ -484,14 +509,38 @@ at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, cons
                           : at::Tensor();
   const bool nhwc_ok = nhwc_in && wsb > 0 && ((uintptr_t)input_c.data_ptr() % 16) == 0;      // wsb > 0 <=> tensor-core path
   if (nhwc_in && !nhwc_ok) input_c = input.contiguous();
-  check_rc(vb200_deform_conv2d_forward_ex(input_c.data_ptr(), weight_c.data_ptr(), packed.defined() ? packed.data_ptr() : nullptr,
-                                          nhwc_ok ? 1 : 0, offset_c.data_ptr(), use_mask ? mask_c.data_ptr() : nullptr, bias_c.data_ptr(),
-                                          out.data_ptr(), dt, (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out, (int)kh, (int)kw,
-                                          (int)stride_h, (int)stride_w, (int)pad_h, (int)pad_w, (int)dilation_h, (int)dilation_w,
-                                          (int)n_weight_grps, (int)n_offset_grps, use_mask ? 1 : 0, wsb ? ws.data_ptr() : nullptr, wsb,
-                                          cur_stream()),
+  void* outs[8];
+  int n_outs = 1;
+  if (dst_ptrs) {
+    TORCH_CHECK(dst_ptrs->size() >= 1 && dst_ptrs->size() <= 8, "deform_conv2d_gather: 1..8 destinations");
+    n_outs = (int)dst_ptrs->size();
+    for (int d = 0; d < n_outs; ++d) outs[d] = reinterpret_cast<void*>(static_cast<uintptr_t>((*dst_ptrs)[d]));
+  } else {
+    outs[0] = out.data_ptr();
+  }
+  check_rc(vb200_deform_conv2d_forward_gather(input_c.data_ptr(), weight_c.data_ptr(), packed.defined() ? packed.data_ptr() : nullptr,
+                                              nhwc_ok ? 1 : 0, offset_c.data_ptr(), use_mask ? mask_c.data_ptr() : nullptr,
+                                              bias_c.data_ptr(), outs, n_outs, dt, (int)batch, (int)c_in, (int)in_h, (int)in_w, (int)c_out,
+                                              (int)kh, (int)kw, (int)stride_h, (int)stride_w, (int)pad_h, (int)pad_w, (int)dilation_h,
+                                              (int)dilation_w, (int)n_weight_grps, (int)n_offset_grps, use_mask ? 1 : 0,
+                                              wsb ? ws.data_ptr() : nullptr, wsb, cur_stream()),
            "deform_conv2d");
   return out;
+}
+
+at::Tensor deform_conv2d(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset,
+                         const at::Tensor& mask, const at::Tensor& bias, int64_t stride_h, int64_t stride_w,
+                         int64_t pad_h, int64_t pad_w, int64_t dilation_h, int64_t dilation_w, int64_t n_weight_grps,
+                         int64_t n_offset_grps, bool use_mask) {
+  return deform_conv2d_impl(input, weight, offset, mask, bias, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, n_weight_grps,
+                            n_offset_grps, use_mask, nullptr);
+}
+
+void deform_conv2d_gather(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& offset, const at::Tensor& mask,
+                          const at::Tensor& bias, at::IntArrayRef dst_ptrs, int64_t stride_h, int64_t stride_w, int64_t pad_h, int64_t pad_w,
+                          int64_t dilation_h, int64_t dilation_w, int64_t n_weight_grps, int64_t n_offset_grps, bool use_mask) {
+  deform_conv2d_impl(input, weight, offset, mask, bias, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, n_weight_grps,
+                     n_offset_grps, use_mask, &dst_ptrs);
 }
 
 // ---- deform_conv2d backward (schema csrc/ops/deform_conv2d.cpp:103-104; reference deform_conv2d_kernel.cu:647-1033) -------
@@ -684,6 +733,8 @@ TORCH_LIBRARY(vision_b200, m) {
   m.def("_deform_conv2d_backward(Tensor grad, Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, SymInt stride_h, SymInt stride_w, SymInt pad_h, SymInt pad_w, SymInt dilation_h, SymInt dilation_w, SymInt groups, SymInt offset_groups, bool use_mask) -> (Tensor, Tensor, Tensor, Tensor, Tensor)");
   m.def("resize(Tensor input, int out_h, int out_w, int mode, bool antialias) -> Tensor");
   m.def("resize_gather(Tensor input, int[] dst_ptrs, int out_h, int out_w, int mode, bool antialias) -> ()");
+  m.def("deform_conv2d_gather(Tensor input, Tensor weight, Tensor offset, Tensor mask, Tensor bias, int[] dst_ptrs, int stride_h, int stride_w, int pad_h, int pad_w, int dilation_h, int dilation_w, int groups, int offset_groups, bool use_mask) -> ()");
+  m.def("roi_align_gather(Tensor input, Tensor rois, int[] dst_ptrs, int mc_ptr, float spatial_scale, int pooled_height, int pooled_width, int sampling_ratio, bool aligned) -> ()");
   m.def("resize_crop_normalize(Tensor input, int resize_h, int resize_w, int crop_top, int crop_left, int crop_h, int crop_w, int mode, bool antialias, float[] mean, float[] std) -> Tensor");
   m.def("box_iou_rotated(Tensor boxes1, Tensor boxes2) -> Tensor");
   m.def("detection_postprocess(Tensor boxes, Tensor scores, Tensor labels, float img_h, float img_w, float score_thresh, bool score_inclusive, float min_size, float nms_thresh, int topk) -> (Tensor, Tensor, Tensor)");
@@ -709,6 +760,8 @@ TORCH_LIBRARY_IMPL(vision_b200, CUDA, m) {
   m.impl("deform_conv2d", TORCH_FN(deform_conv2d));
   m.impl("resize", TORCH_FN(resize));
   m.impl("resize_gather", TORCH_FN(resize_gather));
+  m.impl("deform_conv2d_gather", TORCH_FN(deform_conv2d_gather));
+  m.impl("roi_align_gather", TORCH_FN(roi_align_gather));
   m.impl("_roi_align_backward", TORCH_FN(roi_align_backward));
   m.impl("_roi_pool_backward", TORCH_FN(roi_pool_backward));
   m.impl("_ps_roi_align_backward", TORCH_FN(ps_roi_align_backward));

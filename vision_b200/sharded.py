@@ -239,6 +239,14 @@ class PeerGather:
         shard_bytes = buf[0].numel() * buf.element_size()
         order = [rank] + [r for r in range(world) if r != rank]
         self.dst_ptrs = [int(hdl.buffer_ptrs[r]) + rank * shard_bytes for r in order]
+        # NVSwitch multicast address of this rank's slot (0 when the box / allocation has no multicast object): ONE store to
+        # it is replicated by the switch into every rank's buffer (multimem.st), instead of world - 1 peer stores
+        mc = 0
+        try:
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        except Exception:                            # noqa: BLE001
+            mc = 0
+        self.mc_ptr = mc + rank * shard_bytes if mc else 0
 
     @classmethod
     def create(cls, shard_shape: Sequence[int], dtype: torch.dtype, device, group=None) -> Optional["PeerGather"]:
@@ -288,4 +296,57 @@ def resize_gather(local: torch.Tensor, size, peer: Optional[PeerGather], interpo
     peer.barrier()                                   # every rank is done reading the previous step's result
     torch.ops.vision_b200.resize_gather(local, peer.dst_ptrs, oh, ow, mode, bool(antialias))
     peer.barrier()                                   # every rank's stores have landed everywhere
+    return peer.gathered()
+
+
+def roi_align_gather(input: torch.Tensor, rois: torch.Tensor, peer: Optional[PeerGather], output_size=(7, 7), spatial_scale: float = 1.0,
+                     sampling_ratio: int = -1, aligned: bool = False, multicast: bool = True, group=None):
+    """``roi_align`` of this rank's RoIs + all-gather of the ``[K, C, PH, PW]`` outputs over the ranks, rank-major.
+
+    With a `PeerGather` buffer the exchange is fused into the kernel: every finished bin is stored to all ranks' buffers - one
+    NVSwitch multicast store (``multimem.st``) when the buffer has a multicast address and ``multicast`` is set, otherwise one
+    NVLink peer store per rank.  Without a buffer: the op followed by one NCCL all-gather."""
+    from . import _lib, ops as _ops
+
+    rank, world = _world(group)
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+    if peer is None or world == 1:
+        return all_gather_equal(_ops.roi_align(input, rois, (ph, pw), spatial_scale, sampling_ratio, aligned), group=group)
+    k, c = rois.shape[0], input.shape[1]
+    assert tuple(peer.buf.shape) == (world, k, c, ph, pw) and peer.buf.dtype == input.dtype, "PeerGather buffer does not match the output shard"
+    _lib.load_ops()
+    mc = peer.mc_ptr if (multicast and input.dtype == torch.float32) else 0
+    peer.barrier()
+    torch.ops.vision_b200.roi_align_gather(input, rois, peer.dst_ptrs, mc, float(spatial_scale), ph, pw, int(sampling_ratio), bool(aligned))
+    peer.barrier()
+    return peer.gathered()
+
+
+def deform_conv2d_gather(input: torch.Tensor, offset: torch.Tensor, weight: torch.Tensor, bias, peer: Optional[PeerGather],
+                         stride=(1, 1), padding=(0, 0), dilation=(1, 1), mask=None, group=None):
+    """``deform_conv2d`` on this rank's images + all-gather of the ``[n, C_out, H, W]`` outputs over the ranks, rank-major.
+
+    With a `PeerGather` buffer the tcgen05 kernel's epilogue stores every output element to all ranks' buffers (NVLink peer
+    stores); without one: the op followed by the NCCL exchange."""
+    from . import _lib, ops as _ops
+
+    rank, world = _world(group)
+    if peer is None or world == 1:
+        return all_gather_equal(_ops.deform_conv2d(input, offset, weight, bias, stride, padding, dilation, mask), group=group)
+    use_mask = mask is not None
+    if mask is None:
+        mask = torch.zeros((input.shape[0], 1), device=input.device, dtype=input.dtype)
+    if bias is None:
+        bias = torch.zeros(weight.shape[0], device=input.device, dtype=input.dtype)
+    (sh, sw), (ph, pw), (dh, dw) = _ops._pair(stride), _ops._pair(padding), _ops._pair(dilation)
+    kh, kw = weight.shape[-2:]
+    n_offset_grps = offset.shape[1] // (2 * kh * kw)
+    n_weight_grps = input.shape[1] // weight.shape[1]
+    assert peer.buf.shape[0] == world and peer.buf.shape[1] == input.shape[0] and peer.buf.shape[2] == weight.shape[0] and \
+        tuple(peer.buf.shape[3:]) == tuple(offset.shape[2:]) and peer.buf.dtype == input.dtype, "PeerGather buffer does not match the output shard"
+    _lib.load_ops()
+    peer.barrier()
+    torch.ops.vision_b200.deform_conv2d_gather(input, weight, offset, mask, bias, peer.dst_ptrs, sh, sw, ph, pw, dh, dw, n_weight_grps,
+                                               n_offset_grps, use_mask)
+    peer.barrier()
     return peer.gathered()
