@@ -82,7 +82,33 @@ def dcn():
         env("VB200_DCN_PATH", None)
 
 
-for name, fn in (("roi", roi), ("nms", nms), ("resize", resize), ("dcn", dcn)):
+def band():
+    """round 2: the band-resident roi_align kernel (several bands, split bin rows -> RED) and the multi-destination stores"""
+    x, r, kw = workloads.cfg2_roi_align(seed=3, k=200, batch=2, channels=8, height=80, width=200)
+    r = r.clone()
+    r[::7, 1:3] -= 90.0
+    r[1::11, 3:] += 400.0
+    x, r = x.to(dev), r.to(dev)
+    env("VB200_ROI_ALIGN_PATH", "band")
+    vb.ops.roi_align(x, r, 7, 0.25, 2, False)
+    vb.ops.roi_align(x, r, 7, 0.25, 2, True)
+    env("VB200_ROI_ALIGN_PATH", None)
+    want = vb.ops.roi_align(x, r, 7, 0.25, 2, False)
+    bufs = [torch.empty_like(want) for _ in range(3)]
+    torch.ops.vision_b200.roi_align_gather(x, r, [b.data_ptr() for b in bufs], 0, 0.25, 7, 7, 2, False)
+    img = torch.rand(2, 3, 96, 1024, device=dev).half()
+    o = [torch.empty(2, 3, 17, 40, device=dev, dtype=torch.float16) for _ in range(3)]
+    torch.ops.vision_b200.resize_gather(img, [t.data_ptr() for t in o], 17, 40, 0, True)
+    xi = torch.randn(2, 64, 12, 12, device=dev).bfloat16()
+    w = (torch.randn(128, 64, 3, 3, device=dev) * 0.05).bfloat16()
+    off = (torch.randn(2, 18, 12, 12, device=dev) * 2).bfloat16()
+    m = torch.rand(2, 9, 12, 12, device=dev).bfloat16()
+    bias = torch.randn(128, device=dev).bfloat16()
+    d = [torch.empty(2, 128, 12, 12, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+    torch.ops.vision_b200.deform_conv2d_gather(xi, w, off, m, bias, [t.data_ptr() for t in d], 1, 1, 1, 1, 1, 1, 1, 1, True)
+
+
+for name, fn in (("roi", roi), ("nms", nms), ("resize", resize), ("dcn", dcn), ("band", band)):
     if only in ("all", name):
         fn()
         torch.cuda.synchronize()
