@@ -432,7 +432,7 @@ def block_cfg4(ctx: Ctx, vb, tv, sharded) -> dict:
                                      "bytes_gathered_per_rank": ctx.world * x.numel() * 2, "identical_to_nccl_gather": same,
                                      "nvlink_ingress_floor_ms": ingress / 900e9 * 1e3,
                                      "note": "all-gather fused into the tcgen05 kernel's epilogue: each output element is stored to every rank's gathered "
-                                             "buffer (torch symmetric memory, NVLink peer stores), one device-side barrier before and after; no NCCL "
+                                             "buffer (torch symmetric memory, NVLink peer stores of 256-byte runs), one device-side barrier per step (double-buffered); no NCCL "
                                              "call.  nvlink_ingress_floor_ms = (world-1) x 134 MB received per rank per step at 900 GB/s",
                                      "nccl_overlapped": nccl}
             del want, got
@@ -508,7 +508,8 @@ def block_cfg5(ctx: Ctx, vb, tv, sharded) -> dict:
                                      "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2,
                                      "identical_to_nccl_gather": same,
                                      "note": "all-gather fused into the resize kernel: each finished pixel is stored to every rank's gathered buffer "
-                                             "(torch symmetric memory, NVLink peer stores), one device-side barrier before and after; no NCCL call",
+                                             "(torch symmetric memory, NVLink peer stores: whole 448-byte rows written by one warp), one device-side barrier per step "
+                                             "(double-buffered); no NCCL call",
                                      "nccl_overlapped": nccl}
             del want, got
         else:
@@ -657,7 +658,7 @@ def main():
                     gather.update({"ms_per_step": ok[bname]["ms_per_step"], "value": ok[bname]["value"], "transport": bname})
             gather["note"] += (".  fused_variants: the exchange done by the roi_align kernel's own stores into every rank's gathered buffer (torch symmetric "
                                "memory; multicast = one multimem.st replicated by the NVSwitch, peer_stores = one NVLink store per rank; 28-byte runs, "
-                               "so the links carry partial sectors), one device-side barrier before and after; ms_per_step / value = the fastest "
+                               "so the links carry partial sectors), one device-side barrier per step; ms_per_step / value = the fastest "
                                "transport.  Every rank RECEIVES (world-1) x 50 MB per step: nvlink_ingress_floor_ms is that volume at 900 GB/s, the "
                                "bound of this exchange whatever the transport")
             del ref

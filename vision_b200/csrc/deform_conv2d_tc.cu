@@ -341,20 +341,52 @@ deform_conv2d_tc_kernel(const T* __restrict__ nhwc, const T* __restrict__ wpacke
     const int col_half = warp >> 2;                           // four groups of 4 warps: a quarter of the columns each
     const int pix = pix0 + lane_base + lane;
     constexpr int COLS_PER_WARP = BN / (TC1_GATHER_WARPS / 4);
+    // Full tiles of 16-byte aligned outputs: the 4 warps of a column group transpose 16 channels x 128 pixels through the (now
+    // idle) pipeline stages and write each channel's 256 contiguous bytes with 16-byte vector stores - to `out` and to the peer
+    // slots of the fused all-gather, where whole 256-byte runs instead of 64-byte ones make full NVLink packets.
+    bool vec = sizeof(T) == 2 && pix0 + TC_BM <= HWo && (HWo % 8) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0;
+    for (int d = 0; d < p.n_peer; ++d) vec = vec && (reinterpret_cast<uintptr_t>(p.peer_out[d]) % 16) == 0;
+    if (vec) {
+      constexpr int SLAB = 16 * TC_BM * 2;                    // 16 channels x 128 pixels, 2-byte elements
+      unsigned char* est = stages + col_half * (2 * SLAB);    // two slabs per column group (alternating)
+      const int tg = (warp & 3) * 32 + lane;                  // thread index inside the column group
 #pragma unroll 1
-    for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
-      const int col = col_half * COLS_PER_WARP + c0;
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
-      if (pix < HWo) {
+      for (int c0 = 0, it = 0; c0 < COLS_PER_WARP; c0 += 16, ++it) {
+        const int col = col_half * COLS_PER_WARP + c0;
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
+        T* slab = reinterpret_cast<T*>(est + (it & 1) * SLAB);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int co = nt * BN + col + j;
-          const float bv = bias ? to_acc(bias[co]) : 0.f;
-          const T v = from_acc<T, float>(__uint_as_float(r[j]) + bv);
-          const int64_t idx = ((int64_t)b * p.c_out + co) * HWo + pix;
-          out[idx] = v;
-          for (int d = 0; d < p.n_peer; ++d) reinterpret_cast<T*>(p.peer_out[d])[idx] = v;     // fused all-gather: peer slots
+          const float bv = bias ? to_acc(bias[nt * BN + col + j]) : 0.f;
+          slab[j * TC_BM + tg] = from_acc<T, float>(__uint_as_float(r[j]) + bv);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + col_half) : "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int idx = tg + 128 * h, ch = idx >> 4, seg = idx & 15;
+          const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(slab) + ch * (TC_BM * 2) + seg * 16);
+          const int64_t eoff = (((int64_t)b * p.c_out + nt * BN + col + ch) * HWo + pix0) * 2 + seg * 16;      // bytes
+          *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(out) + eoff) = q;
+          for (int d = 0; d < p.n_peer; ++d) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.peer_out[d]) + eoff) = q;
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
+        const int col = col_half * COLS_PER_WARP + c0;
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, r);
+        if (pix < HWo) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = nt * BN + col + j;
+            const float bv = bias ? to_acc(bias[co]) : 0.f;
+            const T v = from_acc<T, float>(__uint_as_float(r[j]) + bv);
+            const int64_t idx = ((int64_t)b * p.c_out + co) * HWo + pix;
+            out[idx] = v;
+            for (int d = 0; d < p.n_peer; ++d) reinterpret_cast<T*>(p.peer_out[d])[idx] = v;     // fused all-gather: peer slots
+          }
         }
       }
     }

@@ -222,23 +222,26 @@ def sharded_batched_nms_padded(problems: Sequence[tuple], iou_threshold: float, 
 
 # ---- all-gather fused into the producing kernel (peer stores over NVLink / NVSwitch) -------------------------------------
 class PeerGather:
-    """Gathered output buffer ``[world, *shard_shape]`` in symmetric (peer-mapped) device memory.
+    """Gathered output buffers ``[2, world, *shard_shape]`` in symmetric (peer-mapped) device memory.
 
     With it the all-gather that follows a sharded op is not a collective call at all: the op's kernel stores every
     finished output element to its own slot in ALL ranks' buffers (``dst_ptrs``: the local slot first, then the same
     slot of each peer, mapped through ``torch.distributed._symmetric_memory``), so the exchange travels over NVLink
     while the kernel is still streaming its input from HBM - for resize the output is 0.6 % of the input bytes.
-    ``barrier()`` is a stream-ordered device-side barrier over the ranks (no host sync): one before a step (nobody still
-    reads the previous contents) and one after it (every peer's stores have landed).
+    ``barrier()`` is a stream-ordered device-side barrier over the ranks (no host sync), issued ONCE per step, after the
+    kernel: every peer's stores have landed.  Steps alternate between the two buffers, so the rewrite of a buffer two
+    steps later is already ordered behind every rank's reads of it (each rank passes the barrier of the step in between
+    only after all ranks reached it, i.e. after their stream-ordered consumers of the older buffer).
 
     ``PeerGather.create`` returns None where peer mapping is not available (CPU / gloo, one rank, driver without
     fabric or fd handle export); callers then use the NCCL exchange (`sharded_apply_overlapped`)."""
 
     def __init__(self, buf: torch.Tensor, hdl, rank: int, world: int):
-        self.buf, self.hdl, self.rank, self.world = buf, hdl, rank, world
-        shard_bytes = buf[0].numel() * buf.element_size()
+        self.buf, self.hdl, self.rank, self.world = buf, hdl, rank, world          # buf: [2, world, *shard]
+        shard_bytes = buf[0, 0].numel() * buf.element_size()
+        half = world * shard_bytes
         order = [rank] + [r for r in range(world) if r != rank]
-        self.dst_ptrs = [int(hdl.buffer_ptrs[r]) + rank * shard_bytes for r in order]
+        self._dst = [[int(hdl.buffer_ptrs[r]) + k * half + rank * shard_bytes for r in order] for k in range(2)]
         # NVSwitch multicast address of this rank's slot (0 when the box / allocation has no multicast object): ONE store to
         # it is replicated by the switch into every rank's buffer (multimem.st), instead of world - 1 peer stores
         mc = 0
@@ -246,7 +249,8 @@ class PeerGather:
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
         except Exception:                            # noqa: BLE001
             mc = 0
-        self.mc_ptr = mc + rank * shard_bytes if mc else 0
+        self._mc = [mc + k * half + rank * shard_bytes if mc else 0 for k in range(2)]
+        self.cur = 1
 
     @classmethod
     def create(cls, shard_shape: Sequence[int], dtype: torch.dtype, device, group=None) -> Optional["PeerGather"]:
@@ -256,7 +260,7 @@ class PeerGather:
         try:
             import torch.distributed._symmetric_memory as symm
 
-            buf = symm.empty((world,) + tuple(shard_shape), dtype=dtype, device=device)
+            buf = symm.empty((2, world) + tuple(shard_shape), dtype=dtype, device=device)
             hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
             if len(hdl.buffer_ptrs) != world:
                 return None
@@ -267,12 +271,28 @@ class PeerGather:
             warnings.warn(f"vision_b200.sharded.PeerGather: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL")
             return None
 
+    @property
+    def shard_shape(self):
+        return tuple(self.buf.shape[2:])
+
+    def advance(self) -> None:
+        """Switch to the other buffer (call once per step, before the op)."""
+        self.cur ^= 1
+
+    @property
+    def dst_ptrs(self):
+        return self._dst[self.cur]
+
+    @property
+    def mc_ptr(self) -> int:
+        return self._mc[self.cur]
+
     def barrier(self) -> None:
         self.hdl.barrier(channel=0)
 
     def gathered(self) -> torch.Tensor:
-        """Rank-major ``[world * n, ...]`` view of the buffer."""
-        b = self.buf
+        """Rank-major ``[world * n, ...]`` view of the current buffer."""
+        b = self.buf[self.cur]
         return b.reshape((b.shape[0] * b.shape[1],) + tuple(b.shape[2:]))
 
 
@@ -290,10 +310,10 @@ def resize_gather(local: torch.Tensor, size, peer: Optional[PeerGather], interpo
                                         local, chunks=4, group=group)
     n, c, ih, iw = local.shape
     oh, ow = transforms.compute_resized_output_size((ih, iw), size=size)
-    assert tuple(peer.buf.shape) == (world, n, c, oh, ow) and peer.buf.dtype == local.dtype, "PeerGather buffer does not match the output shard"
+    assert peer.shard_shape == (n, c, oh, ow) and peer.buf.dtype == local.dtype, "PeerGather buffer does not match the output shard"
     _lib.load_ops()
     mode = transforms._MODE_CODE[transforms._mode_value(interpolation)]
-    peer.barrier()                                   # every rank is done reading the previous step's result
+    peer.advance()
     torch.ops.vision_b200.resize_gather(local, peer.dst_ptrs, oh, ow, mode, bool(antialias))
     peer.barrier()                                   # every rank's stores have landed everywhere
     return peer.gathered()
@@ -313,10 +333,10 @@ def roi_align_gather(input: torch.Tensor, rois: torch.Tensor, peer: Optional[Pee
     if peer is None or world == 1:
         return all_gather_equal(_ops.roi_align(input, rois, (ph, pw), spatial_scale, sampling_ratio, aligned), group=group)
     k, c = rois.shape[0], input.shape[1]
-    assert tuple(peer.buf.shape) == (world, k, c, ph, pw) and peer.buf.dtype == input.dtype, "PeerGather buffer does not match the output shard"
+    assert peer.shard_shape == (k, c, ph, pw) and peer.buf.dtype == input.dtype, "PeerGather buffer does not match the output shard"
     _lib.load_ops()
+    peer.advance()
     mc = peer.mc_ptr if (multicast and input.dtype == torch.float32) else 0
-    peer.barrier()
     torch.ops.vision_b200.roi_align_gather(input, rois, peer.dst_ptrs, mc, float(spatial_scale), ph, pw, int(sampling_ratio), bool(aligned))
     peer.barrier()
     return peer.gathered()
@@ -342,10 +362,10 @@ def deform_conv2d_gather(input: torch.Tensor, offset: torch.Tensor, weight: torc
     kh, kw = weight.shape[-2:]
     n_offset_grps = offset.shape[1] // (2 * kh * kw)
     n_weight_grps = input.shape[1] // weight.shape[1]
-    assert peer.buf.shape[0] == world and peer.buf.shape[1] == input.shape[0] and peer.buf.shape[2] == weight.shape[0] and \
-        tuple(peer.buf.shape[3:]) == tuple(offset.shape[2:]) and peer.buf.dtype == input.dtype, "PeerGather buffer does not match the output shard"
+    assert peer.shard_shape == (input.shape[0], weight.shape[0]) + tuple(offset.shape[2:]) and peer.buf.dtype == input.dtype, \
+        "PeerGather buffer does not match the output shard"
     _lib.load_ops()
-    peer.barrier()
+    peer.advance()
     torch.ops.vision_b200.deform_conv2d_gather(input, weight, offset, mask, bias, peer.dst_ptrs, sh, sw, ph, pw, dh, dw, n_weight_grps,
                                                n_offset_grps, use_mask)
     peer.barrier()
