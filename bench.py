@@ -508,7 +508,7 @@ def block_cfg5(ctx: Ctx, vb, tv, sharded) -> dict:
                                      "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2,
                                      "identical_to_nccl_gather": same,
                                      "note": "all-gather fused into the resize kernel: each finished pixel is stored to every rank's gathered buffer "
-                                             "(torch symmetric memory, NVLink peer stores: whole 448-byte rows written by one warp), one device-side barrier per step "
+                                             "(torch symmetric memory, NVLink peer stores), one device-side barrier per step "
                                              "(double-buffered); no NCCL call",
                                      "nccl_overlapped": nccl}
             del want, got

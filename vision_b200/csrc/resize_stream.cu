@@ -37,9 +37,6 @@ struct StreamParams {
   // peer's gathered buffer (peer-mapped device memory: the stores travel over NVLink while the input streams from HBM)
   void* dst[kMaxResizeDst];
   int ndst;
-  // ndst > 1 and 16-byte aligned output rows: finished rows are assembled in shared memory and written by ONE warp with
-  // 16-byte vector stores (whole rows instead of a 31-pixel run per warp: the peer stores travel as full NVLink packets)
-  int stage_rows;
 };
 
 __device__ __forceinline__ float centre(float scale, int m) { return scale * ((float)m + 0.5f); }
@@ -142,8 +139,6 @@ resize_aa_stream_kernel(const T* __restrict__ in, StreamParams p, int n_cwarps) 
   float* rowA = reinterpret_cast<float*>(yendy + p.out_h);
   float* rowB = rowA + p.band_cap;
   int* rowK = reinterpret_cast<int*>(rowB + p.band_cap);
-  // two staged output rows (only used with p.stage_rows), 16-byte aligned
-  unsigned char* ostage = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rowK + p.band_cap) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x;
@@ -231,21 +226,6 @@ resize_aa_stream_kernel(const T* __restrict__ in, StreamParams p, int n_cwarps) 
     const int64_t o = doff + (int64_t)row * p.out_w;
     for (int d = 0; d < p.ndst; ++d) reinterpret_cast<T*>(p.dst[d])[o] = q;
   };
-  // staged variant (CTA-uniform calls only): every consumer warp drops its pixels of output row `row` into the row's
-  // shared-memory slot, the consumer warps meet at a named barrier, and warp (row mod n) writes the row to every destination
-  const uint32_t orow_bytes = (uint32_t)p.out_w * sizeof(T);
-  auto put_row = [&](int row, float v) {
-    unsigned char* slot = ostage + (size_t)(row & 1) * ((orow_bytes + 15) & ~15u);
-    if (writer) reinterpret_cast<T*>(slot)[i] = store_px<T>(v);
-    asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
-    if (warp == row % n_cwarps) {
-      const int64_t ob = (plane * (int64_t)p.out_h + row) * orow_bytes;
-      for (uint32_t b = lane * 16u; b < orow_bytes; b += 32u * 16u) {
-        const uint4 q = *reinterpret_cast<const uint4*>(slot + b);
-        for (int d = 0; d < p.ndst; ++d) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.dst[d]) + ob + b) = q;
-      }
-    }
-  };
 
   float acc_lo = 0.f, acc_hi = 0.f;
   int k_cur = oy0;
@@ -272,10 +252,7 @@ resize_aa_stream_kernel(const T* __restrict__ in, StreamParams p, int n_cwarps) 
     const float h = A + __shfl_down_sync(0xffffffffu, B, 1);
     const int k = rowK[rl];
     if (k != k_cur) {                              // CTA-uniform: output row k_cur - 1 is complete
-      if (k_cur - 1 >= oy0) {
-        if (p.stage_rows) put_row(k_cur - 1, acc_lo);
-        else if (writer) put(k_cur - 1, acc_lo);
-      }
+      if (writer && k_cur - 1 >= oy0) put(k_cur - 1, acc_lo);
       acc_lo = acc_hi; acc_hi = 0.f; k_cur = k;
     }
     acc_hi = fmaf(rowA[rl], h, acc_hi);
@@ -283,14 +260,8 @@ resize_aa_stream_kernel(const T* __restrict__ in, StreamParams p, int n_cwarps) 
   }
   // rows of the band are exhausted: acc_lo holds output row k_cur - 1; a band that ended exactly on an
   // interval boundary (k_cur == oy1 - 1 cannot happen: the band includes interval oy1) -> k_cur == oy1
-  if (k_cur - 1 >= oy0 && k_cur - 1 < oy1) {
-    if (p.stage_rows) put_row(k_cur - 1, acc_lo);
-    else if (writer) put(k_cur - 1, acc_lo);
-  }
-  if (k_cur < oy1 && k_cur >= oy0) {
-    if (p.stage_rows) put_row(k_cur, acc_hi);
-    else if (writer) put(k_cur, acc_hi);
-  }
+  if (writer && k_cur - 1 >= oy0 && k_cur - 1 < oy1) put(k_cur - 1, acc_lo);
+  if (writer && k_cur < oy1 && k_cur >= oy0) put(k_cur, acc_hi);
 }
 
 template <typename T, int NP, int NW>
@@ -315,12 +286,7 @@ int launch_stream(const void* in, int64_t planes, const StreamParams& p0, cudaSt
     band_rows = (int)((p.rows_out_per_cta + 2) * p.scale_h) + 4;
   }
   p.band_cap = (band_rows + 31) & ~31;
-  p.stage_rows = 0;
-  if (p.ndst > 1 && ((size_t)p.out_w * sizeof(T)) % 16 == 0) {
-    p.stage_rows = 1;
-    for (int d = 0; d < p.ndst; ++d) if (((uintptr_t)p.dst[d] % 16) != 0) p.stage_rows = 0;
-  }
-  const size_t fixed = (size_t)(p.out_w + p.out_h) * 16 + (size_t)p.band_cap * 12 + 256 + 2 * (((size_t)p.out_w * sizeof(T) + 15) & ~(size_t)15) + 16;
+  const size_t fixed = (size_t)(p.out_w + p.out_h) * 16 + (size_t)p.band_cap * 12 + 256;
   const int ctas_per_sm = (NW <= 8 && NP <= 12) ? 3 : 2;
   const size_t budget = ((size_t)max_smem_optin() - 3072) / ctas_per_sm - 1024;   // smem per CTA (1 KB reserved each)
   if (budget < fixed + 3 * (size_t)p.row_pitch) return 0;
