@@ -18,6 +18,8 @@
 //   * epilogue: tcgen05.ld 32 lanes x 16 columns, + bias, round, coalesced NCHW stores.
 // Pipeline: 3 stages x (A 16 KB + B BN*128 B), full(A)/full(B)/empty mbarriers per stage.
 #include "async_copy.cuh"
+#include <type_traits>
+
 #include "common.cuh"
 #include "dcn_params.h"
 
@@ -1050,8 +1052,10 @@ int launch_tc(const void* input, const void* weight, const void* offset, const v
               const DcnParams& p_in, void* workspace, size_t workspace_bytes, cudaStream_t st, const DcnHints& hints) {
   DcnParams p = p_in;
   {
-    const char* env = env_override(ENV_DCN_BLEND);      // VB200_DCN_BLEND=16: blend the corners in the storage format
-    p.blend16 = env && env[0] == '1' && env[1] == '6';
+    // corner blend: fp32 FFMA2, or packed in the storage format (HFMA2: -5 % time).  Default: packed for fp16 (worst error 0.13 of
+    // the 1e-2 bound on cfg4), fp32 for bf16 (the packed bf16 blend reaches 1.06 of the bound); VB200_DCN_BLEND=16|32 overrides.
+    const char* env = env_override(ENV_DCN_BLEND);
+    p.blend16 = env ? (env[0] == '1' && env[1] == '6') : (sizeof(T) == 2 && std::is_same<T, __half>::value);
   }
   const int KK = p.kh * p.kw, HWi = p.in_h * p.in_w, HWo = p.out_h * p.out_w;
   const size_t nhwc_bytes = hints.input_is_nhwc ? 0 : align256((size_t)p.batch * HWi * p.c_in * sizeof(T));
