@@ -763,3 +763,18 @@ def test_deform_conv2d_gather_writes_every_destination(vb):
         for t in bufs:
             assert torch.equal(t[64:64 + n].view(want.shape), want)
             assert bool((t[:64] == 5).all()) and bool((t[64 + n:] == 5).all())
+
+
+@pytest.mark.gpu
+def test_gather_helpers_without_a_process_group(vb):
+    """sharded.resize_gather / roi_align_gather / deform_conv2d_gather with no peer buffer (one process, no group): the plain op."""
+    from vision_b200 import sharded, workloads
+
+    x = torch.rand(3, 3, 120, 200, device=DEV).half()
+    got = sharded.resize_gather(x, [30, 40], None)
+    assert torch.equal(got if isinstance(got, torch.Tensor) else got.materialize(), vb.transforms.resize_image(x, [30, 40]))
+    f, rois, kw = workloads.cfg2_roi_align(seed=4, k=50, batch=1, channels=8, height=40, width=56)
+    f, rois = f.to(DEV), rois.to(DEV)
+    assert torch.equal(sharded.roi_align_gather(f, rois, None, **kw), vb.ops.roi_align(f, rois, **kw))
+    xi, off, w, b, m = [t.to(DEV) for t in workloads.cfg4_deform_conv2d(seed=5, batch=1, c_in=8, c_out=8, hw=10, dtype=torch.float32)]
+    assert torch.equal(sharded.deform_conv2d_gather(xi, off, w, b, None, 1, 1, 1, m), vb.ops.deform_conv2d(xi, off, w, b, 1, 1, 1, m))
