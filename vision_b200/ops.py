@@ -7,8 +7,6 @@ CPU kernels keep serving CPU tensors through ``torchvision.ops`` itself, untouch
 """
 from __future__ import annotations
 
-from typing import Union
-
 import torch
 from torch import Tensor
 from torch.nn.modules.utils import _pair
@@ -53,25 +51,8 @@ def box_iou_rotated(boxes1: Tensor, boxes2: Tensor) -> Tensor:
 
 
 # ---- RoI ops ------------------------------------------------------------------
-def convert_boxes_to_roi_format(boxes: list[Tensor]) -> Tensor:
-    """torchvision/ops/_utils.py:18-25"""
-    concat_boxes = boxes[0] if len(boxes) == 1 else torch.cat(list(boxes), dim=0)
-    ids = [torch.full_like(b[:, :1], i) for i, b in enumerate(boxes)]
-    ids = ids[0] if len(ids) == 1 else torch.cat(ids, dim=0)
-    return torch.cat([ids, concat_boxes], dim=1)
-
-
-def check_roi_boxes_shape(boxes: Union[Tensor, list[Tensor]]) -> None:
-    """torchvision/ops/_utils.py:28-38 (same AssertionError texts)"""
-    if isinstance(boxes, (list, tuple)):
-        for _tensor in boxes:
-            torch._assert(
-                _tensor.size(1) == 4, "The shape of the tensor in the boxes list is not correct as List[Tensor[L, 4]]"
-            )
-    elif isinstance(boxes, torch.Tensor):
-        torch._assert(boxes.size(1) == 5, "The boxes tensor shape is not correct as Tensor[K, 5]")
-    else:
-        torch._assert(False, "boxes is expected to be a Tensor[L, 5] or a List[Tensor[K, 4]]")
+# box-list handling and its assertion texts are the reference's own helpers (torchvision/ops/_utils.py:18-38), not re-typed
+from torchvision.ops._utils import check_roi_boxes_shape, convert_boxes_to_roi_format  # noqa: E402,F401
 
 
 def _rois(boxes) -> Tensor:

@@ -56,36 +56,13 @@ def _mode_value(interpolation) -> str:
 
 
 def compute_resized_output_size(canvas_size: Sequence[int], size, max_size: Optional[int] = None) -> list[int]:
-    """_compute_resized_output_size (_geometry.py:236-246 -> transforms/functional.py:353-384)."""
+    """The reference's own rule, not a restatement: _compute_resized_output_size (_geometry.py:236-246 ->
+    transforms/functional.py:353-384), incl. its ValueError texts."""
+    from torchvision.transforms.v2.functional._geometry import _compute_resized_output_size
+
     if isinstance(size, int):
         size = [size]
-    elif max_size is not None and size is not None and len(size) != 1:
-        raise ValueError(
-            "max_size should only be passed if size is None or specifies the length of the smaller edge, "
-            "i.e. size should be an int or a sequence of length 1 in torchscript mode."
-        )
-    h, w = canvas_size
-    short, long = (w, h) if w <= h else (h, w)
-    if size is None:
-        if not isinstance(max_size, int):
-            raise ValueError(f"max_size must be an integer when size is None, but got {max_size} instead.")
-        new_short, new_long = int(max_size * short / long), max_size
-        new_w, new_h = (new_short, new_long) if w <= h else (new_long, new_short)
-    elif len(size) == 1:
-        requested_new_short = size[0]
-        new_short, new_long = requested_new_short, int(requested_new_short * long / short)
-        if max_size is not None:
-            if max_size <= requested_new_short:
-                raise ValueError(
-                    f"max_size = {max_size} must be strictly greater than the requested "
-                    f"size for the smaller edge size = {size}"
-                )
-            if new_long > max_size:
-                new_short, new_long = int(max_size * new_short / new_long), max_size
-        new_w, new_h = (new_short, new_long) if w <= h else (new_long, new_short)
-    else:
-        new_w, new_h = size[1], size[0]
-    return [new_h, new_w]
+    return list(_compute_resized_output_size(tuple(canvas_size), size=None if size is None else list(size), max_size=max_size))
 
 
 def supports(image: torch.Tensor, interpolation) -> bool:
