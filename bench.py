@@ -428,13 +428,17 @@ def block_cfg4(ctx: Ctx, vb, tv, sharded) -> dict:
             same = bool(torch.equal(got, want))
             fms = ctx.device_ms(lambda: sharded.deform_conv2d_gather(x, off, w, b, peer, 1, 1, 1, m), steps)
             ingress = (ctx.world - 1) * x.numel() * 2
-            out["with_allgather"] = {"ms_per_step": fms, "value": ctx.world * CFG4_FLOPS / (fms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                     "bytes_gathered_per_rank": ctx.world * x.numel() * 2, "identical_to_nccl_gather": same,
-                                     "nvlink_ingress_floor_ms": ingress / 900e9 * 1e3,
-                                     "note": "all-gather fused into the tcgen05 kernel's epilogue: each output element is stored to every rank's gathered "
-                                             "buffer (torch symmetric memory, NVLink peer stores of 256-byte runs), one device-side barrier per step (double-buffered); no NCCL "
-                                             "call.  nvlink_ingress_floor_ms = (world-1) x 134 MB received per rank per step at 900 GB/s",
-                                     "nccl_overlapped": nccl}
+            if same:                          # a fused result that differs from the NCCL gather would be reported, never adopted
+                out["with_allgather"] = {
+                    "ms_per_step": fms, "value": ctx.world * CFG4_FLOPS / (fms / 1e3) / 1e12, "unit": "TFLOP/s",
+                    "bytes_gathered_per_rank": ctx.world * x.numel() * 2, "identical_to_nccl_gather": True,
+                    "nvlink_ingress_floor_ms": ingress / 900e9 * 1e3,
+                    "note": "all-gather fused into the tcgen05 kernel's epilogue: each output element is stored to every rank's gathered buffer "
+                            "(torch symmetric memory, NVLink peer stores of 256-byte runs), one device-side barrier per step (double-buffered); "
+                            "no NCCL call.  nvlink_ingress_floor_ms = (world-1) x 134 MB received per rank per step at 900 GB/s",
+                    "nccl_overlapped": nccl}
+            else:
+                nccl["fused_peer_stores"] = {"ms_per_step": fms, "identical_to_nccl_gather": False}
             del want, got
         else:
             out["with_allgather"]["peer_stores"] = "unavailable on this box (symmetric memory rendezvous failed); NCCL exchange reported"
@@ -504,13 +508,15 @@ def block_cfg5(ctx: Ctx, vb, tv, sharded) -> dict:
             got = sharded.resize_gather(x, [224, 224], peer)
             same = bool(torch.equal(got, want))
             fms = ctx.device_ms(lambda: sharded.resize_gather(x, [224, 224], peer), steps)
-            out["with_allgather"] = {"ms_per_step": fms, "value": ctx.world * CFG5_BATCH / (fms / 1e3), "unit": "images/s",
-                                     "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2,
-                                     "identical_to_nccl_gather": same,
-                                     "note": "all-gather fused into the resize kernel: each finished pixel is stored to every rank's gathered buffer "
-                                             "(torch symmetric memory, NVLink peer stores), one device-side barrier per step "
-                                             "(double-buffered); no NCCL call",
-                                     "nccl_overlapped": nccl}
+            if same:
+                out["with_allgather"] = {
+                    "ms_per_step": fms, "value": ctx.world * CFG5_BATCH / (fms / 1e3), "unit": "images/s",
+                    "bytes_gathered_per_rank": ctx.world * CFG5_BATCH * 3 * 224 * 224 * 2, "identical_to_nccl_gather": True,
+                    "note": "all-gather fused into the resize kernel: each finished pixel is stored to every rank's gathered buffer (torch symmetric "
+                            "memory, NVLink peer stores), one device-side barrier per step (double-buffered); no NCCL call",
+                    "nccl_overlapped": nccl}
+            else:
+                nccl["fused_peer_stores"] = {"ms_per_step": fms, "identical_to_nccl_gather": False}
             del want, got
         else:
             out["with_allgather"]["peer_stores"] = "unavailable on this box (symmetric memory rendezvous failed); NCCL exchange reported"

@@ -11,6 +11,7 @@ BUILD = os.path.join(ROOT, "vision_b200", "build")
 TARGETS = [  # (object, regex on the demangled function name, output tag)
     ("roi_ops.o", r"roi_align_line_kernel<7, 2, false>", "roi_align_line_kernel"),
     ("roi_ops.o", r"roi_align_line_kernel<7, 2, true>", "roi_align_line_kernel_multilevel"),
+    ("roi_ops.o", r"roi_align_band_kernel<7, 2>", "roi_align_band_kernel"),
     ("roi_ops.o", r"roi_pool_plane_kernel<float, true>", "roi_pool_plane_kernel"),
     ("resize_stream.o", r"resize_aa_stream_kernel<__half, 10, 8>", "resize_aa_stream_kernel_f16"),
     ("deform_conv2d_tc.o", r"deform_conv2d_tc_kernel<__nv_bfloat16, 512, 4, 32>", "deform_conv2d_tc_kernel_bf16_bn512"),
@@ -63,7 +64,7 @@ def main():
             for op, n in ops.most_common():
                 f.write(f"#   {op:12s} {n}\n")
             f.write("\n".join(ins) + "\n")
-        key = {k: ops[k] for k in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "FFMA2", "LDGSTS", "ATOMS", "LDS", "STS", "SHFL", "VOTE") if ops[k]}
+        key = {k: ops[k] for k in ("UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "FFMA2", "HFMA2", "LDGSTS", "ATOMS", "LDS", "STS", "SHFL", "VOTE", "CREDUX", "REDG", "MULTIMEM") if ops[k]}
         print(f"{tag}: {len(ins)} instructions {key}")
 
 
