@@ -201,3 +201,32 @@ def test_install_rebinds_and_restores_python_entry_points():
     after = (torchvision.ops.boxes.batched_nms, poolers._multiscale_roi_align, roi_heads.RoIHeads.postprocess_detections,
              rpn.RegionProposalNetwork.filter_proposals, _presets.ImageClassification.forward)
     assert all(a is b for a, b in zip(before, after))
+
+
+def test_peer_gather_slot_arithmetic():
+    """PeerGather hands the kernels this rank's slot in every rank's buffer: the local copy first, then the peers in rank order, in
+    the buffer the step uses (two alternating buffers); checked with a stand-in handle (no GPU, no process group)."""
+    import torch
+
+    class Handle:
+        buffer_ptrs = [0x1000_0000, 0x2000_0000, 0x3000_0000]
+        multicast_ptr = 0x9000_0000
+
+        def barrier(self, channel=0):
+            self.calls = getattr(self, "calls", 0) + 1
+
+    world, rank, shard = 3, 1, (4, 5)
+    buf = torch.zeros((2, world) + shard, dtype=torch.float16)
+    pg = sharded.PeerGather(buf, Handle(), rank, world)
+    shard_bytes, half = 4 * 5 * 2, 3 * 4 * 5 * 2
+    assert pg.shard_shape == shard
+    for step in range(4):
+        pg.advance()
+        k = step % 2                      # the first step uses buffer 0
+        assert pg.cur == k
+        own = rank * shard_bytes + k * half
+        assert pg.dst_ptrs == [0x2000_0000 + own, 0x1000_0000 + own, 0x3000_0000 + own]
+        assert pg.mc_ptr == 0x9000_0000 + own
+        assert pg.gathered().shape == (world * 4, 5) and pg.gathered().data_ptr() == buf[k].data_ptr()
+    pg.barrier()
+    assert pg.hdl.calls == 1
