@@ -1432,7 +1432,8 @@ static int roi_align_forward_impl(const void* input, const void* rois, void* out
     const size_t geo_pad = roi_align_geo_bytes(num_rois, pooled_h, pooled_w, sampling_ratio);
     int path = roi_align_path(dtype, input, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio);
     const bool want_peers = peers.n > 0 || peers.mc != nullptr;
-    if (want_peers && path == 3) path = 2;       // the band kernel's RED protocol is local-only; same applicability as the line kernel
+    if (want_peers && path == 3)                 // the band kernel's RED protocol is local-only: the line kernel where it fits, else generic + copies
+      path = line_plane_bytes(height, line_pitch(width)) + kLineStageBytes + 1024 <= (size_t)max_smem_optin() ? 2 : 0;
     if (path && (workspace == nullptr || ((uintptr_t)workspace % 16) != 0 ||
                  workspace_bytes < roi_align_ws_bytes(path, batch, channels, height, width, num_rois, pooled_h, pooled_w, sampling_ratio)))
       path = 0;
